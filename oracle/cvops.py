@@ -1,0 +1,434 @@
+"""NumPy restatements of the OpenCV operators on the lane_tracker hot path.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+The reference (pure Python) delegates all arithmetic to ``cv2``, an un-vendored
+and un-pinned third-party dependency (README.md:41-47 of the reference); parity
+is defined against the installed build, OpenCV 4.13.0.  Each function below
+restates the *published fixed-point algorithm* of one operator and cites the
+reference call site it stands in for.  ``tests/test_oracle_cvops.py`` pins
+every one of them bit-for-bit against cv2 itself.
+
+All images are ``uint8``; ``H x W`` planes or ``H x W x 3`` RGB.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+INT_MIN = -(2 ** 31)
+INT_MAX = 2 ** 31 - 1
+
+# --------------------------------------------------------------------------
+# Remap: fixed-point coordinate maps + Q5/Q15 bilinear sampling
+# --------------------------------------------------------------------------
+
+
+def undistort_map_q5(K, D, width, height):
+    """Q5 fixed-point source coordinates of ``cv2.undistort(src,K,D,None,K)``.
+
+    Stands in for lane_tracker.py:832.  Model: k1,k2,p1,p2,k3 only (the shipped
+    ``cam_calib.p`` has 5 coefficients).  Returns int32 arrays ``U, V`` of shape
+    ``[height, width]`` with ``U = rint(32*u)``.
+    """
+    K = np.asarray(K, dtype=np.float64).reshape(3, 3)
+    D = np.asarray(D, dtype=np.float64).ravel()
+    k1, k2, p1, p2 = D[0], D[1], D[2], D[3]
+    k3 = D[4] if D.size > 4 else 0.0
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    iR = np.linalg.inv(K)
+    i = np.arange(height, dtype=np.float64)[:, None]
+    j = np.arange(width, dtype=np.float64)[None, :]
+    _x = (i * iR[0, 1] + iR[0, 2]) + j * iR[0, 0]
+    _y = (i * iR[1, 1] + iR[1, 2]) + j * iR[1, 0]
+    _w = (i * iR[2, 1] + iR[2, 2]) + j * iR[2, 0]
+    x = _x / _w
+    y = _y / _w
+    x2 = x * x
+    y2 = y * y
+    r2 = x2 + y2
+    _2xy = 2.0 * x * y
+    kr = 1.0 + ((k3 * r2 + k2) * r2 + k1) * r2
+    xd = x * kr + p1 * _2xy + p2 * (r2 + 2.0 * x2)
+    yd = y * kr + p1 * (r2 + 2.0 * y2) + p2 * _2xy
+    u = fx * xd + cx
+    v = fy * yd + cy
+    U = np.rint(u * 32.0)
+    V = np.rint(v * 32.0)
+    return (np.clip(U, INT_MIN, INT_MAX).astype(np.int64).astype(np.int32),
+            np.clip(V, INT_MIN, INT_MAX).astype(np.int64).astype(np.int32))
+
+
+def perspective_map_q5(M, dst_width, dst_height):
+    """Q5 source coordinates of ``cv2.warpPerspective(src, M, (dw,dh))``.
+
+    Stands in for lane_tracker.py:834 (M) and :650 (Minv).  OpenCV inverts the
+    3x3 matrix (no WARP_INVERSE_MAP), walks the destination in 64-column blocks
+    and evaluates the homography in fp64 from the block origin.
+    """
+    m = np.linalg.inv(np.asarray(M, dtype=np.float64).reshape(3, 3)).ravel()
+    x = np.arange(dst_width, dtype=np.int64)[None, :]
+    y = np.arange(dst_height, dtype=np.float64)[:, None]
+    xb = ((x // 64) * 64).astype(np.float64)
+    x1 = (x % 64).astype(np.float64)
+    X0 = (m[0] * xb + m[1] * y) + m[2]
+    Y0 = (m[3] * xb + m[4] * y) + m[5]
+    W0 = (m[6] * xb + m[7] * y) + m[8]
+    W = W0 + m[6] * x1
+    with np.errstate(divide="ignore", invalid="ignore"):
+        Wi = np.where(W != 0.0, 32.0 / W, 0.0)
+    fX = np.clip((X0 + m[0] * x1) * Wi, INT_MIN, INT_MAX)
+    fY = np.clip((Y0 + m[3] * x1) * Wi, INT_MIN, INT_MAX)
+    X = np.rint(fX).astype(np.int64)
+    Y = np.rint(fY).astype(np.int64)
+    return X.astype(np.int32), Y.astype(np.int32)
+
+
+def bilinear_q5(src, X, Y):
+    """OpenCV's INTER_LINEAR remap with BORDER_CONSTANT(0) from Q5 coordinates.
+
+    ``sx = X>>5`` (saturated to int16), ``fx = X&31``; the four taps outside
+    the image contribute 0; weights are the Q15 table entries
+    ``32*(32-fx)(32-fy)`` ... which sum to 32768, so
+    ``out = (sum(tap*w) + 512) >> 10`` with the un-scaled 10-bit weights.
+    Works on planes and on HxWxC images (per channel).
+    """
+    src = np.asarray(src)
+    h, w = src.shape[:2]
+    X = X.astype(np.int64)
+    Y = Y.astype(np.int64)
+    sx = np.clip(X >> 5, -32768, 32767)
+    sy = np.clip(Y >> 5, -32768, 32767)
+    fx = X & 31
+    fy = Y & 31
+    s = src.astype(np.int64)
+    if s.ndim == 2:
+        s = s[:, :, None]
+
+    def tap(yy, xx):
+        ok = (yy >= 0) & (yy < h) & (xx >= 0) & (xx < w)
+        v = s[np.clip(yy, 0, h - 1), np.clip(xx, 0, w - 1)]
+        return v * ok[..., None]
+
+    w00 = ((32 - fx) * (32 - fy))[..., None]
+    w01 = (fx * (32 - fy))[..., None]
+    w10 = ((32 - fx) * fy)[..., None]
+    w11 = (fx * fy)[..., None]
+    acc = (tap(sy, sx) * w00 + tap(sy, sx + 1) * w01 +
+           tap(sy + 1, sx) * w10 + tap(sy + 1, sx + 1) * w11)
+    out = ((acc + 512) >> 10).astype(np.uint8)
+    if src.ndim == 2:
+        out = out[:, :, 0]
+    return out
+
+
+def undistort(src, K, D):
+    """lane_tracker.py:832."""
+    h, w = src.shape[:2]
+    U, V = undistort_map_q5(K, D, w, h)
+    return bilinear_q5(src, U, V)
+
+
+def warp_perspective(src, M, dsize):
+    """lane_tracker.py:834 / :650; ``dsize = (width, height)``."""
+    X, Y = perspective_map_q5(M, dsize[0], dsize[1])
+    return bilinear_q5(src, X, Y)
+
+
+# --------------------------------------------------------------------------
+# RGB -> CIE LAB, b plane (8-bit path of cv2.cvtColor(COLOR_RGB2LAB))
+# --------------------------------------------------------------------------
+
+_LAB_TABLES = None
+
+
+def lab_tables():
+    """The two integer LUTs of OpenCV's 8-bit RGB2Lab, built in float32.
+
+    ``g[256]``  : sRGB gamma, scaled to 2040  (uint16)
+    ``cb[3072]``: Lab cube-root curve, scaled to 32768 (uint16)
+    """
+    global _LAB_TABLES
+    if _LAB_TABLES is None:
+        f32 = np.float32
+        i = np.arange(256, dtype=f32)
+        x = i / f32(255.0)
+        lin = np.where(x <= f32(0.04045), x / f32(12.92),
+                       np.power((x + f32(0.055)) / f32(1.055), f32(2.4), dtype=f32))
+        g = np.rint(f32(2040.0) * lin.astype(f32)).astype(np.uint16)
+        t = np.arange(3072, dtype=f32) / f32(2040.0)
+        f = np.where(t < f32(0.008856),
+                     t * f32(7.787) + f32(16.0 / 116.0),
+                     np.cbrt(t, dtype=f32))
+        cb = np.rint(f32(32768.0) * f.astype(f32)).astype(np.uint16)
+        _LAB_TABLES = (g, cb)
+    return _LAB_TABLES
+
+
+def lab_b_plane(rgb):
+    """b channel of ``cv2.cvtColor(rgb, COLOR_RGB2LAB)`` (lane_tracker.py:208)."""
+    g, cb = lab_tables()
+    R = g[rgb[..., 0]].astype(np.int64)
+    G = g[rgb[..., 1]].astype(np.int64)
+    B = g[rgb[..., 2]].astype(np.int64)
+    fY = cb[(871 * R + 2929 * G + 296 * B + 2048) >> 12].astype(np.int64)
+    fZ = cb[(73 * R + 448 * G + 3575 * B + 2048) >> 12].astype(np.int64)
+    b = (200 * (fY - fZ) + 128 * 32768 + 16384) >> 15
+    return np.clip(b, 0, 255).astype(np.uint8)
+
+
+# --------------------------------------------------------------------------
+# Ellipse morphology (lane_tracker.py:203-211, :238)
+# --------------------------------------------------------------------------
+
+
+def ellipse_half_widths(k):
+    """Row half-widths of ``cv2.getStructuringElement(MORPH_ELLIPSE,(k,k))``."""
+    r = k // 2
+    c = k // 2
+    inv_r2 = 1.0 / (r * r) if r else 0.0
+    hw = []
+    for i in range(k):
+        dy = i - r
+        if abs(dy) <= r:
+            dx = int(np.rint(c * np.sqrt((r * r - dy * dy) * inv_r2)))
+        else:
+            dx = 0
+        hw.append(dx)
+    return hw
+
+
+def _hwin(src, w, op, pad):
+    """min/max over the horizontal window [x-w, x+w], out-of-image ignored."""
+    if w == 0:
+        return src
+    h, W = src.shape
+    p = np.full((h, W + 2 * w), pad, dtype=src.dtype)
+    p[:, w:w + W] = src
+    out = p[:, 0:W].copy()
+    for d in range(1, 2 * w + 1):
+        op(out, p[:, d:d + W], out=out)
+    return out
+
+
+def _morph(src, k, is_erode):
+    hw = ellipse_half_widths(k)
+    r = k // 2
+    op = np.minimum if is_erode else np.maximum
+    pad = 255 if is_erode else 0
+    h, W = src.shape
+    cache = {}
+    out = np.full_like(src, pad)
+    for i, w in enumerate(hw):
+        dy = i - r
+        if w not in cache:
+            cache[w] = _hwin(src, w, op, pad)
+        Hm = cache[w]
+        lo = max(0, -dy)
+        hi = min(h, h - dy)
+        if lo < hi:
+            op(out[lo:hi], Hm[lo + dy:hi + dy], out=out[lo:hi])
+    return out
+
+
+def erode_ellipse(src, k):
+    return _morph(src, k, True)
+
+
+def dilate_ellipse(src, k):
+    return _morph(src, k, False)
+
+
+def open_ellipse(src, k):
+    """``cv2.morphologyEx(src, MORPH_OPEN, ellipse(k))`` (lane_tracker.py:238)."""
+    return dilate_ellipse(erode_ellipse(src, k), k)
+
+
+def tophat_ellipse(src, k):
+    """``cv2.morphologyEx(src, MORPH_TOPHAT, ellipse(k))`` (lane_tracker.py:210-211)."""
+    return (src.astype(np.int16) - open_ellipse(src, k).astype(np.int16)).clip(0, 255).astype(np.uint8)
+
+
+# --------------------------------------------------------------------------
+# Thresholds
+# --------------------------------------------------------------------------
+
+
+def _dirsum(p, k, axis, sign):
+    """sum of the k neighbours on one side along an axis, zero padded.
+
+    sign=-1: neighbours at offsets -1..-k ("left"/"up"); +1: +1..+k.
+    """
+    n = p.shape[axis]
+    cs = np.cumsum(p, axis=axis, dtype=np.int64)
+    z = np.zeros_like(np.take(cs, [0], axis=axis))
+    cs0 = np.concatenate([z, cs], axis=axis)  # cs0[i] = sum p[0..i-1]
+    idx = np.arange(n)
+    if sign < 0:
+        hi = idx            # exclusive end = i  -> covers i-k .. i-1
+        lo = np.clip(idx - k, 0, n)
+    else:
+        lo = np.clip(idx + 1, 0, n)
+        hi = np.clip(idx + 1 + k, 0, n)
+    return np.take(cs0, hi, axis=axis) - np.take(cs0, lo, axis=axis)
+
+
+def cross_threshold(img, ksize, C):
+    """``bilateral_adaptive_threshold(img, ksize, C, mode='floor')``.
+
+    lane_tracker.py:14-83: four 1-D ``filter2D`` sums (BORDER_CONSTANT 0) of the
+    k neighbours to the left/right/up/down; a pixel passes iff it beats both
+    horizontal sides or both vertical sides: ``k*p - C*k > side sum``.
+    """
+    p = img.astype(np.int64)
+    t = ksize * p - C * ksize
+    L = _dirsum(p, ksize, 1, -1)
+    R = _dirsum(p, ksize, 1, +1)
+    U = _dirsum(p, ksize, 0, -1)
+    Dn = _dirsum(p, ksize, 0, +1)
+    ok = ((L < t) & (R < t)) | ((U < t) & (Dn < t))
+    return np.where(ok, 255, 0).astype(np.uint8)
+
+
+def box_mean_threshold(img, block, c):
+    """``cv2.adaptiveThreshold(img,255,MEAN_C,THRESH_BINARY,block,-c)``.
+
+    lane_tracker.py:217-218.  Box sum with replicated border, mean rounded to
+    nearest (block*block is odd so there are no ties), pass iff p - mean > c.
+    """
+    h, w = img.shape
+    r = block // 2
+    p = np.pad(img.astype(np.int64), r, mode="edge")
+    cs = np.cumsum(np.cumsum(p, axis=0), axis=1)
+    cs = np.pad(cs, ((1, 0), (1, 0)))
+    S = (cs[block:block + h, block:block + w] - cs[0:h, block:block + w]
+         - cs[block:block + h, 0:w] + cs[0:h, 0:w])
+    n = block * block
+    mean = (2 * S + n) // (2 * n)
+    return np.where(img.astype(np.int64) - mean > c, 255, 0).astype(np.uint8)
+
+
+def in_range(img, lo, hi):
+    """``cv2.inRange`` (lane_tracker.py:223)."""
+    return np.where((img >= lo) & (img <= hi), 255, 0).astype(np.uint8)
+
+
+# --------------------------------------------------------------------------
+# Overlay: fillPoly of the lane polygon + blend
+# --------------------------------------------------------------------------
+
+
+def _line_pixels(x0, y0, x1, y1):
+    """8-connected ``cv::LineIterator`` pixel walk between two points.
+
+    ``cv::Line`` constructs the iterator with ``leftToRight=true``: the walk
+    always starts at the end point with the smaller x.
+    """
+    if x1 < x0:
+        x0, y0, x1, y1 = x1, y1, x0, y0
+    dx = x1 - x0
+    dy = y1 - y0
+    sx = 1 if dx >= 0 else -1
+    sy = 1 if dy >= 0 else -1
+    adx, ady = abs(dx), abs(dy)
+    pts = []
+    if adx >= ady:
+        # x is the major axis:  err starts at -adx/2 style (OpenCV: err = dx - 2dy)
+        err = adx - 2 * ady
+        plus, minus = 2 * adx, -2 * ady
+        # OpenCV: err = dx - (dy + dy); plusDelta = dx + dx; minusDelta = -(dy+dy)
+        x, y = x0, y0
+        for _ in range(adx + 1):
+            pts.append((x, y))
+            mask = -1 if err < 0 else 0
+            err += minus + (plus & mask)
+            y += sy if mask else 0
+            x += sx
+    else:
+        err = ady - 2 * adx
+        plus, minus = 2 * ady, -2 * adx
+        x, y = x0, y0
+        for _ in range(ady + 1):
+            pts.append((x, y))
+            mask = -1 if err < 0 else 0
+            err += minus + (plus & mask)
+            x += sx if mask else 0
+            y += sy
+    return pts
+
+
+def lane_polygon_rows(left_x, left_y, right_x, right_y, width, height):
+    """Row spans ``[lo[y], hi[y]]`` covered by the reference's lane polygon.
+
+    Stands in for ``cv2.fillPoly`` at lane_tracker.py:642-647 with the polygon
+    built from the left polyline top->bottom followed by the right polyline
+    bottom->top.  Both polylines have one vertex per row and end on the bottom
+    row (``get_poly_points`` re-stacks onto the bottom rows, :525-526).
+    Returns int arrays lo, hi of length ``height`` (hi < lo == empty row).
+    Coverage is the union of the even-odd scanline fill and the 8-connected
+    polygon outline, both clipped to the canvas.
+    """
+    lo = np.full(height, width, dtype=np.int64)
+    hi = np.full(height, -1, dtype=np.int64)
+
+    def cover(y, a, b):
+        if 0 <= y < height:
+            a2, b2 = max(min(a, b), 0), min(max(a, b), width - 1)
+            if a2 <= b2:
+                lo[y] = min(lo[y], a2)
+                hi[y] = max(hi[y], b2)
+
+    nl, nr = len(left_x), len(right_x)
+    if nl == 0 or nr == 0:
+        return lo, hi
+    verts = [(int(x), int(y)) for x, y in zip(left_x, left_y)]
+    verts += [(int(x), int(y)) for x, y in zip(right_x[::-1], right_y[::-1])]
+    # (iii) outline
+    n = len(verts)
+    for i in range(n):
+        x0, y0 = verts[i]
+        x1, y1 = verts[(i + 1) % n]
+        for (x, y) in _line_pixels(x0, y0, x1, y1):
+            cover(y, x, x)
+    # (i) rows where both polylines have a vertex
+    L = {int(y): int(x) for x, y in zip(left_x, left_y)}
+    R = {int(y): int(x) for x, y in zip(right_x, right_y)}
+    for y in L:
+        if y in R:
+            cover(y, L[y], R[y])
+    # (ii) slanted closing edge between the two top vertices
+    if nl != nr:
+        (xa, ya) = verts[0]          # left top
+        (xb, yb) = verts[-1]         # right top
+        if ya > yb:                  # right polyline is the longer one
+            top, bot, side = (xb, yb), (xa, ya), R
+        else:
+            top, bot, side = (xa, ya), (xb, yb), L
+        x = top[0] << 16
+        num = (bot[0] - top[0]) << 16
+        den = bot[1] - top[1]
+        dx = abs(num) // den * (1 if num >= 0 else -1)  # C division truncates toward zero
+        for y in range(top[1], bot[1]):
+            e = x
+            s = side[y] << 16
+            a, b = (e, s) if e <= s else (s, e)
+            xs = (a + 65535) >> 16
+            xe = b >> 16
+            if xs <= xe:
+                cover(y, xs, xe)
+            x += dx
+    return lo, hi
+
+
+def lane_canvas(lo, hi, width, height):
+    """RGB canvas with the lane polygon in (0,255,0) (lane_tracker.py:638-647)."""
+    img = np.zeros((height, width, 3), dtype=np.uint8)
+    for y in range(height):
+        if hi[y] >= lo[y]:
+            img[y, lo[y]:hi[y] + 1, 1] = 255
+    return img
+
+
+def add_weighted_03(img, lane):
+    """``cv2.addWeighted(img, 1, lane, 0.3, 0)`` (lane_tracker.py:662): float32."""
+    f = img.astype(np.float32) + lane.astype(np.float32) * np.float32(0.3)
+    return np.clip(np.rint(f), 0, 255).astype(np.uint8)

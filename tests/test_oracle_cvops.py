@@ -1,0 +1,112 @@
+"""Pin oracle/cvops.py bit-for-bit against cv2 itself (the reference's un-vendored kernel library)."""
+import numpy as np
+import pytest
+
+from oracle import cvops
+from lane_tracker_b200 import synth
+
+cv2 = pytest.importorskip("cv2")
+
+CAL = synth.shipped_calibration()
+K, D = CAL["cam_matrix"], CAL["dist_coeffs"]
+M, MINV = CAL["warp_matrices"]
+
+
+@pytest.fixture(scope="module")
+def noise():
+    return np.random.default_rng(7).integers(0, 256, (720, 1280, 3), dtype=np.uint8)
+
+
+@pytest.fixture(scope="module")
+def bv(noise):
+    und = cv2.undistort(noise, K, D, None, K)
+    return cv2.warpPerspective(und, M, (1080, 1100), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
+
+
+def test_undistort(noise):
+    assert np.array_equal(cvops.undistort(noise, K, D), cv2.undistort(noise, K, D, None, K))
+
+
+def test_warp_and_unwarp(noise, bv):
+    und = cv2.undistort(noise, K, D, None, K)
+    assert np.array_equal(cvops.warp_perspective(und, M, (1080, 1100)), bv)
+    assert np.array_equal(cvops.warp_perspective(bv, MINV, (1280, 720)),
+                          cv2.warpPerspective(bv, MINV, (1280, 720)))
+
+
+def test_lab_b_exhaustive_slice():
+    # every (r,g) pair for 16 blue levels = 1M colours; the full 2^24 was checked in the survey
+    r, g, b = np.meshgrid(np.arange(256), np.arange(256), np.arange(0, 256, 17)[:16], indexing="ij")
+    rgb = np.stack([r, g, b], axis=-1).astype(np.uint8).reshape(256, -1, 3)
+    assert np.array_equal(cvops.lab_b_plane(rgb), cv2.cvtColor(rgb, cv2.COLOR_RGB2LAB)[:, :, 2])
+
+
+@pytest.mark.parametrize("k", [5, 29, 55])
+def test_ellipse_morphology(bv, k):
+    se = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (k, k))
+    assert [int(v) for v in (se.sum(1) - 1) // 2] == cvops.ellipse_half_widths(k)
+    smooth = cv2.GaussianBlur(bv[:, :, 1], (0, 0), 3)
+    for plane in (bv[:, :, 0], smooth):
+        assert np.array_equal(cvops.erode_ellipse(plane, k), cv2.erode(plane, se))
+        assert np.array_equal(cvops.dilate_ellipse(plane, k), cv2.dilate(plane, se))
+        assert np.array_equal(cvops.tophat_ellipse(plane, k), cv2.morphologyEx(plane, cv2.MORPH_TOPHAT, se))
+        assert np.array_equal(cvops.open_ellipse(plane, k), cv2.morphologyEx(plane, cv2.MORPH_OPEN, se))
+
+
+@pytest.mark.parametrize("k,C", [(15, 8), (35, 5), (65, 10), (25, 8)])
+def test_cross_threshold(bv, k, C):
+    img = cv2.GaussianBlur(bv[:, :, 2], (0, 0), 2)
+    kl = np.array([[1] * k + [-k]], dtype=np.int16)
+    kr = np.array([[-k] + [1] * k], dtype=np.int16)
+    d = C * k
+    a = cv2.filter2D(img, cv2.CV_16S, kl, anchor=(k, 0), delta=d, borderType=cv2.BORDER_CONSTANT)
+    b = cv2.filter2D(img, cv2.CV_16S, kr, anchor=(0, 0), delta=d, borderType=cv2.BORDER_CONSTANT)
+    c = cv2.filter2D(img, cv2.CV_16S, kl.T.copy(), anchor=(0, k), delta=d, borderType=cv2.BORDER_CONSTANT)
+    e = cv2.filter2D(img, cv2.CV_16S, kr.T.copy(), anchor=(0, 0), delta=d, borderType=cv2.BORDER_CONSTANT)
+    want = np.where(((a < 0) & (b < 0)) | ((c < 0) & (e < 0)), 255, 0).astype(np.uint8)
+    got = cvops.cross_threshold(img, k, C)
+    assert 0 < (got > 0).mean() < 1
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("bs,c", [(15, 5), (35, 5), (15, 8)])
+def test_box_mean_threshold(bv, bs, c):
+    for plane in (bv[:, :, 0], cv2.GaussianBlur(bv[:, :, 1], (0, 0), 2)):
+        want = cv2.adaptiveThreshold(plane, 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY, bs, -c)
+        assert np.array_equal(cvops.box_mean_threshold(plane, bs, c), want)
+
+
+def test_add_weighted(noise):
+    lane = np.random.default_rng(8).integers(0, 256, noise.shape, dtype=np.uint8)
+    assert np.array_equal(cvops.add_weighted_03(noise, lane), cv2.addWeighted(noise, 1, lane, 0.3, 0))
+
+
+def test_fill_poly_lane_polygons():
+    W, H = 1080, 1100
+    rng = np.random.default_rng(1)
+    checked = 0
+    for t in range(120):
+        a = rng.normal(0, 3e-4) * (5 if t % 3 == 0 else 1)
+        b = rng.normal(0, 0.5) * (3 if t % 3 == 0 else 1)
+        c = rng.uniform(100, 700)
+        a2, b2, sep = a + rng.normal(0, 1e-4), b + rng.normal(0, 0.1), rng.uniform(100, 300)
+        partial = 1.0 if t % 2 == 0 else 0.5
+        ploty = np.linspace(H * (1 - partial), H - 1, int(H * partial))
+        xs = []
+        for (aa, bb, cc) in ((a, b, c), (a2, b2, c + sep)):
+            f = aa * (ploty - 1099) ** 2 + bb * (ploty - 1099) + cc
+            f = f[(f <= W - 1) & (f >= 0)]
+            xs.append(f.astype(int))
+        lx, rx = xs
+        if len(lx) == 0 or len(rx) == 0:
+            continue
+        ly = np.arange(H - len(lx), H)
+        ry = np.arange(H - len(rx), H)
+        canvas = np.zeros((H, W, 3), np.uint8)
+        pl = np.array([np.transpose(np.vstack([lx, ly]))])
+        pr = np.array([np.flipud(np.transpose(np.vstack([rx, ry])))])
+        cv2.fillPoly(canvas, np.int_([np.hstack((pl, pr))]), (0, 255, 0))
+        lo, hi = cvops.lane_polygon_rows(lx, ly, rx, ry, W, H)
+        assert np.array_equal(cvops.lane_canvas(lo, hi, W, H), canvas), t
+        checked += 1
+    assert checked > 80
