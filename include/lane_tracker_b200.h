@@ -1,0 +1,215 @@
+/*
+ * lane_tracker_b200 -- C ABI of the B200-native lane-tracking hot path.
+ *
+ * The reference (pierluigiferrari/lane_tracker) has no FFI: its boundary is the
+ * Python class `LaneTracker` (lane_tracker.py:85-1209) called once per frame by
+ * moviepy (process_video.py:43).  This header is the boundary a maintainer would
+ * bind instead (ctypes stub in INTEGRATION.md): every entry point cites the
+ * reference method it replaces.  Conventions:
+ *   - plain C types only; every pointer named d_* is DEVICE memory owned by the
+ *     caller, every h_* is HOST memory owned by the caller;
+ *   - all work is enqueued on the caller's CUDA stream (`stream` is a
+ *     cudaStream_t passed as void*); nothing synchronises unless documented;
+ *   - int return: 0 = ok, <0 = error (see lt_last_error); no exceptions;
+ *   - one handle per GPU; a handle is not thread-safe (the reference object is
+ *     not re-entrant either: it carries tracking state);
+ *   - images are uint8, RGB, row-major HWC, tightly packed.
+ *   - a handle serves `max_streams` independent video streams; per-stream
+ *     tracking state (lane_tracker.py:139-176) lives in device memory.
+ */
+#ifndef LANE_TRACKER_B200_H
+#define LANE_TRACKER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LT_ABI_VERSION 1
+#define LT_MAX_AVERAGE 8          /* capacity of the n_average rings */
+
+typedef struct lt_handle lt_handle;
+
+/* Constructor arguments of LaneTracker.__init__ (lane_tracker.py:101-137) plus the
+ * calibration read by utils.load_camera_calib / load_warp_params (utils.py:13-55). */
+typedef struct lt_config {
+    int32_t img_w, img_h;         /* img_size    (width, height) */
+    int32_t bv_w, bv_h;           /* warped_size (width, height); bv_w must be even */
+    double  cam_matrix[9];        /* row-major 3x3 */
+    double  dist_coeffs[5];       /* k1 k2 p1 p2 k3 */
+    double  M[9];                 /* warp_matrices[0] */
+    double  Minv[9];              /* warp_matrices[1] */
+    double  mppv, mpph;           /* mpp_conversion */
+    int32_t n_fail, n_reset, n_average, print_frame_count;
+    int32_t max_streams;          /* independent streams served by this handle */
+    int32_t device;               /* CUDA device ordinal */
+} lt_config;
+
+/* Keyword options of LaneTracker.process (lane_tracker.py:876-900). */
+typedef struct lt_params {
+    int32_t ksize_r, C_r, ksize_b, C_b;
+    int32_t filter_type;          /* 0 = 'bilateral', 1 = 'neighborhood' */
+    int32_t mask_noise, noise_thresh, ksize_noise, C_noise;
+    int32_t window_width, window_height, search_range;
+    double  mu;
+    int32_t no_success_limit;
+    double  start_slice;
+    int32_t ignore_sides, ignore_bottom;
+    int32_t bandwidth;
+    double  partial;
+    int32_t n_tries;
+} lt_params;
+
+/* Per-stream, per-frame result of lt_process (what process() leaves in the
+ * tracker's attributes, lane_tracker.py:1142-1209). */
+typedef struct lt_result {
+    int32_t counter;              /* frames processed by this stream so far */
+    int32_t attempts;             /* 1 or 2 (lane_tracker.py:1071) */
+    int32_t search_mode;          /* of the last attempt: 0 sliding window, 1 band */
+    int32_t detected_pixels;
+    int32_t valid_lane_lines;
+    int32_t last_detection;
+    int32_t drew_lane;            /* 1: lane polygon blended, 0: failure frame */
+    int32_t n_left, n_right;      /* lane pixels of the last attempt */
+    int32_t n_left_avg, n_right_avg; /* vertices of the averaged polylines */
+    int32_t left_curve_radius, right_curve_radius, average_curve_radius;
+    int32_t success;
+    int32_t fit_rank_deficient;   /* bit0 left, bit1 right: <3 distinct rows */
+    int32_t first_detected, first_valid;      /* outcome of attempt 1 (== final when attempts == 1) */
+    int32_t first_n_left, first_n_right;
+    double  left_fit[3], right_fit[3];   /* last attempt's np.polyfit equivalents */
+    double  left_avg[3], right_avg[3];
+    double  eccentricity;
+    double  validity_d[3];        /* x1_diff, x2_diff, x3_diff of check_validity */
+    double  first_left_fit[3], first_right_fit[3];
+} lt_result;
+
+/* Snapshot of one stream's tracking state (lane_tracker.py:139-176); used by
+ * tests (teacher forcing) and for checkpoint/restore. */
+typedef struct lt_state {
+    int32_t last_detection, counter, success;
+    int32_t ring_len;                             /* len(left_fit_coeffs) */
+    int32_t ring_empty[LT_MAX_AVERAGE];           /* 1 = np.array([]) marker */
+    double  ring_left[LT_MAX_AVERAGE][3], ring_right[LT_MAX_AVERAGE][3];
+    int32_t has_last;
+    double  last_left[3], last_right[3];
+    int32_t has_avg;
+    double  left_avg[3], right_avg[3];
+    int32_t n_left_avg, n_right_avg;              /* polyline vertex counts */
+    int32_t radii_len;
+    int32_t radii[LT_MAX_AVERAGE];
+    int32_t average_curve_radius;
+    double  eccentricity;
+} lt_state;
+
+/* ---- lifetime ------------------------------------------------------------ */
+
+/* LaneTracker.__init__ (lane_tracker.py:101-176) for `max_streams` streams.
+ * Builds the fixed-point remap tables on the device.  Synchronous. */
+int lt_create(const lt_config* cfg, lt_handle** out);
+int lt_destroy(lt_handle* h);
+/* Re-zero the state of the listed streams (ids == NULL: all). Synchronous. */
+int lt_reset(lt_handle* h, const int32_t* ids, int32_t n);
+const char* lt_last_error(void);
+int lt_abi_version(void);
+void lt_default_params(lt_params* p);            /* lane_tracker.py:876-900 */
+/* Number of kernels this library has launched since load (bench bookkeeping). */
+int64_t lt_launch_count(void);
+
+/* ---- the per-frame hot path ---------------------------------------------- */
+
+/* LaneTracker.process (lane_tracker.py:876-1209) for streams 0..n_streams-1.
+ *   d_frames : [n_streams][img_h][img_w][3]
+ *   d_out    : same shape, or NULL for fits-only mode (no overlay rendered)
+ *   params   : one lt_params for all streams (the reference's defaults-are-the-
+ *              config convention, README.md:34)
+ *   d_results: [n_streams] lt_result, device memory (copy back asynchronously)
+ * Stream s uses and updates state slot s.  Putative text overlays (putText,
+ * lane_tracker.py:653-659, 668-672) are not rendered. */
+int lt_process(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int32_t n_streams,
+               const lt_params* params, lt_result* d_results, void* stream);
+
+/* Keep the ordered lane-pixel sets and window centroids of every lt_process call so that
+ * lt_read_capture can return them (the reference exposes them as the attributes left_x/left_y/
+ * right_x/right_y/left_window_centroids, lane_tracker.py:159-166).  Off by default: the
+ * throughput path needs only the moment sums. */
+int lt_set_capture(lt_handle* h, int32_t enable);
+/* attempt: 0 first, 1 second.  h_pixels: (y<<16 | x+32768), up to `capacity` entries;
+ * h_count: true count; h_centroids: LT_MAX_LEVELS ints (sliding-window search only). Synchronous. */
+int lt_read_capture(lt_handle* h, int32_t stream_id, int32_t attempt, int32_t side, uint32_t* h_pixels,
+                    int32_t capacity, int32_t* h_count, int32_t* h_centroids, int32_t* h_ncentroids);
+
+/* ---- stage entry points (mirror the reference's public methods) ----------- */
+
+/* cv2.undistort + cv2.warpPerspective of find_lane_points (lane_tracker.py:832-834).
+ *   d_bv_rgb : [n][bv_h][bv_w][3] (may be NULL: only the internal planes are kept) */
+int lt_remap(lt_handle* h, const uint8_t* d_frames, uint8_t* d_bv_rgb, int32_t n_streams, void* stream);
+
+/* LaneTracker.filter_lane_points (lane_tracker.py:183-240) on caller-supplied
+ * bird's-eye RGB images.  d_mask: [n][bv_h][bv_w] uint8 {0,255}. */
+int lt_filter_lane_points(lt_handle* h, const uint8_t* d_bv_rgb, uint8_t* d_mask, int32_t n_streams,
+                          int32_t filter_type, int32_t ksize_r, int32_t C_r, int32_t ksize_b, int32_t C_b,
+                          int32_t mask_noise, int32_t ksize_noise, int32_t C_noise, int32_t noise_thresh,
+                          void* stream);
+
+/* Pixel-set outputs of the two searches.  Pixels are (y<<16 | x) in the
+ * reference's order; x is stored with a +32768 bias because NumPy slice
+ * wrap-around can report negative x (lane_tracker.py:299-303).
+ *   d_pixels : [n][2][capacity] uint32   (left, right)
+ *   d_counts : [n][2] int32 (true counts, may exceed capacity)
+ *   d_centroids: [n][2][LT_MAX_LEVELS] int32, d_ncentroids: [n][2] (SWS only; may be NULL) */
+#define LT_MAX_LEVELS 128
+int lt_sliding_window_search(lt_handle* h, const uint8_t* d_mask, int32_t n_streams,
+                             int32_t window_width, int32_t window_height, int32_t search_range, double mu,
+                             int32_t no_success_limit, double start_slice, int32_t ignore_sides,
+                             int32_t ignore_bottom, double partial,
+                             uint32_t* d_pixels, int32_t capacity, int32_t* d_counts,
+                             int32_t* d_centroids, int32_t* d_ncentroids, int32_t* d_detected, void* stream);
+
+/* LaneTracker.band_search (lane_tracker.py:449-500); coefficients per stream:
+ * d_coeffs [n][2][3] (left, right) = last_left_coeffs / last_right_coeffs. */
+int lt_band_search(lt_handle* h, const uint8_t* d_mask, int32_t n_streams, const double* d_coeffs,
+                   int32_t bandwidth, int32_t ignore_bottom, double partial,
+                   uint32_t* d_pixels, int32_t capacity, int32_t* d_counts, int32_t* d_detected, void* stream);
+
+/* LaneTracker.fit_poly (lane_tracker.py:502-509): np.polyfit(y, x, 2) per side.
+ *   d_pixels/d_counts as produced above; d_fits [n][2][3]. */
+int lt_fit_poly(lt_handle* h, const uint32_t* d_pixels, int32_t capacity, const int32_t* d_counts,
+                int32_t n_streams, double* d_fits, void* stream);
+
+/* LaneTracker.check_validity (lane_tracker.py:561-627). d_valid [n] int32,
+ * d_diffs [n][3] (may be NULL). */
+int lt_check_validity(lt_handle* h, const double* d_fits, int32_t n_streams, int32_t* d_valid,
+                      double* d_diffs, void* stream);
+
+/* LaneTracker.get_poly_points (lane_tracker.py:511-528).
+ *   d_fits [n][2][3]; d_x [n][2][bv_h] int32 (x of the kept points, re-stacked so
+ *   entry i belongs to row bv_h - count + i); d_counts [n][2]. */
+int lt_get_poly_points(lt_handle* h, const double* d_fits, int32_t n_streams, double partial,
+                       int32_t* d_x, int32_t* d_counts, void* stream);
+
+/* LaneTracker.draw_lane (lane_tracker.py:629-662) without putText: fills the lane
+ * polygon of the given polylines, un-warps and blends it.  d_x/d_counts as above. */
+int lt_draw_lane(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int32_t n_streams,
+                 const int32_t* d_x, const int32_t* d_counts, void* stream);
+
+/* ---- state access (tests, checkpoint/restore) ------------------------------ */
+int lt_get_state(lt_handle* h, int32_t stream_id, lt_state* h_state, int32_t* h_left_avg_x,
+                 int32_t* h_right_avg_x);   /* polylines: bv_h ints each, may be NULL. Synchronous. */
+int lt_set_state(lt_handle* h, int32_t stream_id, const lt_state* h_state, const int32_t* h_left_avg_x,
+                 const int32_t* h_right_avg_x);
+
+/* Debug/test access to internal buffers of the last lt_process / stage call.
+ * what: 0 undistort map (int32 [img_h][img_w][2]), 1 bird's-eye map (int32 [bv_h][bv_w][2]),
+ *       2 overlay map (int32 [img_h][img_w][2]), 3 R plane u8 [bv_h][bv_w], 4 LAB-b plane,
+ *       5 R top-hat, 6 b top-hat, 7 mask u8 {0,255}, 8 merged (pre-open) mask,
+ *       9 lane row spans int32 [bv_h][2], 10 geometry int32[6] = {undistorted ROI first,last+1, overlay rows
+ *       first,last+1, pair-plane width, mask words per row}.
+ * Copies to HOST memory; synchronous. Returns bytes written or <0. */
+int64_t lt_debug_read(lt_handle* h, int32_t what, int32_t stream_id, void* h_dst, int64_t capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LANE_TRACKER_B200_H */

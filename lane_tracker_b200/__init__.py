@@ -1,0 +1,16 @@
+"""lane_tracker_b200 -- B200-native implementation of the lane_tracker per-frame hot path.
+
+The tracker classes need the in-tree CUDA library (liblane_tracker_b200.so) and a CUDA device;
+importing them without either raises.  ``lane_tracker_b200.synth`` (test/bench data) and
+``lane_tracker_b200.utils`` (calibration loaders) are plain NumPy.
+"""
+from .utils import load_camera_calib, load_warp_params  # noqa: F401
+
+__all__ = ["LaneTracker", "BatchedLaneTracker", "load_camera_calib", "load_warp_params"]
+
+
+def __getattr__(name):
+    if name in ("LaneTracker", "BatchedLaneTracker", "make_params", "RESULT_DTYPE"):
+        from . import tracker
+        return getattr(tracker, name)
+    raise AttributeError(name)

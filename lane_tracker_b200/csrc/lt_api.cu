@@ -1,0 +1,509 @@
+// C ABI of lane_tracker_b200 (include/lane_tracker_b200.h): handle lifetime, the batched
+// process() pipeline and the per-method stage entry points.
+#include <stdarg.h>
+#include <string.h>
+#include <atomic>
+#include <vector>
+#include "lt_common.cuh"
+#include "lab_tables.inc"
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void lt_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void lt_count_launch(int n) { g_launches += n; }
+
+extern "C" const char* lt_last_error(void) { return g_err; }
+extern "C" int lt_abi_version(void) { return LT_ABI_VERSION; }
+extern "C" int64_t lt_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" void lt_default_params(lt_params* p) {
+    // lane_tracker.py:876-900
+    p->ksize_r = 15; p->C_r = 8; p->ksize_b = 35; p->C_b = 5; p->filter_type = 0; p->mask_noise = 0;
+    p->noise_thresh = 140; p->ksize_noise = 65; p->C_noise = 10; p->window_width = 30; p->window_height = 40;
+    p->search_range = 20; p->mu = 0.1; p->no_success_limit = 8; p->start_slice = 0.25; p->ignore_sides = 360;
+    p->ignore_bottom = 30; p->bandwidth = 25; p->partial = 1.0; p->n_tries = 2;
+}
+
+static LtAttemptParams attempt_from(const lt_params& p) {
+    LtAttemptParams a;
+    a.filter_type = p.filter_type; a.ksize_r = p.ksize_r; a.C_r = p.C_r; a.ksize_b = p.ksize_b; a.C_b = p.C_b;
+    a.mask_noise = p.mask_noise; a.noise_thresh = p.noise_thresh; a.ksize_noise = p.ksize_noise; a.C_noise = p.C_noise;
+    a.window_width = p.window_width; a.window_height = p.window_height; a.search_range = p.search_range;
+    a.no_success_limit = p.no_success_limit; a.ignore_sides = p.ignore_sides; a.ignore_bottom = p.ignore_bottom;
+    a.bandwidth = p.bandwidth; a.mu = p.mu; a.start_slice = p.start_slice; a.partial = p.partial;
+    return a;
+}
+
+static LtAttemptParams second_attempt() {
+    // hard-coded second attempt, lane_tracker.py:1081-1099
+    lt_params p;
+    lt_default_params(&p);
+    p.C_r = 5; p.filter_type = 1; p.no_success_limit = 50; p.bandwidth = 30; p.partial = 1.0;
+    return attempt_from(p);
+}
+
+static int check_params(const lt_handle* h, const LtAttemptParams& a) {
+    if (a.filter_type != 0 && a.filter_type != 1) {
+        lt_set_error("Unexpected filter mode. Expected modes are 'bilateral' or 'neighborhood'.");
+        return -1;
+    }
+    int kmax = a.filter_type == 0 ? 255 : 255;
+    if (a.ksize_r < 1 || a.ksize_b < 1 || a.ksize_r > kmax || a.ksize_b > kmax || a.ksize_noise < 1 || a.ksize_noise > 255) {
+        lt_set_error("threshold kernel sizes must lie in [1, 255]");
+        return -1;
+    }
+    if (a.filter_type == 1 && ((a.ksize_r & 1) == 0 || (a.ksize_b & 1) == 0 || a.ksize_r < 3 || a.ksize_b < 3)) {
+        lt_set_error("'neighborhood' block sizes must be odd and >= 3 (cv2.adaptiveThreshold)");
+        return -1;
+    }
+    if (a.window_width < 1 || a.window_width > 64 || a.window_height < 1 || a.window_height > h->d.bv_h) {
+        lt_set_error("window_width must lie in [1, 64] and window_height in [1, warped height]");
+        return -1;
+    }
+    if (!(a.partial >= 0.0 && a.partial <= 1.0) || a.ignore_bottom < 0 || a.ignore_bottom > h->d.bv_h) {
+        lt_set_error("partial must lie in [0, 1] and ignore_bottom in [0, warped height]");
+        return -1;
+    }
+    return 0;
+}
+
+template <typename T> static int dev_alloc(T** p, size_t n) {
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+    if (e != cudaSuccess) { lt_set_error("cudaMalloc(%zu bytes) -> %s", n * sizeof(T), cudaGetErrorString(e)); return -2; }
+    return 0;
+}
+
+static void init_state(lt_handle* h, lt_state* s) {
+    memset(s, 0, sizeof(*s));
+    s->last_detection = h->cfg.n_reset + 1;     // lane_tracker.py:140
+}
+
+extern "C" int lt_destroy(lt_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->cfg.device);
+    void* ptrs[] = {h->und_map, h->bv_map, h->ov_map, h->lab_gamma, h->lab_cbrt, h->und_roi, h->planeR, h->planeB,
+                    h->tmpR, h->tmpB, h->topR, h->topB, h->merged, h->mask, h->pixels, h->pix_counts, h->lane_rows,
+                    h->avg_x, h->state, h->att, h->retry_list, h->retry_count, h->draw_flags, h->scratch_bv,
+                    h->cap_pixels, h->cap_counts, h->cap_cents, h->cap_ncents};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    delete h;
+    return 0;
+}
+
+extern "C" int lt_create(const lt_config* cfg, lt_handle** out) {
+    if (!cfg || !out) { lt_set_error("null argument"); return -1; }
+    if (cfg->img_w < 64 || cfg->img_h < 16 || cfg->bv_w < 64 || cfg->bv_h < 16 || (cfg->img_w & 3) || cfg->bv_h > 65535 ||
+        cfg->bv_w > 32767 || cfg->img_w > 32767 || cfg->img_h > 32767) {
+        lt_set_error("unsupported geometry: img %dx%d (width must be a multiple of 4), warped %dx%d", cfg->img_w,
+                     cfg->img_h, cfg->bv_w, cfg->bv_h);
+        return -1;
+    }
+    if (cfg->max_streams < 1 || cfg->n_average < 1 || cfg->n_average > LT_MAX_AVERAGE) {
+        lt_set_error("max_streams must be >= 1 and n_average in [1, %d]", LT_MAX_AVERAGE);
+        return -1;
+    }
+    LT_CUDA(cudaSetDevice(cfg->device));
+    lt_handle* h = new lt_handle();
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    h->S = cfg->max_streams;
+    LtDims& d = h->d;
+    d.img_w = cfg->img_w; d.img_h = cfg->img_h; d.bv_w = cfg->bv_w; d.bv_h = cfg->bv_h;
+    d.p2 = 32 * ((cfg->bv_w + 63) / 64);
+    d.mwords = 2 * d.p2 / 32;
+    h->stream_plane = (size_t)d.bv_h * d.p2;
+    h->stream_mask = (size_t)d.bv_h * d.mwords;
+    h->pix_cap = LT_PIX_CAP_DEFAULT;
+    const size_t S = h->S, npx = (size_t)d.img_w * d.img_h, nbv = (size_t)d.bv_w * d.bv_h;
+    int rc = 0;
+#define A(ptr, n) if (!rc) rc = dev_alloc(&h->ptr, (n))
+    A(und_map, npx); A(bv_map, nbv); A(ov_map, npx); A(lab_gamma, 256); A(lab_cbrt, 3072);
+    if (rc) { lt_destroy(h); return rc; }
+    cudaStream_t st = 0;
+    if ((rc = lt_launch_build_maps(h, st))) { lt_destroy(h); return rc; }
+    cudaMemcpy(h->lab_gamma, LT_LAB_GAMMA, sizeof(LT_LAB_GAMMA), cudaMemcpyHostToDevice);
+    cudaMemcpy(h->lab_cbrt, LT_LAB_CBRT, sizeof(LT_LAB_CBRT), cudaMemcpyHostToDevice);
+    // rows of the undistorted frame that the bird's-eye view can touch / frame rows the overlay can touch
+    {
+        std::vector<int2> m(nbv);
+        cudaError_t e = cudaMemcpy(m.data(), h->bv_map, nbv * sizeof(int2), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { lt_set_error("map build failed: %s", cudaGetErrorString(e)); lt_destroy(h); return -2; }
+        int r0 = d.img_h, r1 = 0;
+        for (size_t i = 0; i < nbv; ++i) {
+            int sx = m[i].x >> 5, sy = m[i].y >> 5;
+            if (sx + 1 < 0 || sx >= d.img_w) continue;
+            for (int yy = sy; yy <= sy + 1; ++yy)
+                if (yy >= 0 && yy < d.img_h) { r0 = yy < r0 ? yy : r0; r1 = yy + 1 > r1 ? yy + 1 : r1; }
+        }
+        if (r0 >= r1) { r0 = 0; r1 = 1; }
+        d.roi0 = r0; d.roi1 = r1;
+        std::vector<int2> o(npx);
+        cudaMemcpy(o.data(), h->ov_map, npx * sizeof(int2), cudaMemcpyDeviceToHost);
+        int o0 = d.img_h, o1 = 0;
+        for (int y = 0; y < d.img_h; ++y)
+            for (int x = 0; x < d.img_w; ++x) {
+                int2 q = o[(size_t)y * d.img_w + x];
+                int sx = q.x >> 5, sy = q.y >> 5;
+                if (sx + 1 >= 0 && sx < d.bv_w && sy + 1 >= 0 && sy < d.bv_h) { o0 = y < o0 ? y : o0; o1 = y + 1 > o1 ? y + 1 : o1; }
+            }
+        if (o0 >= o1) { o0 = 0; o1 = 0; }
+        d.ov0 = o0; d.ov1 = o1;
+    }
+    A(und_roi, S * (size_t)(d.roi1 - d.roi0) * d.img_w);
+    A(planeR, S * h->stream_plane); A(planeB, S * h->stream_plane);
+    A(tmpR, S * h->stream_plane); A(tmpB, S * h->stream_plane);
+    A(topR, S * h->stream_plane); A(topB, S * h->stream_plane);
+    A(merged, S * h->stream_mask); A(mask, S * h->stream_mask);
+    A(pixels, S * 2 * (size_t)h->pix_cap); A(pix_counts, S * 2);
+    A(lane_rows, S * (size_t)d.bv_h); A(avg_x, S * 2 * (size_t)d.bv_h);
+    A(state, S); A(att, 2 * S); A(retry_list, S); A(retry_count, 1); A(draw_flags, 2 * S);
+#undef A
+    if (rc) { lt_destroy(h); return rc; }
+    cudaMemset(h->avg_x, 0, S * 2 * (size_t)d.bv_h * sizeof(int));
+    cudaMemset(h->lane_rows, 0, S * (size_t)d.bv_h * sizeof(int2));
+    cudaMemset(h->draw_flags, 0, 2 * S * sizeof(int));
+    cudaMemset(h->retry_count, 0, sizeof(int));
+    cudaMemset(h->att, 0, 2 * S * sizeof(LtAttemptOut));
+    *out = h;
+    rc = lt_reset(h, nullptr, 0);
+    if (rc) { lt_destroy(h); *out = nullptr; return rc; }
+    LT_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+
+extern "C" int lt_reset(lt_handle* h, const int32_t* ids, int32_t n) {
+    if (!h) { lt_set_error("null handle"); return -1; }
+    LT_CUDA(cudaSetDevice(h->cfg.device));
+    LtDevState z;
+    init_state(h, &z.s);
+    if (!ids) {
+        std::vector<LtDevState> all(h->S, z);
+        LT_CUDA(cudaMemcpy(h->state, all.data(), all.size() * sizeof(LtDevState), cudaMemcpyHostToDevice));
+        return 0;
+    }
+    for (int i = 0; i < n; ++i) {
+        if (ids[i] < 0 || ids[i] >= h->S) { lt_set_error("stream id %d out of range", ids[i]); return -1; }
+        LT_CUDA(cudaMemcpy(h->state + ids[i], &z, sizeof(z), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+static int check_n(lt_handle* h, int n) {
+    if (!h) { lt_set_error("null handle"); return -1; }
+    if (n < 1 || n > h->S) { lt_set_error("n_streams %d outside [1, %d]", n, h->S); return -1; }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// process()
+// ---------------------------------------------------------------------------
+
+extern "C" int lt_process(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int32_t n, const lt_params* params,
+                          lt_result* d_results, void* stream) {
+    int rc;
+    if ((rc = check_n(h, n))) return rc;
+    if (!d_frames || !params || !d_results) { lt_set_error("null argument"); return -1; }
+    if (d_out == d_frames) { lt_set_error("d_out must not alias d_frames"); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    LtAttemptParams p1 = attempt_from(*params), p2 = second_attempt();
+    if ((rc = check_params(h, p1))) return rc;
+    const bool two = (params->n_tries >= 2) || (params->n_tries == -1);
+    // find_lane_points (lane_tracker.py:795-874), first attempt, all streams
+    if ((rc = lt_launch_undistort(h, d_frames, n, st))) return rc;
+    if ((rc = lt_launch_warp(h, nullptr, n, st))) return rc;
+    if ((rc = lt_launch_filter(h, n, p1, nullptr, nullptr, st))) return rc;
+    LtSearchArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.mask = h->mask; sa.mode = 0; sa.att = h->att; sa.do_fit = 1;
+    const size_t S = h->S;
+    if (h->capture) {
+        sa.by_stream = 1; sa.pixels = h->cap_pixels; sa.pix_cap = h->pix_cap; sa.pix_counts = h->cap_counts;
+        sa.centroids = h->cap_cents; sa.ncentroids = h->cap_ncents;
+    }
+    if ((rc = lt_launch_search(h, n, p1, sa, nullptr, nullptr, st))) return rc;
+    if (two) {
+        // second attempt only for the streams whose first attempt failed (lane_tracker.py:1071-1128).
+        // The reference re-runs undistort + warp here; their outputs are unchanged, so the planes are reused.
+        if ((rc = lt_launch_select_retry(h, n, params->n_tries, st))) return rc;
+        if ((rc = lt_launch_filter(h, n, p2, h->retry_list, h->retry_count, st))) return rc;
+        sa.att = h->att + h->S;
+        if (h->capture) {
+            sa.pixels = h->cap_pixels + S * 2 * (size_t)h->pix_cap; sa.pix_counts = h->cap_counts + S * 2;
+            sa.centroids = h->cap_cents + S * 2 * LT_MAX_LEVELS; sa.ncentroids = h->cap_ncents + S * 2;
+        }
+        if ((rc = lt_launch_search(h, n, p2, sa, h->retry_list, h->retry_count, st))) return rc;
+    }
+    if ((rc = lt_launch_update_state(h, n, d_results, two ? 2 : 1, st))) return rc;
+    if (d_out) {
+        if ((rc = lt_launch_overlay(h, d_frames, d_out, n, h->draw_flags, st))) return rc;
+    }
+    return 0;
+}
+
+extern "C" int lt_set_capture(lt_handle* h, int32_t enable) {
+    if (!h) { lt_set_error("null handle"); return -1; }
+    LT_CUDA(cudaSetDevice(h->cfg.device));
+    if (enable && !h->cap_pixels) {
+        const size_t S = h->S;
+        int rc = 0;
+        if (!rc) rc = dev_alloc(&h->cap_pixels, 2 * S * 2 * (size_t)h->pix_cap);
+        if (!rc) rc = dev_alloc(&h->cap_counts, 2 * S * 2);
+        if (!rc) rc = dev_alloc(&h->cap_cents, 2 * S * 2 * (size_t)LT_MAX_LEVELS);
+        if (!rc) rc = dev_alloc(&h->cap_ncents, 2 * S * 2);
+        if (rc) return rc;
+        cudaMemset(h->cap_counts, 0, 2 * S * 2 * sizeof(int));
+        cudaMemset(h->cap_ncents, 0, 2 * S * 2 * sizeof(int));
+    }
+    h->capture = enable ? 1 : 0;
+    return 0;
+}
+
+extern "C" int lt_read_capture(lt_handle* h, int32_t id, int32_t attempt, int32_t side, uint32_t* h_pixels,
+                               int32_t capacity, int32_t* h_count, int32_t* h_centroids, int32_t* h_ncentroids) {
+    if (!h || id < 0 || id >= h->S || attempt < 0 || attempt > 1 || side < 0 || side > 1 || !h_count) {
+        lt_set_error("bad argument");
+        return -1;
+    }
+    if (!h->cap_pixels) { lt_set_error("capture is not enabled (lt_set_capture)"); return -1; }
+    LT_CUDA(cudaSetDevice(h->cfg.device));
+    LT_CUDA(cudaDeviceSynchronize());
+    const size_t S = h->S, slot = ((size_t)attempt * S + id) * 2 + side;
+    LT_CUDA(cudaMemcpy(h_count, h->cap_counts + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    int n = *h_count < h->pix_cap ? *h_count : h->pix_cap;
+    if (n > capacity) n = capacity;
+    if (h_pixels && n > 0)
+        LT_CUDA(cudaMemcpy(h_pixels, h->cap_pixels + slot * (size_t)h->pix_cap, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (h_centroids && h_ncentroids) {
+        LT_CUDA(cudaMemcpy(h_ncentroids, h->cap_ncents + slot, sizeof(int), cudaMemcpyDeviceToHost));
+        LT_CUDA(cudaMemcpy(h_centroids, h->cap_cents + slot * LT_MAX_LEVELS, LT_MAX_LEVELS * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// stage entry points
+// ---------------------------------------------------------------------------
+
+extern "C" int lt_remap(lt_handle* h, const uint8_t* d_frames, uint8_t* d_bv_rgb, int32_t n, void* stream) {
+    int rc;
+    if ((rc = check_n(h, n))) return rc;
+    if (!d_frames) { lt_set_error("null argument"); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = lt_launch_undistort(h, d_frames, n, st))) return rc;
+    return lt_launch_warp(h, d_bv_rgb, n, st);
+}
+
+extern "C" int lt_filter_lane_points(lt_handle* h, const uint8_t* d_bv_rgb, uint8_t* d_mask, int32_t n,
+                                     int32_t filter_type, int32_t ksize_r, int32_t C_r, int32_t ksize_b, int32_t C_b,
+                                     int32_t mask_noise, int32_t ksize_noise, int32_t C_noise, int32_t noise_thresh,
+                                     void* stream) {
+    int rc;
+    if ((rc = check_n(h, n))) return rc;
+    if (!d_mask) { lt_set_error("null argument"); return -1; }
+    lt_params dp;
+    lt_default_params(&dp);
+    LtAttemptParams p = attempt_from(dp);
+    p.filter_type = filter_type; p.ksize_r = ksize_r; p.C_r = C_r; p.ksize_b = ksize_b; p.C_b = C_b;
+    p.mask_noise = mask_noise; p.ksize_noise = ksize_noise; p.C_noise = C_noise; p.noise_thresh = noise_thresh;
+    if ((rc = check_params(h, p))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_bv_rgb) {   // NULL: reuse the planes left by the last lt_remap / lt_process
+        if ((rc = lt_launch_planes_from_bv(h, d_bv_rgb, n, st))) return rc;
+    }
+    if ((rc = lt_launch_filter(h, n, p, nullptr, nullptr, st))) return rc;
+    return lt_launch_mask_to_u8(h, h->mask, d_mask, n, st);
+}
+
+__global__ void k_detected_from_counts(const int* counts, int n, int* detected) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) detected[s] = (counts[2 * s] > 0 && counts[2 * s + 1] > 0) ? 1 : 0;
+}
+
+static int run_search_api(lt_handle* h, const uint8_t* d_mask, int n, const LtAttemptParams& p, int mode,
+                          const double* d_coeffs, uint32_t* d_pixels, int cap, int* d_counts, int* d_centroids,
+                          int* d_ncentroids, int* d_detected, cudaStream_t st) {
+    int rc;
+    if (!d_counts || (d_pixels && cap < 1)) { lt_set_error("d_counts is required; capacity must be positive"); return -1; }
+    if (d_mask) {   // NULL: search the mask left by the last filter call
+        if ((rc = lt_launch_u8_to_mask(h, d_mask, h->mask, n, st))) return rc;
+    }
+    LtSearchArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.mask = h->mask; sa.mode = mode; sa.coeffs = d_coeffs; sa.pixels = d_pixels; sa.pix_cap = cap;
+    sa.pix_counts = d_counts; sa.centroids = d_centroids; sa.ncentroids = d_ncentroids; sa.att = h->att; sa.do_fit = 1;
+    if ((rc = lt_launch_search(h, n, p, sa, nullptr, nullptr, st))) return rc;
+    if (d_detected) {
+        k_detected_from_counts<<<lt_div_up(n, 128), 128, 0, st>>>(d_counts, n, d_detected);
+        LT_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int lt_sliding_window_search(lt_handle* h, const uint8_t* d_mask, int32_t n, int32_t window_width,
+                                        int32_t window_height, int32_t search_range, double mu,
+                                        int32_t no_success_limit, double start_slice, int32_t ignore_sides,
+                                        int32_t ignore_bottom, double partial, uint32_t* d_pixels, int32_t capacity,
+                                        int32_t* d_counts, int32_t* d_centroids, int32_t* d_ncentroids,
+                                        int32_t* d_detected, void* stream) {
+    int rc;
+    if ((rc = check_n(h, n))) return rc;
+    lt_params dp;
+    lt_default_params(&dp);
+    LtAttemptParams p = attempt_from(dp);
+    p.window_width = window_width; p.window_height = window_height; p.search_range = search_range; p.mu = mu;
+    p.no_success_limit = no_success_limit; p.start_slice = start_slice; p.ignore_sides = ignore_sides;
+    p.ignore_bottom = ignore_bottom; p.partial = partial;
+    if ((rc = check_params(h, p))) return rc;
+    if ((d_centroids == nullptr) != (d_ncentroids == nullptr)) { lt_set_error("centroid outputs come in pairs"); return -1; }
+    return run_search_api(h, d_mask, n, p, 1, nullptr, d_pixels, capacity, d_counts, d_centroids, d_ncentroids,
+                          d_detected, (cudaStream_t)stream);
+}
+
+extern "C" int lt_band_search(lt_handle* h, const uint8_t* d_mask, int32_t n, const double* d_coeffs,
+                              int32_t bandwidth, int32_t ignore_bottom, double partial, uint32_t* d_pixels,
+                              int32_t capacity, int32_t* d_counts, int32_t* d_detected, void* stream) {
+    int rc;
+    if ((rc = check_n(h, n))) return rc;
+    if (!d_coeffs) { lt_set_error("band_search needs the previous fit coefficients"); return -1; }
+    lt_params dp;
+    lt_default_params(&dp);
+    LtAttemptParams p = attempt_from(dp);
+    p.bandwidth = bandwidth; p.ignore_bottom = ignore_bottom; p.partial = partial;
+    if ((rc = check_params(h, p))) return rc;
+    return run_search_api(h, d_mask, n, p, 2, d_coeffs, d_pixels, capacity, d_counts, nullptr, nullptr, d_detected,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int lt_fit_poly(lt_handle* h, const uint32_t* d_pixels, int32_t capacity, const int32_t* d_counts,
+                           int32_t n, double* d_fits, void* stream) {
+    int rc;
+    if ((rc = check_n(h, n))) return rc;
+    if (!d_pixels || !d_counts || !d_fits) { lt_set_error("null argument"); return -1; }
+    return lt_launch_fit_pixels(h, d_pixels, capacity, d_counts, n, d_fits, (cudaStream_t)stream);
+}
+
+extern "C" int lt_check_validity(lt_handle* h, const double* d_fits, int32_t n, int32_t* d_valid, double* d_diffs,
+                                 void* stream) {
+    int rc;
+    if ((rc = check_n(h, n))) return rc;
+    if (!d_fits || !d_valid) { lt_set_error("null argument"); return -1; }
+    return lt_launch_validity(h, d_fits, n, d_valid, d_diffs, (cudaStream_t)stream);
+}
+
+extern "C" int lt_get_poly_points(lt_handle* h, const double* d_fits, int32_t n, double partial, int32_t* d_x,
+                                  int32_t* d_counts, void* stream) {
+    int rc;
+    if ((rc = check_n(h, n))) return rc;
+    if (!d_fits || !d_x || !d_counts) { lt_set_error("null argument"); return -1; }
+    if (!(partial >= 0.0 && partial <= 1.0)) { lt_set_error("partial must lie in [0, 1]"); return -1; }
+    return lt_launch_poly_points(h, d_fits, n, partial, d_x, d_counts, (cudaStream_t)stream);
+}
+
+extern "C" int lt_draw_lane(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int32_t n, const int32_t* d_x,
+                            const int32_t* d_counts, void* stream) {
+    int rc;
+    if ((rc = check_n(h, n))) return rc;
+    if (!d_frames || !d_out || !d_x || !d_counts || d_out == d_frames) { lt_set_error("null or aliased argument"); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = lt_launch_lane_rows(h, d_x, d_counts, n, st))) return rc;
+    return lt_launch_overlay(h, d_frames, d_out, n, h->draw_flags, st);
+}
+
+// ---------------------------------------------------------------------------
+// state and debug access (synchronous)
+// ---------------------------------------------------------------------------
+
+extern "C" int lt_get_state(lt_handle* h, int32_t id, lt_state* hs, int32_t* h_lx, int32_t* h_rx) {
+    if (!h || !hs || id < 0 || id >= h->S) { lt_set_error("bad argument"); return -1; }
+    LT_CUDA(cudaSetDevice(h->cfg.device));
+    LT_CUDA(cudaDeviceSynchronize());
+    LT_CUDA(cudaMemcpy(hs, &h->state[id].s, sizeof(lt_state), cudaMemcpyDeviceToHost));
+    size_t H = h->d.bv_h;
+    if (h_lx) LT_CUDA(cudaMemcpy(h_lx, h->avg_x + (size_t)id * 2 * H, H * sizeof(int), cudaMemcpyDeviceToHost));
+    if (h_rx) LT_CUDA(cudaMemcpy(h_rx, h->avg_x + (size_t)id * 2 * H + H, H * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int lt_set_state(lt_handle* h, int32_t id, const lt_state* hs, const int32_t* h_lx, const int32_t* h_rx) {
+    if (!h || !hs || id < 0 || id >= h->S) { lt_set_error("bad argument"); return -1; }
+    if (hs->ring_len < 0 || hs->ring_len > LT_MAX_AVERAGE || hs->radii_len < 0 || hs->radii_len > LT_MAX_AVERAGE ||
+        hs->n_left_avg < 0 || hs->n_left_avg > h->d.bv_h || hs->n_right_avg < 0 || hs->n_right_avg > h->d.bv_h) {
+        lt_set_error("inconsistent lt_state");
+        return -1;
+    }
+    LT_CUDA(cudaSetDevice(h->cfg.device));
+    LT_CUDA(cudaDeviceSynchronize());
+    LT_CUDA(cudaMemcpy(&h->state[id].s, hs, sizeof(lt_state), cudaMemcpyHostToDevice));
+    size_t H = h->d.bv_h;
+    if (h_lx) LT_CUDA(cudaMemcpy(h->avg_x + (size_t)id * 2 * H, h_lx, H * sizeof(int), cudaMemcpyHostToDevice));
+    if (h_rx) LT_CUDA(cudaMemcpy(h->avg_x + (size_t)id * 2 * H + H, h_rx, H * sizeof(int), cudaMemcpyHostToDevice));
+    if (hs->has_avg && h_lx && h_rx) {
+        // rebuild the cached polygon rows of this stream
+        int counts[2] = {hs->n_left_avg, hs->n_right_avg};
+        int* d_counts = nullptr;
+        LT_CUDA(cudaMalloc((void**)&d_counts, 2 * sizeof(int)));
+        cudaMemcpy(d_counts, counts, sizeof(counts), cudaMemcpyHostToDevice);
+        // lt_launch_lane_rows works on slot 0..n-1; shift the base pointers to this stream
+        lt_handle tmp = *h;
+        tmp.lane_rows = h->lane_rows + (size_t)id * H;
+        tmp.draw_flags = h->draw_flags + id;
+        int rc = lt_launch_lane_rows(&tmp, h->avg_x + (size_t)id * 2 * H, d_counts, 1, 0);
+        cudaDeviceSynchronize();
+        cudaFree(d_counts);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" int64_t lt_debug_read(lt_handle* h, int32_t what, int32_t id, void* dst, int64_t cap) {
+    if (!h || !dst || id < 0 || id >= h->S) { lt_set_error("bad argument"); return -1; }
+    if (cudaSetDevice(h->cfg.device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+        lt_set_error("device error: %s", cudaGetErrorString(cudaGetLastError()));
+        return -2;
+    }
+    const LtDims& d = h->d;
+    const size_t npx = (size_t)d.img_w * d.img_h, nbv = (size_t)d.bv_w * d.bv_h;
+    const void* src = nullptr;
+    size_t bytes = 0;
+    uint8_t* tmp = nullptr;
+    int rc = 0;
+    switch (what) {
+        case 0: src = h->und_map; bytes = npx * sizeof(int2); break;
+        case 1: src = h->bv_map; bytes = nbv * sizeof(int2); break;
+        case 2: src = h->ov_map; bytes = npx * sizeof(int2); break;
+        case 3: case 4: case 5: case 6: case 7: case 8: {
+            bytes = nbv;
+            if (cudaMalloc((void**)&tmp, nbv) != cudaSuccess) { lt_set_error("cudaMalloc failed"); return -2; }
+            lt_handle one = *h;     // view of this stream as slot 0
+            if (what <= 6) {
+                const uint32_t* pl = what == 3 ? h->planeR : what == 4 ? h->planeB : what == 5 ? h->topR : h->topB;
+                rc = lt_launch_plane_to_u8(&one, pl + (size_t)id * h->stream_plane, tmp, 1, 0);
+            } else {
+                const uint32_t* bits = what == 7 ? h->mask : h->merged;
+                rc = lt_launch_mask_to_u8(&one, bits + (size_t)id * h->stream_mask, tmp, 1, 0);
+            }
+            src = tmp;
+            break;
+        }
+        case 9: src = h->lane_rows + (size_t)id * d.bv_h; bytes = (size_t)d.bv_h * sizeof(int2); break;
+        case 10: {
+            int v[6] = {d.roi0, d.roi1, d.ov0, d.ov1, d.p2, d.mwords};
+            if (cap < (int64_t)sizeof(v)) { lt_set_error("buffer too small"); return -1; }
+            memcpy(dst, v, sizeof(v));
+            return sizeof(v);
+        }
+        default: lt_set_error("unknown debug buffer %d", what); return -1;
+    }
+    if (rc) { if (tmp) cudaFree(tmp); return rc; }
+    if ((int64_t)bytes > cap) { if (tmp) cudaFree(tmp); lt_set_error("buffer too small: need %zu bytes", bytes); return -1; }
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+    if (tmp) cudaFree(tmp);
+    if (e != cudaSuccess) { lt_set_error("copy failed: %s", cudaGetErrorString(e)); return -2; }
+    return (int64_t)bytes;
+}

@@ -1,0 +1,144 @@
+// Shared declarations of the lane_tracker_b200 CUDA library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/lane_tracker_b200.h"
+
+// ---------------------------------------------------------------------------
+// Plane layout ("pair-packed"): a bird's-eye plane of width W is held as
+// P2 = 32*ceil(W/64) uint32 entries per row; entry x carries pixel (y, x) in its
+// low 16 bits and pixel (y, x + P2) in its high 16 bits.  Two independent image
+// strips ride in the two u16 lanes of every register, which is what
+// VIMNMX.U16x2 / packed adds want, and 32 consecutive entries of either lane
+// are exactly one word of the bit-packed mask.
+// Bit mask layout: row of 2*P2/32 uint32 words, bit (x & 31) of word (x >> 5).
+// ---------------------------------------------------------------------------
+
+#define LT_PIX_CAP_DEFAULT 65536
+
+struct LtDims {
+    int img_w, img_h, bv_w, bv_h;
+    int p2;        // pair-plane width in entries (multiple of 32)
+    int mwords;    // mask words per row = 2*p2/32
+    int roi0, roi1;   // undistorted rows materialised: [roi0, roi1)
+    int ov0, ov1;     // frame rows whose overlay taps can hit the bird's-eye view: [ov0, ov1)
+};
+
+// Per-stream tracking state on the device (lane_tracker.py:139-176).
+struct LtDevState {
+    lt_state s;
+};
+
+struct LtAttemptParams {   // parameters of one attempt, device-visible
+    int filter_type, ksize_r, C_r, ksize_b, C_b, mask_noise, noise_thresh, ksize_noise, C_noise;
+    int window_width, window_height, search_range, no_success_limit, ignore_sides, ignore_bottom, bandwidth;
+    double mu, start_slice, partial;
+};
+
+// Scratch result of one search+fit+validity pass for one stream.
+struct LtAttemptOut {
+    int detected, valid, mode, rank_def;
+    int n[2];
+    double fit[2][3];
+    double diffs[3];
+    double partial;   // the partial that get_poly_points() will see on success
+};
+
+struct lt_handle {
+    lt_config cfg;
+    LtDims d;
+    int S;                       // max streams
+    // shared tables
+    int2* und_map;               // [img_h][img_w]
+    int2* bv_map;                // [bv_h][bv_w]
+    int2* ov_map;                // [img_h][img_w]
+    unsigned short* lab_gamma;   // [256]
+    unsigned short* lab_cbrt;    // [3072]
+    // per-stream buffers
+    uchar4* und_roi;             // [S][roi rows][img_w]
+    uint32_t* planeR; uint32_t* planeB;     // [S][bv_h][p2]
+    uint32_t* tmpR;   uint32_t* tmpB;       // eroded planes / box row sums
+    uint32_t* topR;   uint32_t* topB;       // top-hat planes
+    uint32_t* merged; uint32_t* mask;       // [S][bv_h][mwords]
+    uint32_t* pixels;            // [S][2][pix_cap]
+    int pix_cap;
+    int* pix_counts;             // [S][2]
+    int2* lane_rows;             // [S][bv_h]
+    int* avg_x;                  // [S][2][bv_h]   averaged polylines (state)
+    LtDevState* state;           // [S]
+    LtAttemptOut* att;           // [S]
+    int* retry_list; int* retry_count;      // streams that need attempt 2
+    int* draw_flags;             // [S]
+    int capture;                 // lt_set_capture
+    uint32_t* cap_pixels;        // [2 attempts][S][2][pix_cap]
+    int* cap_counts;             // [2][S][2]
+    int* cap_cents;              // [2][S][2][LT_MAX_LEVELS]
+    int* cap_ncents;             // [2][S][2]
+    uint8_t* scratch_bv;         // lazily allocated [S][bv_h][bv_w][3] for stage calls
+    size_t stream_plane;         // entries per stream in a pair plane
+    size_t stream_mask;          // words per stream in a bit mask
+};
+
+extern "C" int64_t lt_launch_count(void);
+void lt_count_launch(int n = 1);
+void lt_set_error(const char* fmt, ...);
+
+#define LT_CUDA(call)                                                                 \
+    do {                                                                              \
+        cudaError_t _e = (call);                                                      \
+        if (_e != cudaSuccess) {                                                      \
+            lt_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return -2;                                                                \
+        }                                                                             \
+    } while (0)
+
+#define LT_LAUNCH_CHECK()                                                             \
+    do {                                                                              \
+        lt_count_launch();                                                            \
+        cudaError_t _e = cudaGetLastError();                                          \
+        if (_e != cudaSuccess) {                                                      \
+            lt_set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return -3;                                                                \
+        }                                                                             \
+    } while (0)
+
+// ---- stage launchers (defined in the .cu files) -----------------------------
+// `list`/`count` (device pointers, may be NULL) restrict a launch to the streams
+// list[0..*count): CTAs whose stream slot is >= *count exit immediately.
+
+int lt_launch_build_maps(lt_handle* h, cudaStream_t st);
+int lt_launch_undistort(lt_handle* h, const uint8_t* d_frames, int n, cudaStream_t st);
+int lt_launch_warp(lt_handle* h, uint8_t* d_bv_rgb, int n, cudaStream_t st);
+int lt_launch_planes_from_bv(lt_handle* h, const uint8_t* d_bv_rgb, int n, cudaStream_t st);
+int lt_launch_overlay(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int n, const int* d_draw,
+                      cudaStream_t st);
+
+int lt_launch_filter(lt_handle* h, int n, const LtAttemptParams& p, const int* list, const int* count,
+                     cudaStream_t st);
+int lt_launch_mask_to_u8(lt_handle* h, const uint32_t* bits, uint8_t* d_mask, int n, cudaStream_t st);
+int lt_launch_u8_to_mask(lt_handle* h, const uint8_t* d_mask, uint32_t* bits, int n, cudaStream_t st);
+int lt_launch_plane_to_u8(lt_handle* h, const uint32_t* plane, uint8_t* d_dst, int n, cudaStream_t st);
+
+struct LtSearchArgs {
+    const uint32_t* mask;        // [n][bv_h][mwords]
+    int mode;                    // 0: per-stream from state, 1: force SWS, 2: force band with `coeffs`
+    const double* coeffs;        // [n][2][3] for mode 2
+    uint32_t* pixels; int pix_cap; int* pix_counts;   // optional ordered pixel lists
+    int* centroids; int* ncentroids;                  // optional, SWS
+    LtAttemptOut* att;           // [n] out
+    int do_fit;                  // also fit + validity
+    int by_stream;               // index pixel/centroid outputs by stream id instead of launch slot
+};
+int lt_launch_search(lt_handle* h, int n, const LtAttemptParams& p, const LtSearchArgs& a, const int* list,
+                     const int* count, cudaStream_t st);
+int lt_launch_select_retry(lt_handle* h, int n, int n_tries, cudaStream_t st);
+int lt_launch_update_state(lt_handle* h, int n, lt_result* d_results, int attempts_allowed, cudaStream_t st);
+int lt_launch_fit_pixels(lt_handle* h, const uint32_t* d_pixels, int cap, const int* d_counts, int n,
+                         double* d_fits, cudaStream_t st);
+int lt_launch_validity(lt_handle* h, const double* d_fits, int n, int* d_valid, double* d_diffs, cudaStream_t st);
+int lt_launch_poly_points(lt_handle* h, const double* d_fits, int n, double partial, int* d_x, int* d_counts,
+                          cudaStream_t st);
+int lt_launch_lane_rows(lt_handle* h, const int* d_x, const int* d_counts, int n, cudaStream_t st);
+
+static inline int lt_div_up(int a, int b) { return (a + b - 1) / b; }

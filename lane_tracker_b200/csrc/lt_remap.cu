@@ -1,0 +1,316 @@
+// Remap stage: cv2.undistort + cv2.warpPerspective (lane_tracker.py:832-834) and the
+// overlay of draw_lane (lane_tracker.py:629-662), as fixed-point gather kernels.
+//
+// OpenCV evaluates the source coordinates in fp64, rounds them to 1/32 px (Q5) and
+// interpolates with a Q15 weight table; the coordinate tables depend only on the
+// calibration, so they are built once per handle (kernels below, fp64 with explicit
+// round-to-nearest intrinsics: no FMA contraction, same operation order as OpenCV)
+// and shared by every stream.  Compiled with -fmad=false.
+#include "lt_common.cuh"
+
+// ---------------------------------------------------------------------------
+// coordinate tables
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ double mul64(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add64(double a, double b) { return __dadd_rn(a, b); }
+
+__device__ __forceinline__ int round_sat_i32(double v) {
+    v = fmax(-2147483648.0, fmin(2147483647.0, v));
+    return (int)rint(v);
+}
+
+struct UndistortCoef {
+    double iR[9];
+    double k1, k2, p1, p2, k3, fx, fy, cx, cy;
+};
+
+// cv2.undistort(src, K, D, None, K): Q5 source coordinates of every destination pixel.
+__global__ void k_build_undistort_map(int2* __restrict__ map, int w, int h, UndistortCoef c) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (j >= w || i >= h) return;
+    double di = (double)i, dj = (double)j;
+    double _x = add64(add64(mul64(di, c.iR[1]), c.iR[2]), mul64(dj, c.iR[0]));
+    double _y = add64(add64(mul64(di, c.iR[4]), c.iR[5]), mul64(dj, c.iR[3]));
+    double _w = add64(add64(mul64(di, c.iR[7]), c.iR[8]), mul64(dj, c.iR[6]));
+    double x = __ddiv_rn(_x, _w), y = __ddiv_rn(_y, _w);
+    double x2 = mul64(x, x), y2 = mul64(y, y);
+    double r2 = add64(x2, y2);
+    double _2xy = mul64(mul64(2.0, x), y);
+    double kr = add64(1.0, mul64(add64(mul64(add64(mul64(c.k3, r2), c.k2), r2), c.k1), r2));
+    double xd = add64(add64(mul64(x, kr), mul64(c.p1, _2xy)), mul64(c.p2, add64(r2, mul64(2.0, x2))));
+    double yd = add64(add64(mul64(y, kr), mul64(c.p1, add64(r2, mul64(2.0, y2)))), mul64(c.p2, _2xy));
+    double u = add64(mul64(c.fx, xd), c.cx);
+    double v = add64(mul64(c.fy, yd), c.cy);
+    map[(size_t)i * w + j] = make_int2(round_sat_i32(mul64(u, 32.0)), round_sat_i32(mul64(v, 32.0)));
+}
+
+struct Mat9 { double m[9]; };
+
+// cv2.warpPerspective(src, M, (dw, dh)): `m` is inv(M); 64-column block origin as in OpenCV.
+__global__ void k_build_perspective_map(int2* __restrict__ map, int dw, int dh, Mat9 mm) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= dw || y >= dh) return;
+    const double* m = mm.m;
+    double xb = (double)((x >> 6) << 6), x1 = (double)(x & 63), dy = (double)y;
+    double X0 = add64(add64(mul64(m[0], xb), mul64(m[1], dy)), m[2]);
+    double Y0 = add64(add64(mul64(m[3], xb), mul64(m[4], dy)), m[5]);
+    double W0 = add64(add64(mul64(m[6], xb), mul64(m[7], dy)), m[8]);
+    double W = add64(W0, mul64(m[6], x1));
+    W = (W != 0.0) ? __ddiv_rn(32.0, W) : 0.0;
+    double fX = mul64(add64(X0, mul64(m[0], x1)), W);
+    double fY = mul64(add64(Y0, mul64(m[3], x1)), W);
+    map[(size_t)y * dw + x] = make_int2(round_sat_i32(fX), round_sat_i32(fY));
+}
+
+static void invert3x3(const double* a, double* o) {
+    // adjugate / determinant (what cv::invert does for 3x3)
+    double d = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) +
+               a[2] * (a[3] * a[7] - a[4] * a[6]);
+    d = (d != 0.0) ? 1.0 / d : 0.0;
+    o[0] = (a[4] * a[8] - a[5] * a[7]) * d;
+    o[1] = (a[2] * a[7] - a[1] * a[8]) * d;
+    o[2] = (a[1] * a[5] - a[2] * a[4]) * d;
+    o[3] = (a[5] * a[6] - a[3] * a[8]) * d;
+    o[4] = (a[0] * a[8] - a[2] * a[6]) * d;
+    o[5] = (a[2] * a[3] - a[0] * a[5]) * d;
+    o[6] = (a[3] * a[7] - a[4] * a[6]) * d;
+    o[7] = (a[1] * a[6] - a[0] * a[7]) * d;
+    o[8] = (a[0] * a[4] - a[1] * a[3]) * d;
+}
+
+int lt_launch_build_maps(lt_handle* h, cudaStream_t st) {
+    const lt_config& c = h->cfg;
+    UndistortCoef uc;
+    invert3x3(c.cam_matrix, uc.iR);
+    uc.k1 = c.dist_coeffs[0]; uc.k2 = c.dist_coeffs[1]; uc.p1 = c.dist_coeffs[2];
+    uc.p2 = c.dist_coeffs[3]; uc.k3 = c.dist_coeffs[4];
+    uc.fx = c.cam_matrix[0]; uc.fy = c.cam_matrix[4]; uc.cx = c.cam_matrix[2]; uc.cy = c.cam_matrix[5];
+    dim3 b(256), g1(lt_div_up(c.img_w, 256), c.img_h), g2(lt_div_up(c.bv_w, 256), c.bv_h);
+    k_build_undistort_map<<<g1, b, 0, st>>>(h->und_map, c.img_w, c.img_h, uc);
+    LT_LAUNCH_CHECK();
+    Mat9 mi;
+    invert3x3(c.M, mi.m);
+    k_build_perspective_map<<<g2, b, 0, st>>>(h->bv_map, c.bv_w, c.bv_h, mi);
+    LT_LAUNCH_CHECK();
+    invert3x3(c.Minv, mi.m);
+    k_build_perspective_map<<<g1, b, 0, st>>>(h->ov_map, c.img_w, c.img_h, mi);
+    LT_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// bilinear sampling helpers (OpenCV remap, INTER_LINEAR, BORDER_CONSTANT 0)
+// ---------------------------------------------------------------------------
+
+struct Tap4 {
+    int sx, sy, w00, w01, w10, w11;
+};
+
+__device__ __forceinline__ Tap4 make_taps(int2 q) {
+    Tap4 t;
+    int sx = q.x >> 5, sy = q.y >> 5;
+    t.sx = max(-32768, min(32767, sx));
+    t.sy = max(-32768, min(32767, sy));
+    int fx = q.x & 31, fy = q.y & 31;
+    t.w00 = (32 - fx) * (32 - fy);
+    t.w01 = fx * (32 - fy);
+    t.w10 = (32 - fx) * fy;
+    t.w11 = fx * fy;
+    return t;
+}
+
+// ---------------------------------------------------------------------------
+// undistort: frame rows -> undistorted ROI rows [roi0, roi1), RGBX
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t load_rgb(const uint8_t* __restrict__ img, int w, int h, int y, int x) {
+    if ((unsigned)y >= (unsigned)h || (unsigned)x >= (unsigned)w) return 0u;
+    const uint8_t* p = img + ((size_t)y * w + x) * 3;
+    return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+}
+
+__device__ __forceinline__ uint32_t blend_rgb(uint32_t a, uint32_t b, uint32_t c, uint32_t d, const Tap4& t) {
+    uint32_t out = 0;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        int s = 8 * ch;
+        int v = (int)((a >> s) & 255) * t.w00 + (int)((b >> s) & 255) * t.w01 +
+                (int)((c >> s) & 255) * t.w10 + (int)((d >> s) & 255) * t.w11;
+        out |= (uint32_t)((v + 512) >> 10) << s;
+    }
+    return out;
+}
+
+__global__ void __launch_bounds__(256)
+k_undistort_roi(const uint8_t* __restrict__ frames, uchar4* __restrict__ und, const int2* __restrict__ map,
+                LtDims d) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = d.roi0 + blockIdx.y;
+    int s = blockIdx.z;
+    if (j >= d.img_w) return;
+    const uint8_t* img = frames + (size_t)s * d.img_w * d.img_h * 3;
+    Tap4 t = make_taps(__ldg(&map[(size_t)i * d.img_w + j]));
+    uint32_t a = load_rgb(img, d.img_w, d.img_h, t.sy, t.sx);
+    uint32_t b = load_rgb(img, d.img_w, d.img_h, t.sy, t.sx + 1);
+    uint32_t c = load_rgb(img, d.img_w, d.img_h, t.sy + 1, t.sx);
+    uint32_t e = load_rgb(img, d.img_w, d.img_h, t.sy + 1, t.sx + 1);
+    uint32_t o = blend_rgb(a, b, c, e, t);
+    und[((size_t)s * (d.roi1 - d.roi0) + (i - d.roi0)) * d.img_w + j] =
+        make_uchar4(o & 255, (o >> 8) & 255, (o >> 16) & 255, 0);
+}
+
+int lt_launch_undistort(lt_handle* h, const uint8_t* d_frames, int n, cudaStream_t st) {
+    const LtDims& d = h->d;
+    dim3 g(lt_div_up(d.img_w, 256), d.roi1 - d.roi0, n);
+    k_undistort_roi<<<g, 256, 0, st>>>(d_frames, h->und_roi, h->und_map, d);
+    LT_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// warp to the bird's-eye view, emitting the two planes the filter consumes:
+// RGB R and CIE-Lab b (lane_tracker.py:207-208), pair-packed
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ int lab_b(uint32_t rgb, const unsigned short* __restrict__ g,
+                                     const unsigned short* __restrict__ cb) {
+    int R = __ldg(&g[rgb & 255]), G = __ldg(&g[(rgb >> 8) & 255]), B = __ldg(&g[(rgb >> 16) & 255]);
+    int fY = __ldg(&cb[(871 * R + 2929 * G + 296 * B + 2048) >> 12]);
+    int fZ = __ldg(&cb[(73 * R + 448 * G + 3575 * B + 2048) >> 12]);
+    int b = (200 * (fY - fZ) + 128 * 32768 + 16384) >> 15;
+    return max(0, min(255, b));
+}
+
+__device__ __forceinline__ uint32_t und_tap(const uchar4* __restrict__ und, const LtDims& d, int y, int x) {
+    if ((unsigned)y >= (unsigned)d.img_h || (unsigned)x >= (unsigned)d.img_w) return 0u;   // BORDER_CONSTANT
+    if (y < d.roi0 || y >= d.roi1) return 0u;   // cannot happen: the ROI covers every in-image tap
+    uchar4 v = __ldg(&und[(size_t)(y - d.roi0) * d.img_w + x]);
+    return (uint32_t)v.x | ((uint32_t)v.y << 8) | ((uint32_t)v.z << 16);
+}
+
+__global__ void __launch_bounds__(256)
+k_warp_planes(const uchar4* __restrict__ und_all, const int2* __restrict__ map, uint32_t* __restrict__ planeR,
+              uint32_t* __restrict__ planeB, uint8_t* __restrict__ bv_rgb,
+              const unsigned short* __restrict__ g, const unsigned short* __restrict__ cb, LtDims d) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y, s = blockIdx.z;
+    if (x >= d.p2) return;
+    const uchar4* und = und_all + (size_t)s * (d.roi1 - d.roi0) * d.img_w;
+    uint32_t r2 = 0, b2 = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        int px = x + half * d.p2;
+        if (px < d.bv_w) {
+            Tap4 t = make_taps(__ldg(&map[(size_t)y * d.bv_w + px]));
+            uint32_t a = und_tap(und, d, t.sy, t.sx), b = und_tap(und, d, t.sy, t.sx + 1);
+            uint32_t c = und_tap(und, d, t.sy + 1, t.sx), e = und_tap(und, d, t.sy + 1, t.sx + 1);
+            uint32_t o = blend_rgb(a, b, c, e, t);
+            r2 |= (o & 255) << (16 * half);
+            b2 |= (uint32_t)lab_b(o, g, cb) << (16 * half);
+            if (bv_rgb) {
+                uint8_t* p = bv_rgb + (((size_t)s * d.bv_h + y) * d.bv_w + px) * 3;
+                p[0] = o & 255; p[1] = (o >> 8) & 255; p[2] = (o >> 16) & 255;
+            }
+        }
+    }
+    size_t o = ((size_t)s * d.bv_h + y) * d.p2 + x;
+    planeR[o] = r2;
+    planeB[o] = b2;
+}
+
+int lt_launch_warp(lt_handle* h, uint8_t* d_bv_rgb, int n, cudaStream_t st) {
+    const LtDims& d = h->d;
+    dim3 g(lt_div_up(d.p2, 256), d.bv_h, n);
+    k_warp_planes<<<g, 256, 0, st>>>(h->und_roi, h->bv_map, h->planeR, h->planeB, d_bv_rgb, h->lab_gamma,
+                                     h->lab_cbrt, d);
+    LT_LAUNCH_CHECK();
+    return 0;
+}
+
+// planes from a caller-supplied bird's-eye RGB image (filter_lane_points API, lane_tracker.py:207-208)
+__global__ void __launch_bounds__(256)
+k_planes_from_bv(const uint8_t* __restrict__ bv_rgb, uint32_t* __restrict__ planeR, uint32_t* __restrict__ planeB,
+                 const unsigned short* __restrict__ g, const unsigned short* __restrict__ cb, LtDims d) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y, s = blockIdx.z;
+    if (x >= d.p2) return;
+    uint32_t r2 = 0, b2 = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        int px = x + half * d.p2;
+        if (px < d.bv_w) {
+            const uint8_t* p = bv_rgb + (((size_t)s * d.bv_h + y) * d.bv_w + px) * 3;
+            uint32_t o = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+            r2 |= (o & 255) << (16 * half);
+            b2 |= (uint32_t)lab_b(o, g, cb) << (16 * half);
+        }
+    }
+    size_t o = ((size_t)s * d.bv_h + y) * d.p2 + x;
+    planeR[o] = r2;
+    planeB[o] = b2;
+}
+
+int lt_launch_planes_from_bv(lt_handle* h, const uint8_t* d_bv_rgb, int n, cudaStream_t st) {
+    const LtDims& d = h->d;
+    dim3 g(lt_div_up(d.p2, 256), d.bv_h, n);
+    k_planes_from_bv<<<g, 256, 0, st>>>(d_bv_rgb, h->planeR, h->planeB, h->lab_gamma, h->lab_cbrt, d);
+    LT_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// overlay: fillPoly canvas (row spans) -> warpPerspective(Minv) -> addWeighted(1, 0.3)
+// Only the G channel can change: the canvas is (0,255,0) (lane_tracker.py:647).
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ int lane_tap(const int2* __restrict__ rows, const LtDims& d, int y, int x) {
+    if ((unsigned)y >= (unsigned)d.bv_h || (unsigned)x >= (unsigned)d.bv_w) return 0;
+    int2 r = __ldg(&rows[y]);
+    return (x >= r.x && x <= r.y) ? 255 : 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_overlay(const uint8_t* __restrict__ frames, uint8_t* __restrict__ out, const int2* __restrict__ map,
+          const int2* __restrict__ lane_rows, const int* __restrict__ draw, LtDims d) {
+    // one thread = 4 pixels = 12 bytes (three aligned 32-bit words); img_w % 4 == 0 is checked at create
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y, s = blockIdx.z;
+    int qw = d.img_w >> 2;
+    if (q >= qw) return;
+    size_t base = (((size_t)s * d.img_h + y) * d.img_w + (size_t)q * 4) * 3;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(frames + base);
+    uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+    if (draw[s] && y >= d.ov0 && y < d.ov1) {
+        const int2* rows = lane_rows + (size_t)s * d.bv_h;
+        uint32_t gch[4] = {(w0 >> 8) & 255, w1 & 255, (w1 >> 24) & 255, (w2 >> 16) & 255};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            Tap4 t = make_taps(__ldg(&map[(size_t)y * d.img_w + q * 4 + k]));
+            int v = lane_tap(rows, d, t.sy, t.sx) * t.w00 + lane_tap(rows, d, t.sy, t.sx + 1) * t.w01 +
+                    lane_tap(rows, d, t.sy + 1, t.sx) * t.w10 + lane_tap(rows, d, t.sy + 1, t.sx + 1) * t.w11;
+            v = (v + 512) >> 10;
+            if (v) {
+                // cv2.addWeighted(img,1,lane,0.3,0): float32 a + b*0.3f, round half to even, saturate
+                float f = __fadd_rn((float)gch[k], __fmul_rn((float)v, 0.3f));
+                gch[k] = (uint32_t)min(255, __float2int_rn(f));
+            }
+        }
+        w0 = (w0 & 0xFFFF00FFu) | (gch[0] << 8);
+        w1 = (w1 & 0x00FFFF00u) | gch[1] | (gch[2] << 24);
+        w2 = (w2 & 0xFF00FFFFu) | (gch[3] << 16);
+    }
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + base);
+    dst[0] = w0; dst[1] = w1; dst[2] = w2;
+}
+
+int lt_launch_overlay(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int n, const int* d_draw,
+                      cudaStream_t st) {
+    const LtDims& d = h->d;
+    dim3 g(lt_div_up(d.img_w / 4, 256), d.img_h, n);
+    k_overlay<<<g, 256, 0, st>>>(d_frames, d_out, h->ov_map, h->lane_rows, d_draw, d);
+    LT_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,555 @@
+"""Host-side mirror of the reference's ``LaneTracker`` (lane_tracker.py:85-1209).
+
+``LaneTracker``         drop-in for the reference class: same constructor, same methods, NumPy in /
+                        NumPy out, one stream.  Every method runs on the GPU through the C ABI.
+``BatchedLaneTracker``  the throughput interface: S independent streams per call on device-resident
+                        ``torch`` tensors, per-stream tracking state held in device memory.
+
+PyTorch is used for device memory, pinned staging buffers and CUDA streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import LT_MAX_LEVELS, check, lt_config, lt_params, lt_result, lt_state
+
+RESULT_DTYPE = np.dtype(lt_result)
+
+_FILTER_TYPES = {"bilateral": 0, "neighborhood": 1}
+
+# keyword defaults of the reference methods
+PROCESS_DEFAULTS = dict(
+    ksize_r=15, C_r=8, ksize_b=35, C_b=5, filter_type="bilateral", mask_noise=False, noise_thresh=140,
+    ksize_noise=65, C_noise=10, window_width=30, window_height=40, search_range=20, mu=0.1,
+    no_success_limit=8, start_slice=0.25, ignore_sides=360, ignore_bottom=30, bandwidth=25, partial=1.0,
+    n_tries=2)
+
+
+def _filter_code(filter_type):
+    if filter_type not in _FILTER_TYPES:
+        # same exception type and message as lane_tracker.py:219-220
+        raise ValueError("Unexpected filter mode. Expected modes are 'bilateral' or 'neighborhood'.")
+    return _FILTER_TYPES[filter_type]
+
+
+def make_params(**kw):
+    p = dict(PROCESS_DEFAULTS)
+    unknown = set(kw) - set(p)
+    if unknown:
+        raise TypeError("process() got unexpected keyword arguments %s" % sorted(unknown))
+    p.update(kw)
+    out = lt_params()
+    out.filter_type = _filter_code(p.pop("filter_type"))
+    out.mask_noise = int(bool(p.pop("mask_noise")))
+    for k, v in p.items():
+        setattr(out, k, float(v) if k in ("mu", "start_slice", "partial") else int(v))
+    return out
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class BatchedLaneTracker:
+    """S independent lane trackers advanced by one frame each per ``process`` call."""
+
+    def __init__(self, n_streams, img_size, warped_size, cam_matrix, dist_coeffs, warp_matrices,
+                 mpp_conversion, n_fail=8, n_reset=4, n_average=2, print_frame_count=False, device=None):
+        self._h = None
+        if not torch.cuda.is_available():
+            raise _lib.LaneTrackerError("lane_tracker_b200 needs a CUDA device; there is no CPU path")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else
+                                   (device if isinstance(device, int) else torch.device(device).index or 0))
+        self.n_streams = int(n_streams)
+        self.img_size = tuple(int(v) for v in img_size)
+        self.warped_size = tuple(int(v) for v in warped_size)
+        self.n_fail, self.n_reset, self.n_average = int(n_fail), int(n_reset), int(n_average)
+        cfg = lt_config()
+        cfg.img_w, cfg.img_h = self.img_size
+        cfg.bv_w, cfg.bv_h = self.warped_size
+        cfg.cam_matrix[:] = [float(v) for v in np.asarray(cam_matrix, dtype=np.float64).reshape(9)]
+        d = np.asarray(dist_coeffs, dtype=np.float64).ravel()
+        if d.size > 5 and np.any(d[5:] != 0):
+            raise ValueError("only the 5-coefficient distortion model (k1,k2,p1,p2,k3) is supported")
+        cfg.dist_coeffs[:] = [float(v) for v in np.concatenate([d[:5], np.zeros(max(0, 5 - d.size))])]
+        cfg.M[:] = [float(v) for v in np.asarray(warp_matrices[0], dtype=np.float64).reshape(9)]
+        cfg.Minv[:] = [float(v) for v in np.asarray(warp_matrices[1], dtype=np.float64).reshape(9)]
+        cfg.mppv, cfg.mpph = float(mpp_conversion[0]), float(mpp_conversion[1])
+        cfg.n_fail, cfg.n_reset, cfg.n_average = self.n_fail, self.n_reset, self.n_average
+        cfg.print_frame_count = int(bool(print_frame_count))
+        cfg.max_streams = self.n_streams
+        cfg.device = self.device.index
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib.lt_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        S = self.n_streams
+        self._results_dev = torch.zeros(S * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
+        self._results_host = torch.zeros(S * RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        geo = np.zeros(6, dtype=np.int32)
+        check(self.lib.lt_debug_read(self._h, 10, 0, geo.ctypes.data_as(C.c_void_p), geo.nbytes))
+        self.geometry = dict(roi_rows=(int(geo[0]), int(geo[1])), overlay_rows=(int(geo[2]), int(geo[3])),
+                             plane_width=int(geo[4]), mask_words=int(geo[5]))
+
+    # -- lifetime -----------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.lt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self, ids=None):
+        if ids is None:
+            check(self.lib.lt_reset(self._h, None, 0))
+        else:
+            arr = (C.c_int32 * len(ids))(*[int(i) for i in ids])
+            check(self.lib.lt_reset(self._h, arr, len(ids)))
+
+    def set_capture(self, enable=True):
+        check(self.lib.lt_set_capture(self._h, int(bool(enable))))
+
+    # -- hot path -----------------------------------------------------------
+    def _check_frames(self, frames):
+        w, h = self.img_size
+        if not (isinstance(frames, torch.Tensor) and frames.is_cuda and frames.dtype == torch.uint8 and
+                frames.is_contiguous() and frames.dim() == 4 and tuple(frames.shape[1:]) == (h, w, 3)):
+            raise ValueError("frames must be a contiguous CUDA uint8 tensor [n, %d, %d, 3]" % (h, w))
+        if frames.shape[0] < 1 or frames.shape[0] > self.n_streams:
+            raise ValueError("got %d frames for %d streams" % (frames.shape[0], self.n_streams))
+        return int(frames.shape[0])
+
+    def process_async(self, frames, out=None, params=None, **kw):
+        """Enqueue one frame per stream on the current CUDA stream; returns the device result buffer.
+
+        frames: uint8 CUDA tensor [n, H, W, 3] (RGB).  out: same shape or None (fits-only mode)."""
+        n = self._check_frames(frames)
+        if out is not None and (out.shape != frames.shape or out.dtype != torch.uint8 or not out.is_cuda or
+                                not out.is_contiguous()):
+            raise ValueError("out must match frames")
+        p = params if params is not None else make_params(**kw)
+        check(self.lib.lt_process(self._h, _ptr(frames), _ptr(out), n, C.byref(p), _ptr(self._results_dev),
+                                  _stream_ptr(self.device)))
+        return n
+
+    def fetch_results(self, n=None):
+        """Copy the last results to pinned host memory and return them as a structured array."""
+        n = self.n_streams if n is None else n
+        nbytes = n * RESULT_DTYPE.itemsize
+        self._results_host[:nbytes].copy_(self._results_dev[:nbytes], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._results_host[:nbytes].numpy().view(RESULT_DTYPE).copy()
+
+    def process(self, frames, out=None, params=None, **kw):
+        n = self.process_async(frames, out, params, **kw)
+        return self.fetch_results(n)
+
+    # -- stage methods (device tensors) ---------------------------------------
+    def remap(self, frames, want_bv=True):
+        n = self._check_frames(frames)
+        bw, bh = self.warped_size
+        bv = torch.empty((n, bh, bw, 3), dtype=torch.uint8, device=self.device) if want_bv else None
+        check(self.lib.lt_remap(self._h, _ptr(frames), _ptr(bv), n, _stream_ptr(self.device)))
+        return bv
+
+    def filter_lane_points(self, bv, filter_type="bilateral", ksize_r=25, C_r=8, ksize_b=35, C_b=5,
+                           mask_noise=False, ksize_noise=65, C_noise=10, noise_thresh=135):
+        """bv: uint8 CUDA [n, bh, bw, 3] or None (reuse the planes of the last remap)."""
+        bw, bh = self.warped_size
+        n = self.n_streams if bv is None else int(bv.shape[0])
+        if bv is not None and not (bv.is_cuda and bv.dtype == torch.uint8 and bv.is_contiguous() and
+                                   tuple(bv.shape[1:]) == (bh, bw, 3)):
+            raise ValueError("bv must be a contiguous CUDA uint8 tensor [n, %d, %d, 3]" % (bh, bw))
+        mask = torch.empty((n, bh, bw), dtype=torch.uint8, device=self.device)
+        check(self.lib.lt_filter_lane_points(self._h, _ptr(bv), _ptr(mask), n, _filter_code(filter_type),
+                                             int(ksize_r), int(C_r), int(ksize_b), int(C_b), int(bool(mask_noise)),
+                                             int(ksize_noise), int(C_noise), int(noise_thresh),
+                                             _stream_ptr(self.device)))
+        return mask
+
+    def _decode_pixels(self, pixels, counts, n):
+        pix = pixels.cpu().numpy().view(np.uint32)
+        cnt = counts.cpu().numpy().reshape(n, 2)
+        out = []
+        for s in range(n):
+            sides = []
+            for side in range(2):
+                k = int(cnt[s, side])
+                if k > pix.shape[2]:
+                    raise _lib.LaneTrackerError("pixel capacity exceeded: %d > %d" % (k, pix.shape[2]))
+                v = pix[s, side, :k]
+                sides.append(((v >> 16).astype(np.int64), (v & 0xFFFF).astype(np.int64) - 32768))
+            out.append(sides)
+        return out, cnt
+
+    def sliding_window_search(self, mask, window_width, window_height, search_range, mu, no_success_limit,
+                              start_slice=0.25, ignore_sides=360, ignore_bottom=30, partial=1, capacity=65536):
+        n = int(mask.shape[0])
+        pixels = torch.empty((n, 2, capacity), dtype=torch.int32, device=self.device)
+        counts = torch.zeros((n, 2), dtype=torch.int32, device=self.device)
+        cents = torch.zeros((n, 2, LT_MAX_LEVELS), dtype=torch.int32, device=self.device)
+        ncents = torch.zeros((n, 2), dtype=torch.int32, device=self.device)
+        det = torch.zeros((n,), dtype=torch.int32, device=self.device)
+        check(self.lib.lt_sliding_window_search(
+            self._h, _ptr(mask), n, int(window_width), int(window_height), int(search_range), float(mu),
+            int(no_success_limit), float(start_slice), int(ignore_sides), int(ignore_bottom), float(partial),
+            _ptr(pixels), capacity, _ptr(counts), _ptr(cents), _ptr(ncents), _ptr(det), _stream_ptr(self.device)))
+        px, _ = self._decode_pixels(pixels, counts, n)
+        c = cents.cpu().numpy()
+        nc = ncents.cpu().numpy()
+        cent_lists = [[list(map(int, c[s, side, :nc[s, side]])) for side in range(2)] for s in range(n)]
+        return px, cent_lists, det.cpu().numpy().astype(bool)
+
+    def band_search(self, mask, coeffs, bandwidth, ignore_bottom=30, partial=1, capacity=65536):
+        n = int(mask.shape[0])
+        cf = torch.as_tensor(np.asarray(coeffs, dtype=np.float64).reshape(n, 2, 3)).to(self.device)
+        pixels = torch.empty((n, 2, capacity), dtype=torch.int32, device=self.device)
+        counts = torch.zeros((n, 2), dtype=torch.int32, device=self.device)
+        det = torch.zeros((n,), dtype=torch.int32, device=self.device)
+        check(self.lib.lt_band_search(self._h, _ptr(mask), n, _ptr(cf), int(bandwidth), int(ignore_bottom),
+                                      float(partial), _ptr(pixels), capacity, _ptr(counts), _ptr(det),
+                                      _stream_ptr(self.device)))
+        px, _ = self._decode_pixels(pixels, counts, n)
+        return px, det.cpu().numpy().astype(bool)
+
+    def fit_poly(self, pixel_sets):
+        """pixel_sets: per stream [(ly, lx), (ry, rx)] integer arrays -> float64 [n, 2, 3]."""
+        n = len(pixel_sets)
+        cap = max(1, max(len(side[0]) for ps in pixel_sets for side in ps))
+        buf = np.zeros((n, 2, cap), dtype=np.uint32)
+        cnt = np.zeros((n, 2), dtype=np.int32)
+        for s, ps in enumerate(pixel_sets):
+            for side, (ys, xs) in enumerate(ps):
+                ys = np.asarray(ys, dtype=np.int64)
+                xs = np.asarray(xs, dtype=np.int64)
+                buf[s, side, :len(ys)] = ((ys << 16) | (xs + 32768)).astype(np.uint32)
+                cnt[s, side] = len(ys)
+        d_buf = torch.as_tensor(buf.view(np.int32)).to(self.device)
+        d_cnt = torch.as_tensor(cnt).to(self.device)
+        fits = torch.zeros((n, 2, 3), dtype=torch.float64, device=self.device)
+        check(self.lib.lt_fit_poly(self._h, _ptr(d_buf), cap, _ptr(d_cnt), n, _ptr(fits), _stream_ptr(self.device)))
+        return fits.cpu().numpy()
+
+    def check_validity(self, fits):
+        f = torch.as_tensor(np.asarray(fits, dtype=np.float64).reshape(-1, 2, 3)).to(self.device)
+        n = int(f.shape[0])
+        valid = torch.zeros((n,), dtype=torch.int32, device=self.device)
+        diffs = torch.zeros((n, 3), dtype=torch.float64, device=self.device)
+        check(self.lib.lt_check_validity(self._h, _ptr(f), n, _ptr(valid), _ptr(diffs), _stream_ptr(self.device)))
+        return valid.cpu().numpy().astype(bool), diffs.cpu().numpy()
+
+    def get_poly_points(self, fits, partial=1.0):
+        f = torch.as_tensor(np.asarray(fits, dtype=np.float64).reshape(-1, 2, 3)).to(self.device)
+        n = int(f.shape[0])
+        bh = self.warped_size[1]
+        xs = torch.zeros((n, 2, bh), dtype=torch.int32, device=self.device)
+        cnt = torch.zeros((n, 2), dtype=torch.int32, device=self.device)
+        check(self.lib.lt_get_poly_points(self._h, _ptr(f), n, float(partial), _ptr(xs), _ptr(cnt),
+                                          _stream_ptr(self.device)))
+        return xs, cnt
+
+    def draw_lane(self, frames, xs, counts):
+        n = self._check_frames(frames)
+        out = torch.empty_like(frames)
+        check(self.lib.lt_draw_lane(self._h, _ptr(frames), _ptr(out), n, _ptr(xs), _ptr(counts),
+                                    _stream_ptr(self.device)))
+        return out
+
+    # -- state / debug -------------------------------------------------------
+    def get_state(self, stream_id=0):
+        st = lt_state()
+        bh = self.warped_size[1]
+        lx = np.zeros(bh, dtype=np.int32)
+        rx = np.zeros(bh, dtype=np.int32)
+        check(self.lib.lt_get_state(self._h, int(stream_id), C.byref(st), lx.ctypes.data_as(C.c_void_p),
+                                    rx.ctypes.data_as(C.c_void_p)))
+        return st, lx[:st.n_left_avg].copy(), rx[:st.n_right_avg].copy()
+
+    def set_state(self, stream_id, st, left_avg_x=None, right_avg_x=None):
+        bh = self.warped_size[1]
+        lx = np.zeros(bh, dtype=np.int32)
+        rx = np.zeros(bh, dtype=np.int32)
+        if left_avg_x is not None:
+            lx[:len(left_avg_x)] = left_avg_x
+        if right_avg_x is not None:
+            rx[:len(right_avg_x)] = right_avg_x
+        check(self.lib.lt_set_state(self._h, int(stream_id), C.byref(st), lx.ctypes.data_as(C.c_void_p),
+                                    rx.ctypes.data_as(C.c_void_p)))
+
+    def read_capture(self, stream_id, attempt):
+        """Ordered pixel sets [(ly, lx), (ry, rx)] and centroid lists of one attempt of the last process()."""
+        cap = 65536
+        sides, cents = [], []
+        for side in range(2):
+            buf = np.zeros(cap, dtype=np.uint32)
+            cnt = C.c_int32(0)
+            cbuf = np.zeros(LT_MAX_LEVELS, dtype=np.int32)
+            ncent = C.c_int32(0)
+            check(self.lib.lt_read_capture(self._h, int(stream_id), int(attempt), side,
+                                           buf.ctypes.data_as(C.c_void_p), cap, C.byref(cnt),
+                                           cbuf.ctypes.data_as(C.c_void_p), C.byref(ncent)))
+            if cnt.value > cap:
+                raise _lib.LaneTrackerError("pixel capacity exceeded")
+            v = buf[:cnt.value]
+            sides.append(((v >> 16).astype(np.int64), (v & 0xFFFF).astype(np.int64) - 32768))
+            cents.append([int(c) for c in cbuf[:ncent.value]])
+        return sides, cents
+
+    _DEBUG = dict(undistort_map=0, bv_map=1, overlay_map=2, r_plane=3, b_plane=4, r_tophat=5, b_tophat=6,
+                  mask=7, merged=8, lane_rows=9)
+
+    def debug_read(self, what, stream_id=0):
+        code = self._DEBUG[what]
+        w, h = self.img_size
+        bw, bh = self.warped_size
+        if code in (0, 2):
+            out = np.zeros((h, w, 2), dtype=np.int32)
+        elif code == 1:
+            out = np.zeros((bh, bw, 2), dtype=np.int32)
+        elif code == 9:
+            out = np.zeros((bh, 2), dtype=np.int32)
+        else:
+            out = np.zeros((bh, bw), dtype=np.uint8)
+        check(self.lib.lt_debug_read(self._h, code, int(stream_id), out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+
+class LaneTracker:
+    """Drop-in for the reference ``LaneTracker`` (same constructor, lane_tracker.py:101).
+
+    NumPy arrays in, NumPy arrays out; every computation runs on the GPU.  Differences from the
+    reference, all documented in DESIGN.md: the putText overlays are not rendered, the caller's
+    ``img`` is never modified, and the debug views (``visualize_search``, ``split_view``) raise
+    ``NotImplementedError``.
+    """
+
+    def __init__(self, img_size, warped_size, cam_matrix, dist_coeffs, warp_matrices, mpp_conversion,
+                 n_fail=8, n_reset=4, n_average=2, print_frame_count=False, device=None):
+        self.img_size = img_size
+        self.warped_size = warped_size
+        self.cam_matrix = cam_matrix
+        self.dist_coeffs = dist_coeffs
+        self.M, self.Minv = warp_matrices[0], warp_matrices[1]
+        self.mppv, self.mpph = mpp_conversion[0], mpp_conversion[1]
+        self.n_reset, self.n_fail, self.n_average = n_reset, n_fail, n_average
+        self.print_frame_count = print_frame_count
+        self._bt = BatchedLaneTracker(1, img_size, warped_size, cam_matrix, dist_coeffs, warp_matrices,
+                                      mpp_conversion, n_fail, n_reset, n_average, print_frame_count, device)
+        self._bt.set_capture(True)
+        dev = self._bt.device
+        w, h = self._bt.img_size
+        self._in_host = torch.empty((1, h, w, 3), dtype=torch.uint8).pin_memory()
+        self._out_host = torch.empty((1, h, w, 3), dtype=torch.uint8).pin_memory()
+        self._in_dev = torch.empty((1, h, w, 3), dtype=torch.uint8, device=dev)
+        self._out_dev = torch.empty((1, h, w, 3), dtype=torch.uint8, device=dev)
+        # state attributes, lane_tracker.py:139-176
+        self.last_detection = n_reset + 1
+        self.detected_pixels = False
+        self.valid_lane_lines = False
+        self.left_fit_coeffs, self.right_fit_coeffs = [], []
+        self.last_left_coeffs = self.last_right_coeffs = None
+        self.left_avg_coeffs = self.right_avg_coeffs = None
+        self.left_avg_y = np.array([])
+        self.left_avg_x = np.array([])
+        self.right_avg_y = np.array([])
+        self.right_avg_x = np.array([])
+        self.left_y = self.left_x = self.right_y = self.right_x = None
+        self.left_window_centroids = self.right_window_centroids = None
+        self.left_curve_radius = self.right_curve_radius = None
+        self.average_curve_radius = None
+        self.average_curve_radii = []
+        self.eccentricity = None
+        self.counter = 0
+        self.success = 0
+        self.last_result = None
+
+    def get_success_ratio(self):
+        return self.success / self.counter, self.success, self.counter
+
+    # ------------------------------------------------------------ helpers
+    def _upload(self, arr, shape):
+        a = np.ascontiguousarray(arr, dtype=np.uint8)
+        if a.shape != shape:
+            raise ValueError("expected an array of shape %s, got %s" % (shape, a.shape))
+        return torch.from_numpy(a).to(self._bt.device)
+
+    def _sync_state(self, res):
+        st, lx, rx = self._bt.get_state(0)
+        bh = self._bt.warped_size[1]
+        self.last_detection = int(st.last_detection)
+        self.counter, self.success = int(st.counter), int(st.success)
+        self.left_fit_coeffs = [np.array([]) if st.ring_empty[i] else np.array(st.ring_left[i][:])
+                                for i in range(st.ring_len)]
+        self.right_fit_coeffs = [np.array([]) if st.ring_empty[i] else np.array(st.ring_right[i][:])
+                                 for i in range(st.ring_len)]
+        if st.has_last:
+            self.last_left_coeffs = np.array(st.last_left[:])
+            self.last_right_coeffs = np.array(st.last_right[:])
+        if st.has_avg:
+            self.left_avg_coeffs = np.array(st.left_avg[:])
+            self.right_avg_coeffs = np.array(st.right_avg[:])
+            self.left_avg_x = lx.astype(np.int64)
+            self.right_avg_x = rx.astype(np.int64)
+            self.left_avg_y = np.arange(bh - len(lx), bh, dtype=np.int64)
+            self.right_avg_y = np.arange(bh - len(rx), bh, dtype=np.int64)
+            self.average_curve_radius = int(st.average_curve_radius)
+            self.eccentricity = float(st.eccentricity)
+        self.average_curve_radii = [int(st.radii[i]) for i in range(st.radii_len)]
+        if res is not None:
+            self.detected_pixels = bool(res["detected_pixels"])
+            self.valid_lane_lines = bool(res["valid_lane_lines"])
+            if res["valid_lane_lines"]:
+                self.left_curve_radius = int(res["left_curve_radius"])
+                self.right_curve_radius = int(res["right_curve_radius"])
+            # pixel sets / centroids are only replaced by a search that found pixels on both sides
+            for attempt in range(int(res["attempts"])):
+                det = res["first_detected"] if attempt == 0 else res["detected_pixels"]
+                if int(res["attempts"]) == 1:
+                    det = res["detected_pixels"]
+                if det:
+                    sides, cents = self._bt.read_capture(0, attempt)
+                    (self.left_y, self.left_x), (self.right_y, self.right_x) = sides
+                    if len(cents[0]) or len(cents[1]):
+                        self.left_window_centroids, self.right_window_centroids = cents
+
+    # ------------------------------------------------------------ methods
+    def process(self, img, ksize_r=15, C_r=8, ksize_b=35, C_b=5, filter_type="bilateral", mask_noise=False,
+                noise_thresh=140, ksize_noise=65, C_noise=10, window_width=30, window_height=40,
+                search_range=20, mu=0.1, no_success_limit=8, start_slice=0.25, ignore_sides=360,
+                ignore_bottom=30, bandwidth=25, partial=1.0, n_tries=2, visualize_search=False,
+                split_view=False, diagnostics=False):
+        """lane_tracker.py:876-1209.  Returns the annotated frame (new array)."""
+        if visualize_search or split_view:
+            raise NotImplementedError("debug views are outside the B200 hot path (SURVEY.md section 8f)")
+        p = make_params(ksize_r=ksize_r, C_r=C_r, ksize_b=ksize_b, C_b=C_b, filter_type=filter_type,
+                        mask_noise=mask_noise, noise_thresh=noise_thresh, ksize_noise=ksize_noise,
+                        C_noise=C_noise, window_width=window_width, window_height=window_height,
+                        search_range=search_range, mu=mu, no_success_limit=no_success_limit,
+                        start_slice=start_slice, ignore_sides=ignore_sides, ignore_bottom=ignore_bottom,
+                        bandwidth=bandwidth, partial=partial, n_tries=n_tries)
+        w, h = self._bt.img_size
+        a = np.asarray(img)
+        if a.shape != (h, w, 3) or a.dtype != np.uint8:
+            raise ValueError("img must be uint8 [%d, %d, 3]" % (h, w))
+        self._in_host[0].numpy()[...] = a
+        self._in_dev.copy_(self._in_host, non_blocking=True)
+        self._bt.process_async(self._in_dev, self._out_dev, params=p)
+        self._out_host.copy_(self._out_dev, non_blocking=True)
+        res = self._bt.fetch_results(1)[0]
+        self.last_result = res
+        self._sync_state(res)
+        if diagnostics:
+            print("attempts=%d mode=%s detected=%s valid=%s" % (res["attempts"], "bs" if res["search_mode"] else "sws",
+                                                                bool(res["detected_pixels"]), bool(res["valid_lane_lines"])))
+        return self._out_host[0].numpy().copy()
+
+    def find_lane_points(self, img, ksize_r=15, C_r=8, ksize_b=35, C_b=5, filter_type="bilateral",
+                         mask_noise=True, noise_thresh=140, ksize_noise=65, C_noise=10, window_width=30,
+                         window_height=40, search_range=20, mu=0.1, no_success_limit=8, start_slice=0.25,
+                         ignore_sides=360, ignore_bottom=30, bandwidth=30, partial=0.5, diagnostics=False):
+        """lane_tracker.py:795-874."""
+        w, h = self._bt.img_size
+        frames = self._upload(img, (h, w, 3)).unsqueeze(0)
+        self._bt.remap(frames, want_bv=False)
+        mask = self._bt.filter_lane_points(None, filter_type, ksize_r, C_r, ksize_b, C_b, mask_noise,
+                                           ksize_noise, C_noise, noise_thresh)[:1]
+        if self.last_detection > self.n_reset:
+            self._sws(mask, window_width, window_height, search_range, mu, no_success_limit, start_slice,
+                      ignore_sides, ignore_bottom, partial)
+            mode = "sws"
+        else:
+            self._bs(mask, bandwidth, ignore_bottom, partial)
+            mode = "bs"
+        return mask[0].cpu().numpy(), mode
+
+    def filter_lane_points(self, img, filter_type="bilateral", ksize_r=25, C_r=8, ksize_b=35, C_b=5,
+                           mask_noise=False, ksize_noise=65, C_noise=10, noise_thresh=135):
+        """lane_tracker.py:183-240: bird's-eye RGB image -> binary mask {0,255}."""
+        _filter_code(filter_type)
+        bw, bh = self._bt.warped_size
+        bv = self._upload(img, (bh, bw, 3)).unsqueeze(0)
+        mask = self._bt.filter_lane_points(bv, filter_type, ksize_r, C_r, ksize_b, C_b, mask_noise,
+                                           ksize_noise, C_noise, noise_thresh)
+        return mask[0].cpu().numpy()
+
+    def _mask_dev(self, img):
+        bw, bh = self._bt.warped_size
+        if isinstance(img, torch.Tensor):
+            return img
+        return self._upload(img, (bh, bw)).unsqueeze(0)
+
+    def _sws(self, mask, *a):
+        px, cents, det = self._bt.sliding_window_search(mask, *a)
+        self.detected_pixels = bool(det[0])
+        if det[0]:
+            (self.left_y, self.left_x), (self.right_y, self.right_x) = px[0]
+            self.left_window_centroids, self.right_window_centroids = cents[0]
+
+    def _bs(self, mask, bandwidth, ignore_bottom, partial):
+        coeffs = np.stack([self.last_left_coeffs, self.last_right_coeffs])[None]
+        px, det = self._bt.band_search(mask, coeffs, bandwidth, ignore_bottom, partial)
+        self.detected_pixels = bool(det[0])
+        if det[0]:
+            (self.left_y, self.left_x), (self.right_y, self.right_x) = px[0]
+
+    def sliding_window_search(self, img, window_width, window_height, search_range, mu, no_success_limit,
+                              start_slice=0.25, ignore_sides=360, ignore_bottom=30, partial=1, diagnostics=False):
+        """lane_tracker.py:242-447."""
+        self._sws(self._mask_dev(img), window_width, window_height, search_range, mu, no_success_limit,
+                  start_slice, ignore_sides, ignore_bottom, partial)
+
+    def band_search(self, img, bandwidth, ignore_bottom=30, partial=1, diagnostics=False):
+        """lane_tracker.py:449-500."""
+        if self.last_left_coeffs is None:
+            raise TypeError("band_search needs last_left_coeffs / last_right_coeffs from a previous valid fit")
+        self._bs(self._mask_dev(img), bandwidth, ignore_bottom, partial)
+
+    def fit_poly(self):
+        """lane_tracker.py:502-509."""
+        f = self._bt.fit_poly([[(self.left_y, self.left_x), (self.right_y, self.right_x)]])
+        return f[0, 0].copy(), f[0, 1].copy()
+
+    def get_poly_points(self, left_fit_coeffs, right_fit_coeffs, partial=1):
+        """lane_tracker.py:511-528."""
+        xs, cnt = self._bt.get_poly_points(np.stack([left_fit_coeffs, right_fit_coeffs])[None], partial)
+        xs, cnt = xs.cpu().numpy()[0], cnt.cpu().numpy()[0]
+        bh = self._bt.warped_size[1]
+        lx, rx = xs[0, :cnt[0]].astype(np.int64), xs[1, :cnt[1]].astype(np.int64)
+        return (np.arange(bh - cnt[0], bh, dtype=np.int64), lx, np.arange(bh - cnt[1], bh, dtype=np.int64), rx)
+
+    def check_validity(self, left_fit_coeffs, right_fit_coeffs, diagnostics=False):
+        """lane_tracker.py:561-627."""
+        valid, diffs = self._bt.check_validity(np.stack([left_fit_coeffs, right_fit_coeffs])[None])
+        self.valid_lane_lines = bool(valid[0])
+        if diagnostics:
+            print("x1_diff == {:.2f}, x2_diff == {:.2f}, x3_diff == {:.2f}, valid == {}".format(*diffs[0], valid[0]))
+
+    def draw_lane(self, img):
+        """lane_tracker.py:629-662 (without putText): uses left_avg_x / right_avg_x."""
+        w, h = self._bt.img_size
+        bh = self._bt.warped_size[1]
+        frames = self._upload(img, (h, w, 3)).unsqueeze(0)
+        xs = np.zeros((1, 2, bh), dtype=np.int32)
+        cnt = np.array([[len(self.left_avg_x), len(self.right_avg_x)]], dtype=np.int32)
+        xs[0, 0, :cnt[0, 0]] = self.left_avg_x
+        xs[0, 1, :cnt[0, 1]] = self.right_avg_x
+        out = self._bt.draw_lane(frames, torch.as_tensor(xs).to(self._bt.device),
+                                 torch.as_tensor(cnt).to(self._bt.device))
+        return out[0].cpu().numpy()
+
+    def print_failure(self, img):
+        """lane_tracker.py:664-673 without the putText overlay: the frame is returned unchanged."""
+        return np.array(img, copy=True)

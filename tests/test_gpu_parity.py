@@ -1,0 +1,389 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden digests
+recorded from the reference.  Bit-exact for every integer/byte/index result; polynomial coefficients
+within 1e-6 relative of np.polyfit (BASELINE.json north_star), in practice ~1e-11."""
+import warnings
+
+import numpy as np
+import pytest
+
+import _fixtures as fx
+from lane_tracker_b200 import synth
+from oracle import cvops
+from oracle.tracker import OracleLaneTracker, ATTEMPT2
+
+pytestmark = pytest.mark.gpu
+
+CAL = synth.shipped_calibration()
+GOLD = fx.golden()
+FIT_RTOL = 1e-6   # tolerance stated by north_star for coefficients vs np.polyfit
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.fixture(scope="module")
+def bt(torch_mod):
+    from lane_tracker_b200 import BatchedLaneTracker
+    t = BatchedLaneTracker(4, **CAL)
+    yield t
+    t.close()
+
+
+@pytest.fixture(scope="module")
+def frames_np():
+    rng = np.random.default_rng(11)
+    return np.stack([fx.load_frame("test1.jpg"), synth.RoadVideo(0).frame(3), fx.load_frame("straight_lines2.jpg"),
+                     rng.integers(0, 256, (720, 1280, 3), dtype=np.uint8)])
+
+
+@pytest.fixture(scope="module")
+def oracle_stages(frames_np):
+    """Oracle intermediates for the four fixture frames (NumPy restatements only)."""
+    out = []
+    for f in frames_np:
+        o = OracleLaneTracker(**CAL)
+        bv = o._remap(f)
+        rec = dict(bv=bv, und=o.trace["undistorted"])
+        m1 = o.filter_lane_points(bv, "bilateral", 15, 8, 35, 5, False, 65, 10, 140)
+        rec.update(mask1=m1, r_plane=o.trace["r_plane"], b_plane=o.trace["b_plane"], r_tophat=o.trace["r_tophat"],
+                   b_tophat=o.trace["b_tophat"], merged1=o.trace["merged"])
+        rec["mask2"] = o.filter_lane_points(bv, "neighborhood", 15, 5, 35, 5, False, 65, 10, 140)
+        rec["mask3"] = o.filter_lane_points(bv, "bilateral", 15, 8, 35, 5, True, 65, 10, 140)
+        out.append(rec)
+    return out
+
+
+def _mism(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return int((a != b).sum())
+
+
+def test_library_loaded_is_in_tree():
+    from lane_tracker_b200 import _lib
+    lib = _lib.load()
+    assert "lane_tracker_b200/liblane_tracker_b200.so" in _lib.LIB_PATH and lib.lt_abi_version() == 1
+
+
+def test_coordinate_tables(bt):
+    U, V = cvops.undistort_map_q5(CAL["cam_matrix"], CAL["dist_coeffs"], 1280, 720)
+    got = bt.debug_read("undistort_map")
+    assert _mism(got[..., 0], U) == 0 and _mism(got[..., 1], V) == 0
+    X, Y = cvops.perspective_map_q5(CAL["warp_matrices"][0], 1080, 1100)
+    got = bt.debug_read("bv_map")
+    assert _mism(got[..., 0], X) == 0 and _mism(got[..., 1], Y) == 0
+    X, Y = cvops.perspective_map_q5(CAL["warp_matrices"][1], 1280, 720)
+    got = bt.debug_read("overlay_map")
+    assert _mism(got[..., 0], X) == 0 and _mism(got[..., 1], Y) == 0
+    # the materialised undistorted rows cover exactly what the bird's-eye view samples (SURVEY: rows 457-694)
+    assert bt.geometry["roi_rows"] == (457, 695)
+
+
+def test_remap_bit_exact(bt, torch_mod, frames_np, oracle_stages):
+    d = torch_mod.as_tensor(frames_np).cuda()
+    bv = bt.remap(d).cpu().numpy()
+    for i, rec in enumerate(oracle_stages):
+        assert _mism(bv[i], rec["bv"]) == 0, i
+        assert _mism(bt.debug_read("r_plane", i), rec["r_plane"]) == 0, i
+        assert _mism(bt.debug_read("b_plane", i), rec["b_plane"]) == 0, i
+    assert fx.sha(bv[0]) == GOLD["images"]["test1.jpg"]["bv"]
+    assert fx.sha(bv[2]) == GOLD["images"]["straight_lines2.jpg"]["bv"]
+
+
+def test_filter_masks_bit_exact(bt, torch_mod, oracle_stages):
+    bvs = torch_mod.as_tensor(np.stack([r["bv"] for r in oracle_stages])).cuda()
+    m1 = bt.filter_lane_points(bvs, "bilateral", 15, 8, 35, 5, False, 65, 10, 140).cpu().numpy()
+    for i, rec in enumerate(oracle_stages):
+        assert _mism(bt.debug_read("r_tophat", i), rec["r_tophat"]) == 0, i
+        assert _mism(bt.debug_read("b_tophat", i), rec["b_tophat"]) == 0, i
+        assert _mism(bt.debug_read("merged", i), rec["merged1"]) == 0, i
+        assert _mism(m1[i], rec["mask1"]) == 0, i
+    m2 = bt.filter_lane_points(bvs, "neighborhood", 15, 5, 35, 5, False, 65, 10, 140).cpu().numpy()
+    m3 = bt.filter_lane_points(bvs, "bilateral", 15, 8, 35, 5, True, 65, 10, 140).cpu().numpy()
+    for i, rec in enumerate(oracle_stages):
+        assert _mism(m2[i], rec["mask2"]) == 0, i
+        assert _mism(m3[i], rec["mask3"]) == 0, i
+    g = GOLD["images"]["test1.jpg"]
+    assert fx.sha(m1[0]) == g["mask_bilateral"] and fx.sha(m2[0]) == g["mask_neighborhood"]
+    assert fx.sha(m3[0]) == g["mask_bilateral_noise"]
+
+
+@pytest.mark.parametrize("k,C", [(25, 8), (7, 2), (64, 3)])
+def test_filter_other_kernel_sizes(bt, torch_mod, oracle_stages, k, C):
+    bv = oracle_stages[0]["bv"]
+    o = OracleLaneTracker(**CAL)
+    want = o.filter_lane_points(bv, "bilateral", k, C, k + 6, C, False, 65, 10, 140)
+    got = bt.filter_lane_points(torch_mod.as_tensor(bv[None]).cuda(), "bilateral", k, C, k + 6, C).cpu().numpy()[0]
+    assert _mism(got, want) == 0
+    kb = k | 1
+    want = o.filter_lane_points(bv, "neighborhood", kb, C, kb + 8, C + 1, False, 65, 10, 140)
+    got = bt.filter_lane_points(torch_mod.as_tensor(bv[None]).cuda(), "neighborhood", kb, C, kb + 8, C + 1).cpu().numpy()[0]
+    assert _mism(got, want) == 0
+
+
+def _oracle_sws(mask, nsl, partial=1.0, **kw):
+    o = OracleLaneTracker(**CAL)
+    args = dict(window_width=30, window_height=40, search_range=20, mu=0.1, no_success_limit=nsl,
+                start_slice=0.25, ignore_sides=360, ignore_bottom=30, partial=partial)
+    args.update(kw)
+    o.sliding_window_search(mask, **args)
+    return o
+
+
+def test_sliding_window_search_pixel_sets(bt, torch_mod, oracle_stages):
+    cases = []
+    for rec in oracle_stages:
+        cases += [(rec["mask1"], 8, 1.0), (rec["mask2"], 50, 1.0), (rec["mask1"], 8, 0.5)]
+    sparse = np.zeros((1100, 1080), np.uint8)                 # edge cases: nearly empty / one-sided masks
+    sparse[1040:1060, 400:404] = 255
+    cases += [(sparse, 8, 1.0), (np.zeros((1100, 1080), np.uint8), 8, 1.0)]
+    for ci, (mask, nsl, partial) in enumerate(cases):
+        o = _oracle_sws(mask, nsl, partial)
+        px, cents, det = bt.sliding_window_search(torch_mod.as_tensor(mask[None]).cuda(), 30, 40, 20, 0.1, nsl,
+                                                  0.25, 360, 30, partial)
+        assert bool(det[0]) == o.detected_pixels, ci
+        got_c = cents[0]
+        assert got_c[0] == o.trace["sws_centroids"][0] and got_c[1] == o.trace["sws_centroids"][1], ci
+        if o.detected_pixels:
+            (ly, lx), (ry, rx) = px[0]
+            assert np.array_equal(ly, o.left_y) and np.array_equal(lx, o.left_x), ci
+            assert np.array_equal(ry, o.right_y) and np.array_equal(rx, o.right_x), ci
+
+
+def test_sliding_window_other_parameters(bt, torch_mod, oracle_stages):
+    mask = oracle_stages[1]["mask1"]
+    for kw in (dict(window_width=40, window_height=55, search_range=35, mu=0.3), dict(ignore_sides=200, start_slice=0.5),
+               dict(window_width=17, window_height=25, ignore_bottom=0)):
+        o = _oracle_sws(mask, 8, 1.0, **kw)
+        a = dict(window_width=30, window_height=40, search_range=20, mu=0.1, no_success_limit=8, start_slice=0.25,
+                 ignore_sides=360, ignore_bottom=30, partial=1.0)
+        a.update(kw)
+        px, cents, det = bt.sliding_window_search(torch_mod.as_tensor(mask[None]).cuda(), a["window_width"],
+                                                  a["window_height"], a["search_range"], a["mu"], a["no_success_limit"],
+                                                  a["start_slice"], a["ignore_sides"], a["ignore_bottom"], a["partial"])
+        assert bool(det[0]) == o.detected_pixels
+        assert cents[0][0] == o.trace["sws_centroids"][0] and cents[0][1] == o.trace["sws_centroids"][1], kw
+        if o.detected_pixels:
+            (ly, lx), (ry, rx) = px[0]
+            assert np.array_equal(ly, o.left_y) and np.array_equal(lx, o.left_x), kw
+            assert np.array_equal(ry, o.right_y) and np.array_equal(rx, o.right_x), kw
+
+
+def test_band_search_and_fit(bt, torch_mod, oracle_stages):
+    warnings.simplefilter("ignore")
+    mask = oracle_stages[1]["mask1"]
+    o = _oracle_sws(mask, 8)
+    lf, rf = o.fit_poly()
+    for bw, partial, ib in ((25, 1.0, 30), (30, 0.5, 30), (40, 1.0, 0)):
+        o.last_left_coeffs, o.last_right_coeffs = lf, rf
+        o.band_search(mask, bw, ib, partial)
+        px, det = bt.band_search(torch_mod.as_tensor(mask[None]).cuda(), np.stack([lf, rf])[None], bw, ib, partial)
+        assert bool(det[0]) == o.detected_pixels
+        (ly, lx), (ry, rx) = px[0]
+        assert np.array_equal(ly, o.left_y) and np.array_equal(lx, o.left_x)
+        assert np.array_equal(ry, o.right_y) and np.array_equal(rx, o.right_x)
+        fits = bt.fit_poly([[(ly, lx), (ry, rx)]])[0]
+        wl, wr = o.fit_poly()
+        np.testing.assert_allclose(fits[0], wl, rtol=FIT_RTOL, atol=0)
+        np.testing.assert_allclose(fits[1], wr, rtol=FIT_RTOL, atol=0)
+        assert np.max(np.abs(fits[0] / wl - 1)) < 1e-9 and np.max(np.abs(fits[1] / wr - 1)) < 1e-9
+
+
+def test_fit_poly_rank_deficient_and_random(bt):
+    warnings.simplefilter("ignore")
+    rng = np.random.default_rng(3)
+    sets = []
+    ys = np.full(20, 700); xs = rng.integers(300, 340, 20)            # one row
+    sets.append([(ys, xs), (np.array([10, 10, 900]), np.array([5, 9, 700]))])   # two rows
+    for _ in range(6):
+        n = int(rng.integers(3, 4000))
+        y = rng.integers(0, 1100, n); x = np.clip((2e-4 * (y - 500.0) ** 2 + 0.1 * y + 300 + rng.normal(0, 4, n)), 0, 1079).astype(int)
+        y2 = rng.integers(0, 1100, n); x2 = rng.integers(0, 1080, n)
+        sets.append([(y, x), (y2, x2)])
+    fits = bt.fit_poly(sets)
+    for s, ps in enumerate(sets):
+        for side in range(2):
+            want = np.polyfit(ps[side][0], ps[side][1], 2)
+            np.testing.assert_allclose(fits[s, side], want, rtol=FIT_RTOL, atol=1e-9 * np.abs(want).max())
+
+
+def test_check_validity_and_poly_points(bt):
+    rng = np.random.default_rng(5)
+    o = OracleLaneTracker(**CAL)
+    fits = []
+    for t in range(300):
+        a = rng.normal(0, 2e-4); b = rng.normal(0, 0.3); c = rng.uniform(200, 600)
+        sep = rng.uniform(60, 260)
+        fits.append([[a, b - 2 * a * 1099, a * 1099 ** 2 - b * 1099 + c],
+                     [a + rng.normal(0, 5e-5), b + rng.normal(0, 0.1) - 2 * a * 1099, a * 1099 ** 2 - b * 1099 + c + sep]])
+    fits = np.array(fits)
+    valid, diffs = bt.check_validity(fits)
+    assert 10 < valid.sum() < 290
+    for i, f in enumerate(fits):
+        o.check_validity(f[0], f[1])
+        assert bool(valid[i]) == o.valid_lane_lines, i
+        assert tuple(diffs[i]) == tuple(o.trace["validity"]), i
+    for partial in (1.0, 0.5, 0.73):
+        xs, cnt = bt.get_poly_points(fits[:40], partial)
+        xs, cnt = xs.cpu().numpy(), cnt.cpu().numpy()
+        for i, f in enumerate(fits[:40]):
+            ly, lx, ry, rx = o.get_poly_points(f[0], f[1], partial)
+            assert cnt[i, 0] == len(lx) and cnt[i, 1] == len(rx)
+            assert np.array_equal(xs[i, 0, :len(lx)], lx) and np.array_equal(xs[i, 1, :len(rx)], rx)
+
+
+def test_draw_lane_overlay(bt, torch_mod, frames_np):
+    rng = np.random.default_rng(9)
+    o = OracleLaneTracker(**CAL)
+    for t in range(6):
+        a = rng.normal(0, 3e-4) * (4 if t % 2 else 1); b = rng.normal(0, 0.4); c = rng.uniform(150, 600)
+        lf = np.array([a, b - 2 * a * 1099, a * 1099 ** 2 - b * 1099 + c])
+        rf = lf + np.array([rng.normal(0, 5e-5), rng.normal(0, 0.05), rng.uniform(120, 260)])
+        partial = 1.0 if t < 4 else 0.5
+        o.left_avg_y, o.left_avg_x, o.right_avg_y, o.right_avg_x = o.get_poly_points(lf, rf, partial)
+        if len(o.left_avg_x) == 0 or len(o.right_avg_x) == 0:
+            continue
+        want = o.draw_lane(frames_np[t % 4])
+        xs, cnt = bt.get_poly_points(np.stack([lf, rf])[None], partial)
+        got = bt.draw_lane(torch_mod.as_tensor(frames_np[t % 4][None]).cuda(), xs, cnt).cpu().numpy()[0]
+        rows = bt.debug_read("lane_rows", 0)
+        lo, hi = o.trace["lane_rows"]
+        filled = hi >= lo
+        assert np.array_equal(rows[filled, 0], lo[filled]) and np.array_equal(rows[filled, 1], hi[filled]), t
+        assert np.all(rows[~filled, 1] < rows[~filled, 0]), t
+        assert _mism(got, want) == 0, t
+
+
+def _check_result_against_golden(res, want, st, lx, rx):
+    assert int(res["last_detection"]) == want["last_detection"]
+    assert int(res["counter"]) == want["counter"] and int(res["success"]) == want["success"]
+    assert bool(res["valid_lane_lines"]) == want["valid"]
+    assert bool(res["detected_pixels"]) == want["detected_pixels"]
+    if want["last_left"] is not None:
+        np.testing.assert_allclose(np.array(st.last_left[:]), want["last_left"], rtol=FIT_RTOL)
+        np.testing.assert_allclose(np.array(st.last_right[:]), want["last_right"], rtol=FIT_RTOL)
+        np.testing.assert_allclose(np.array(st.left_avg[:]), want["left_avg"], rtol=FIT_RTOL)
+        np.testing.assert_allclose(np.array(st.right_avg[:]), want["right_avg"], rtol=FIT_RTOL)
+    assert st.n_left_avg == want["n_left_avg"] and st.n_right_avg == want["n_right_avg"]
+    bh = 1100
+    digest = fx.sha(np.concatenate([np.arange(bh - len(lx), bh), lx.astype(np.int64), np.arange(bh - len(rx), bh),
+                                    rx.astype(np.int64)]).astype(np.int64)) if want["n_left_avg"] else None
+    if digest is not None:
+        assert digest == want["avg_xy"]
+    if want["radius"] is not None:
+        assert int(st.average_curve_radius) == want["radius"]
+        assert [int(st.radii[i]) for i in range(st.radii_len)] == want["radii"]
+        assert float(st.eccentricity) == pytest.approx(want["ecc"], rel=1e-12, abs=1e-15)
+
+
+def test_process_scenario_matches_reference_golden(torch_mod):
+    """48 frames through the drop-in class: SWS -> band tracking -> 12-frame outage -> recovery."""
+    from lane_tracker_b200 import LaneTracker
+    sc = GOLD["scenario"]
+    vid = synth.RoadVideo(sc["seed"])
+    outage = fx.load_frame(sc["outage_frame"])
+    lt = LaneTracker(**CAL)
+    for rec in sc["frames"]:
+        frame = outage if rec["kind"] == "outage" else vid.frame(rec["t"])
+        keep = frame.copy()
+        out = lt.process(frame)
+        assert np.array_equal(frame, keep)
+        w = rec["state"]
+        st, lx, rx = lt._bt.get_state(0)
+        _check_result_against_golden(lt.last_result, w, st, lx, rx)
+        assert fx.out_digest(out) == rec["out"], rec["t"]
+        if w["pix"] is not None:
+            assert fx.pix_digest(lt.left_y, lt.left_x, lt.right_y, lt.right_x) == w["pix"], rec["t"]
+    r = lt.get_success_ratio()
+    assert [float(r[0]), int(r[1]), int(r[2])] == sc["success_ratio"]
+
+
+def test_process_bundled_frames_match_reference_golden(torch_mod):
+    """All 11 bundled frames (always two attempts + sliding-window search, all invalid), batched."""
+    from lane_tracker_b200 import BatchedLaneTracker
+    names = fx.frame_names()
+    frames = np.stack([fx.load_frame(n) for n in names])
+    bt11 = BatchedLaneTracker(len(names), **CAL)
+    bt11.set_capture(True)
+    d = torch_mod.as_tensor(frames).cuda()
+    out = torch_mod.empty_like(d)
+    res = bt11.process(d, out)
+    out = out.cpu().numpy()
+    for i, n in enumerate(names):
+        g = GOLD["images"][n]
+        assert fx.sha(frames[i]) == g["frame"]
+        assert int(res[i]["attempts"]) == 2 and not res[i]["valid_lane_lines"]
+        assert fx.out_digest(out[i]) == g["process_out"], n
+        assert fx.sha(bt11.debug_read("mask", i)) == g["mask_neighborhood"], n
+        for attempt, key in ((0, "sws_bilateral"), (1, "sws_neighborhood")):
+            w = g[key]
+            sides, cents = bt11.read_capture(i, attempt)
+            det = len(sides[0][0]) > 0 and len(sides[1][0]) > 0
+            assert det == w["detected"], (n, key)
+            if det:
+                assert fx.pix_digest(sides[0][0], sides[0][1], sides[1][0], sides[1][1]) == w["pix"], (n, key)
+                assert cents[0] == w["left_centroids"] and cents[1] == w["right_centroids"], (n, key)
+        w2 = g["sws_neighborhood"]
+        if w2["detected"]:
+            np.testing.assert_allclose(res[i]["left_fit"], w2["left_fit"], rtol=FIT_RTOL)
+            np.testing.assert_allclose(res[i]["right_fit"], w2["right_fit"], rtol=FIT_RTOL)
+        w1 = g["sws_bilateral"]
+        if w1["detected"]:
+            np.testing.assert_allclose(res[i]["first_left_fit"], w1["left_fit"], rtol=FIT_RTOL)
+            np.testing.assert_allclose(res[i]["first_right_fit"], w1["right_fit"], rtol=FIT_RTOL)
+            assert bool(res[i]["first_valid"]) == w1["valid"]
+    bt11.close()
+
+
+def test_batched_streams_are_independent(torch_mod):
+    """Stream s of a batch behaves exactly like a single-stream tracker fed the same frames."""
+    from lane_tracker_b200 import BatchedLaneTracker
+    S, T = 3, 5
+    vids = [synth.RoadVideo(s) for s in range(S)]
+    b = BatchedLaneTracker(S, **CAL)
+    singles = [BatchedLaneTracker(1, **CAL) for _ in range(S)]
+    for t in range(T):
+        fr = np.stack([v.frame(t) for v in vids])
+        d = torch_mod.as_tensor(fr).cuda()
+        out = torch_mod.empty_like(d)
+        res = b.process(d, out)
+        for s in range(S):
+            o1 = torch_mod.empty_like(d[s:s + 1])
+            r1 = singles[s].process(d[s:s + 1].contiguous(), o1)
+            assert r1[0].tobytes() == res[s].tobytes()
+            assert torch_mod.equal(o1[0], out[s])
+    for t in singles + [b]:
+        t.close()
+
+
+def test_state_roundtrip_and_teacher_forcing(torch_mod):
+    from lane_tracker_b200 import BatchedLaneTracker
+    vid = synth.RoadVideo(2)
+    a = BatchedLaneTracker(1, **CAL)
+    b = BatchedLaneTracker(1, **CAL)
+    for t in range(3):
+        a.process(torch_mod.as_tensor(vid.frame(t)[None]).cuda())
+    st, lx, rx = a.get_state(0)
+    b.set_state(0, st, lx, rx)
+    f = torch_mod.as_tensor(vid.frame(3)[None]).cuda()
+    oa, ob = torch_mod.empty_like(f), torch_mod.empty_like(f)
+    ra, rb = a.process(f, oa), b.process(f, ob)
+    assert ra[0].tobytes() == rb[0].tobytes() and torch_mod.equal(oa, ob)
+    a.reset()
+    assert a.get_state(0)[0].last_detection == 5 and a.get_state(0)[0].counter == 0
+    a.close(); b.close()
+
+
+def test_error_conventions(bt, torch_mod):
+    from lane_tracker_b200 import LaneTracker, _lib
+    lt = LaneTracker(**CAL)
+    with pytest.raises(ValueError, match="Unexpected filter mode"):
+        lt.filter_lane_points(np.zeros((1100, 1080, 3), np.uint8), filter_type="gaussian")
+    with pytest.raises(ValueError):
+        lt.process(np.zeros((10, 10, 3), np.uint8))
+    with pytest.raises(_lib.LaneTrackerError):
+        bt.filter_lane_points(torch_mod.zeros((1, 1100, 1080, 3), dtype=torch_mod.uint8, device="cuda"), "neighborhood", 14, 5, 35, 5)
