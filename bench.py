@@ -1,0 +1,350 @@
+#!/usr/bin/env python3
+"""Benchmark of the lane-tracking hot path (BASELINE.json metric: frames/sec at 1280x720, batched streams).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on the host cores
+
+Workload (BASELINE.json configs[2] per GPU; configs[3] = the same 64 streams on each of N GPUs): 64 independent
+synthetic 1280x720 road videos per GPU, one frame per stream per step, full process() semantics (sliding-window
+search on the first frame, band-search tracking afterwards, overlay rendered).  Streams are sharded across
+ranks with no collective on the data path; torch.distributed is used only for the timing barrier.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec at 1280x720 (batched streams)"
+STREAMS_PER_GPU = 64
+FRAME_POOL = 4                       # pre-rendered frames per stream, cycled
+FRAME_BYTES = 1280 * 720 * 3
+ALGO_BYTES_PER_FRAME = 2 * FRAME_BYTES + 128          # frame in + annotated frame out + results
+PLANE_PIXELS = 1080 * 1100
+MORPH_ALGO_BYTES_PER_FRAME = 2 * PLANE_PIXELS         # one u8 plane read + one u8 plane written per morphology launch
+
+
+def measured_peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                p = [v.strip() for v in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm on the host cores (oracle port with the reference's own cv2 calls)
+# ----------------------------------------------------------------------------------------------
+
+def _cpu_worker(args):
+    """One stream on one core: returns (frames processed, seconds, success count)."""
+    seed, n_frames, warm = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    import warnings
+    warnings.simplefilter("ignore")
+    from lane_tracker_b200 import synth
+    from oracle.tracker import OracleLaneTracker
+    backend = "numpy"
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+        backend = "cv2"
+    except Exception:
+        pass
+    vid = synth.RoadVideo(seed)
+    frames = [vid.frame(t % FRAME_POOL) for t in range(min(FRAME_POOL, warm + n_frames))]
+    trk = OracleLaneTracker(**synth.shipped_calibration(), backend=backend)
+    for t in range(warm):
+        trk.process(frames[t % len(frames)].copy())
+    t0 = time.perf_counter()
+    for t in range(warm, warm + n_frames):
+        trk.process(frames[t % len(frames)].copy())
+    dt = time.perf_counter() - t0
+    return n_frames, dt, trk.success, backend
+
+
+def cpu_baseline(budget_s=20.0):
+    """Bounded sample of the same workload on all host cores: one stream per core."""
+    import multiprocessing as mp
+    cores = host_cores()
+    per_frame = 0.35            # s/frame/core with cv2 single-threaded, refined below
+    n_frames = max(2, int(budget_s / per_frame))
+    jobs = [(s, n_frames, 1) for s in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    frames = sum(r[0] for r in res)
+    slowest = max(r[1] for r in res)
+    return {"value": frames / slowest, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": "%d streams x %d frames (1 warm-up frame each), one process per core, %s operators, "
+                      "single-threaded; %.1f s wall" % (cores, n_frames, res[0][3], wall),
+            "success_ratio": sum(r[2] for r in res) / float(sum(r[0] + 1 for r in res))}
+
+
+def run_reference_arm(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    cores = host_cores()
+    frames_per_step = 1            # per stream; a step = one frame on each of `cores` parallel streams
+    n_frames = args.steps * frames_per_step
+    jobs = [(s, n_frames, args.warmup) for s in range(cores)]
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    slowest = max(r[1] for r in res)
+    value = sum(r[0] for r in res) / slowest
+    sample = ("%d of the %d streams (one per host core) x %d frames after %d warm-up frames; %s operators, "
+              "1 thread per process" % (cores, STREAMS_PER_GPU * args.gpus, n_frames, args.warmup, res[0][3]))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * slowest / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n_gpus):
+    return {"workload": "64 independent synthetic 1280x720 streams batched per B200 (BASELINE.json configs[2]; "
+                        "x N GPUs = configs[3] sharding, no collective)",
+            "streams_per_gpu": STREAMS_PER_GPU, "frame_pool_per_stream": FRAME_POOL, "mode": "process() with overlay",
+            "bird_view": "1080x1100", "parallelism": "streams sharded over %d GPU(s), no data-path collective" % n_gpus,
+            "l2": "inputs larger than L2: %.0f MB of distinct frames read per step" % (STREAMS_PER_GPU * FRAME_BYTES / 1e6)}
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+
+def run_gpu_arm(args):
+    import torch
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    cpu_line = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_line = cpu_baseline(args.cpu_budget)        # before CUDA is initialised: the workers are forked
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)      # timing barrier only; the data path has no collective
+    from lane_tracker_b200 import BatchedLaneTracker, _lib, synth
+
+    S, P = STREAMS_PER_GPU, FRAME_POOL
+    t_render = time.perf_counter()
+    pool_np = synth.render_streams(S, P, first_seed=rank * S, workers=max(1, min(host_cores() // max(world, 1), 32)))
+    t_render = time.perf_counter() - t_render
+    pool_host = torch.from_numpy(pool_np).pin_memory()                 # [S, P, H, W, 3]
+    pool_dev = pool_host.to(dev).permute(1, 0, 2, 3, 4).contiguous()   # [P, S, H, W, 3]: one contiguous batch per step
+    host_batches = pool_host.permute(1, 0, 2, 3, 4).contiguous().pin_memory()
+    out_dev = torch.empty_like(pool_dev[0])
+    out_host = torch.empty(out_dev.shape, dtype=torch.uint8).pin_memory()
+
+    trk = BatchedLaneTracker(S, **synth.shipped_calibration(), device=local)
+    lib = _lib.load()
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step(i):
+        trk.process_async(pool_dev[i % P], out_dev)
+
+    # ---- device-resident throughput ------------------------------------------------------------
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    trk.profile_begin(args.steps)
+    launches0 = lib.lt_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record(stream)
+    barrier()
+    launches = lib.lt_launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    stage_ms, prof_calls = trk.profile_read()
+    res = trk.fetch_results(S)
+    valid_frac = float(res["valid_lane_lines"].mean())
+    band_frac = float((res["search_mode"] == 1).mean())
+
+    # ---- end to end: pinned host frames in, annotated frames + results out, every step ----------
+    def e2e_step(i):
+        pool_dev[i % P].copy_(host_batches[i % P], non_blocking=True)
+        trk.process_async(pool_dev[i % P], out_dev)
+        out_host.copy_(out_dev, non_blocking=True)
+        trk._results_host.copy_(trk._results_dev, non_blocking=True)
+
+    for i in range(min(args.warmup, 3)):
+        e2e_step(i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for i in range(args.steps):
+        e2e_step(i)
+    f1.record(stream)
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    if distributed:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    frames_total = world * S * args.steps
+    value = frames_total / (ms * 1e-3)
+    e2e_value = frames_total / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        top = max(stage_ms, key=stage_ms.get)
+        total_stage = sum(stage_ms.values())
+        morph = {k: stage_ms[k] for k in ("erode55", "tophat55", "erode29", "tophat29")}
+        dom = max(morph, key=morph.get)
+        dom_ms_per_launch = morph[dom] / max(prof_calls, 1)
+        achieved = S * MORPH_ALGO_BYTES_PER_FRAME / (dom_ms_per_launch * 1e-3) / 1e9 if dom_ms_per_launch > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": "k_morph<%s> (%s)" % ("55" if "55" in dom else "29", dom),
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": peak_src, "ms_per_launch": dom_ms_per_launch,
+                    "algorithmic_bytes_per_launch": S * MORPH_ALGO_BYTES_PER_FRAME,
+                    "share_of_step": morph[dom] / total_stage if total_stage else None,
+                    "note": "ellipse morphology is shared-memory/ALU bound, not HBM bound (DESIGN.md); "
+                            "whole-path figure in roofline_path"}
+        path_gbs = value * ALGO_BYTES_PER_FRAME / 1e9 / world
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(world),
+            "roofline": roofline,
+            "roofline_path": {"bound": "hbm", "achieved": path_gbs, "peak": peak, "unit": "GB/s",
+                              "frac": path_gbs / peak, "algorithmic_bytes_per_frame": ALGO_BYTES_PER_FRAME,
+                              "per_gpu": True},
+            "stage_ms_per_step": {k: v / max(prof_calls, 1) for k, v in stage_ms.items() if v > 0},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": S * FRAME_BYTES * world,
+                    "d2h_bytes_per_step": (S * FRAME_BYTES + trk._results_dev.numel()) * world,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "tracking": {"valid_fraction_last_step": valid_frac, "band_search_fraction_last_step": band_frac},
+            "render_s": t_render,
+        }
+        if cpu_line is not None:
+            line["cpu_baseline"] = cpu_line
+        print(json.dumps(line))
+    trk.close()
+    if distributed:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

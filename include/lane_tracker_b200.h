@@ -140,6 +140,16 @@ int lt_set_capture(lt_handle* h, int32_t enable);
 int lt_read_capture(lt_handle* h, int32_t stream_id, int32_t attempt, int32_t side, uint32_t* h_pixels,
                     int32_t capacity, int32_t* h_count, int32_t* h_centroids, int32_t* h_ncentroids);
 
+/* ---- in-stream stage timing (bench.py's roofline figures) --------------------
+ * lt_profile_begin arms CUDA-event recording at every stage boundary of the next `max_calls`
+ * lt_process calls (events are recorded on the caller's stream, no synchronisation);
+ * lt_profile_read synchronises, sums the per-stage durations [ms] over the recorded calls,
+ * and disarms.  Stage ids: lt_stage_name(0..LT_NSTAGES-1). */
+#define LT_NSTAGES 16
+int lt_profile_begin(lt_handle* h, int32_t max_calls);
+int lt_profile_read(lt_handle* h, double* h_stage_ms, int32_t* h_calls);
+const char* lt_stage_name(int32_t stage);
+
 /* ---- stage entry points (mirror the reference's public methods) ----------- */
 
 /* cv2.undistort + cv2.warpPerspective of find_lane_points (lane_tracker.py:832-834).

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "liblane_tracker_b200.so")
 LT_MAX_AVERAGE = 8
 LT_MAX_LEVELS = 128
 LT_ABI_VERSION = 1
+LT_NSTAGES = 16
 
 i32, f64 = C.c_int32, C.c_double
 
@@ -69,6 +70,9 @@ SIGNATURES = {
     "lt_process": (C.c_int, [P, P, P, i32, C.POINTER(lt_params), P, P]),
     "lt_set_capture": (C.c_int, [P, i32]),
     "lt_read_capture": (C.c_int, [P, i32, i32, i32, P, i32, C.POINTER(i32), P, C.POINTER(i32)]),
+    "lt_profile_begin": (C.c_int, [P, i32]),
+    "lt_profile_read": (C.c_int, [P, C.POINTER(f64), C.POINTER(i32)]),
+    "lt_stage_name": (C.c_char_p, [i32]),
     "lt_remap": (C.c_int, [P, P, P, i32, P]),
     "lt_filter_lane_points": (C.c_int, [P, P, P, i32] + [i32] * 9 + [P]),
     "lt_sliding_window_search": (C.c_int, [P, P, i32, i32, i32, i32, f64, i32, f64, i32, i32, f64,

@@ -92,6 +92,8 @@ extern "C" int lt_destroy(lt_handle* h) {
                     h->avg_x, h->state, h->att, h->retry_list, h->retry_count, h->draw_flags, h->scratch_bv,
                     h->cap_pixels, h->cap_counts, h->cap_cents, h->cap_ncents};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < h->prof_cap; ++i) cudaEventDestroy(h->prof_ev[i]);
+    delete[] h->prof_ev; delete[] h->prof_stage;
     delete h;
     return 0;
 }
@@ -194,6 +196,12 @@ extern "C" int lt_reset(lt_handle* h, const int32_t* ids, int32_t n) {
     return 0;
 }
 
+static int check_any_n(lt_handle* h, int n) {   // stage calls that touch no per-stream buffer of the handle
+    if (!h) { lt_set_error("null handle"); return -1; }
+    if (n < 1) { lt_set_error("n_streams must be positive"); return -1; }
+    return 0;
+}
+
 static int check_n(lt_handle* h, int n) {
     if (!h) { lt_set_error("null handle"); return -1; }
     if (n < 1 || n > h->S) { lt_set_error("n_streams %d outside [1, %d]", n, h->S); return -1; }
@@ -215,8 +223,12 @@ extern "C" int lt_process(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out,
     if ((rc = check_params(h, p1))) return rc;
     const bool two = (params->n_tries >= 2) || (params->n_tries == -1);
     // find_lane_points (lane_tracker.py:795-874), first attempt, all streams
+    if (h->prof_active && h->prof_calls >= h->prof_max_calls) h->prof_active = 0;
+    lt_prof_mark(h, ST_BEGIN, st);
     if ((rc = lt_launch_undistort(h, d_frames, n, st))) return rc;
+    lt_prof_mark(h, ST_UNDISTORT, st);
     if ((rc = lt_launch_warp(h, nullptr, n, st))) return rc;
+    lt_prof_mark(h, ST_WARP, st);
     if ((rc = lt_launch_filter(h, n, p1, nullptr, nullptr, st))) return rc;
     LtSearchArgs sa;
     memset(&sa, 0, sizeof(sa));
@@ -227,10 +239,12 @@ extern "C" int lt_process(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out,
         sa.centroids = h->cap_cents; sa.ncentroids = h->cap_ncents;
     }
     if ((rc = lt_launch_search(h, n, p1, sa, nullptr, nullptr, st))) return rc;
+    lt_prof_mark(h, ST_SEARCH, st);
     if (two) {
         // second attempt only for the streams whose first attempt failed (lane_tracker.py:1071-1128).
         // The reference re-runs undistort + warp here; their outputs are unchanged, so the planes are reused.
         if ((rc = lt_launch_select_retry(h, n, params->n_tries, st))) return rc;
+        lt_prof_mark(h, ST_RETRY_SELECT, st);
         if ((rc = lt_launch_filter(h, n, p2, h->retry_list, h->retry_count, st))) return rc;
         sa.att = h->att + h->S;
         if (h->capture) {
@@ -238,11 +252,58 @@ extern "C" int lt_process(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out,
             sa.centroids = h->cap_cents + S * 2 * LT_MAX_LEVELS; sa.ncentroids = h->cap_ncents + S * 2;
         }
         if ((rc = lt_launch_search(h, n, p2, sa, h->retry_list, h->retry_count, st))) return rc;
+        lt_prof_mark(h, ST_SEARCH, st);
     }
     if ((rc = lt_launch_update_state(h, n, d_results, two ? 2 : 1, st))) return rc;
+    lt_prof_mark(h, ST_UPDATE, st);
     if (d_out) {
         if ((rc = lt_launch_overlay(h, d_frames, d_out, n, h->draw_flags, st))) return rc;
+        lt_prof_mark(h, ST_OVERLAY, st);
     }
+    if (h->prof_active) h->prof_calls++;
+    return 0;
+}
+
+static const char* STAGE_NAMES[LT_NSTAGES] = {"begin", "undistort", "warp", "erode55", "erode29", "tophat55", "tophat29",
+                                               "cross_r", "cross_b", "box", "noise", "open5", "search", "retry_select",
+                                               "update_state", "overlay"};
+extern "C" const char* lt_stage_name(int32_t s) { return (s >= 0 && s < LT_NSTAGES) ? STAGE_NAMES[s] : "?"; }
+
+void lt_prof_mark(lt_handle* h, int stage, cudaStream_t st) {
+    if (!h->prof_active || h->prof_n >= h->prof_cap) return;
+    h->prof_stage[h->prof_n] = stage;
+    cudaEventRecord(h->prof_ev[h->prof_n], st);
+    h->prof_n++;
+}
+
+extern "C" int lt_profile_begin(lt_handle* h, int32_t max_calls) {
+    if (!h || max_calls < 1 || max_calls > 4096) { lt_set_error("bad argument"); return -1; }
+    LT_CUDA(cudaSetDevice(h->cfg.device));
+    int need = max_calls * 32;
+    if (need > h->prof_cap) {
+        cudaEvent_t* ev = new cudaEvent_t[need];
+        for (int i = 0; i < need; ++i) LT_CUDA(cudaEventCreate(&ev[i]));
+        for (int i = 0; i < h->prof_cap; ++i) cudaEventDestroy(h->prof_ev[i]);
+        delete[] h->prof_ev; delete[] h->prof_stage;
+        h->prof_ev = ev; h->prof_stage = new int[need]; h->prof_cap = need;
+    }
+    h->prof_n = 0; h->prof_calls = 0; h->prof_max_calls = max_calls; h->prof_active = 1;
+    return 0;
+}
+
+extern "C" int lt_profile_read(lt_handle* h, double* ms, int32_t* calls) {
+    if (!h || !ms || !calls) { lt_set_error("bad argument"); return -1; }
+    LT_CUDA(cudaSetDevice(h->cfg.device));
+    LT_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < LT_NSTAGES; ++i) ms[i] = 0.0;
+    for (int i = 1; i < h->prof_n; ++i) {
+        if (h->prof_stage[i] == ST_BEGIN) continue;
+        float t = 0.f;
+        LT_CUDA(cudaEventElapsedTime(&t, h->prof_ev[i - 1], h->prof_ev[i]));
+        ms[h->prof_stage[i]] += t;
+    }
+    *calls = h->prof_calls;
+    h->prof_active = 0;
     return 0;
 }
 
@@ -383,7 +444,7 @@ extern "C" int lt_band_search(lt_handle* h, const uint8_t* d_mask, int32_t n, co
 extern "C" int lt_fit_poly(lt_handle* h, const uint32_t* d_pixels, int32_t capacity, const int32_t* d_counts,
                            int32_t n, double* d_fits, void* stream) {
     int rc;
-    if ((rc = check_n(h, n))) return rc;
+    if ((rc = check_any_n(h, n))) return rc;
     if (!d_pixels || !d_counts || !d_fits) { lt_set_error("null argument"); return -1; }
     return lt_launch_fit_pixels(h, d_pixels, capacity, d_counts, n, d_fits, (cudaStream_t)stream);
 }
@@ -391,7 +452,7 @@ extern "C" int lt_fit_poly(lt_handle* h, const uint32_t* d_pixels, int32_t capac
 extern "C" int lt_check_validity(lt_handle* h, const double* d_fits, int32_t n, int32_t* d_valid, double* d_diffs,
                                  void* stream) {
     int rc;
-    if ((rc = check_n(h, n))) return rc;
+    if ((rc = check_any_n(h, n))) return rc;
     if (!d_fits || !d_valid) { lt_set_error("null argument"); return -1; }
     return lt_launch_validity(h, d_fits, n, d_valid, d_diffs, (cudaStream_t)stream);
 }
@@ -399,7 +460,7 @@ extern "C" int lt_check_validity(lt_handle* h, const double* d_fits, int32_t n, 
 extern "C" int lt_get_poly_points(lt_handle* h, const double* d_fits, int32_t n, double partial, int32_t* d_x,
                                   int32_t* d_counts, void* stream) {
     int rc;
-    if ((rc = check_n(h, n))) return rc;
+    if ((rc = check_any_n(h, n))) return rc;
     if (!d_fits || !d_x || !d_counts) { lt_set_error("null argument"); return -1; }
     if (!(partial >= 0.0 && partial <= 1.0)) { lt_set_error("partial must lie in [0, 1]"); return -1; }
     return lt_launch_poly_points(h, d_fits, n, partial, d_x, d_counts, (cudaStream_t)stream);

@@ -75,6 +75,7 @@ struct lt_handle {
     int* cap_counts;             // [2][S][2]
     int* cap_cents;              // [2][S][2][LT_MAX_LEVELS]
     int* cap_ncents;             // [2][S][2]
+    cudaEvent_t* prof_ev; int* prof_stage; int prof_cap, prof_n, prof_active, prof_calls, prof_max_calls;
     uint8_t* scratch_bv;         // lazily allocated [S][bv_h][bv_w][3] for stage calls
     size_t stream_plane;         // entries per stream in a pair plane
     size_t stream_mask;          // words per stream in a bit mask
@@ -140,5 +141,9 @@ int lt_launch_validity(lt_handle* h, const double* d_fits, int n, int* d_valid, 
 int lt_launch_poly_points(lt_handle* h, const double* d_fits, int n, double partial, int* d_x, int* d_counts,
                           cudaStream_t st);
 int lt_launch_lane_rows(lt_handle* h, const int* d_x, const int* d_counts, int n, cudaStream_t st);
+
+enum LtStage { ST_BEGIN = 0, ST_UNDISTORT, ST_WARP, ST_ERODE55, ST_ERODE29, ST_TOPHAT55, ST_TOPHAT29, ST_CROSS_R,
+               ST_CROSS_B, ST_BOX, ST_NOISE, ST_OPEN5, ST_SEARCH, ST_RETRY_SELECT, ST_UPDATE, ST_OVERLAY };
+void lt_prof_mark(lt_handle* h, int stage, cudaStream_t st);   // "stage just finished being enqueued"
 
 static inline int lt_div_up(int a, int b) { return (a + b - 1) / b; }

@@ -604,14 +604,21 @@ int lt_launch_filter(lt_handle* h, int n, const LtAttemptParams& p, const int* l
         int bands = 1;
         while (bands < 8 && n * tiles * bands < 296) ++bands;
         if ((rc = launch_morph<55, false, false>(h, h->planeB, h->tmpB, nullptr, n, list, count, bands, st))) return rc;
+        lt_prof_mark(h, ST_ERODE55, st);
         if ((rc = launch_morph<29, false, false>(h, h->planeR, h->tmpR, nullptr, n, list, count, bands, st))) return rc;
+        lt_prof_mark(h, ST_ERODE29, st);
         if ((rc = launch_morph<55, true, true>(h, h->tmpB, h->topB, h->planeB, n, list, count, bands, st))) return rc;
+        lt_prof_mark(h, ST_TOPHAT55, st);
         if ((rc = launch_morph<29, true, true>(h, h->tmpR, h->topR, h->planeR, n, list, count, bands, st))) return rc;
+        lt_prof_mark(h, ST_TOPHAT29, st);
         if ((rc = launch_cross(h, h->topR, h->merged, p.ksize_r, p.C_r, 0, n, list, count, st))) return rc;
+        lt_prof_mark(h, ST_CROSS_R, st);
         if ((rc = launch_cross(h, h->topB, h->merged, p.ksize_b, p.C_b, 1, n, list, count, st))) return rc;
+        lt_prof_mark(h, ST_CROSS_B, st);
     } else {
         if ((rc = launch_box(h, h->planeR, h->tmpR, h->merged, p.ksize_r, p.C_r, 0, n, list, count, st))) return rc;
         if ((rc = launch_box(h, h->planeB, h->tmpB, h->merged, p.ksize_b, p.C_b, 1, n, list, count, st))) return rc;
+        lt_prof_mark(h, ST_BOX, st);
     }
     if (p.mask_noise) {
         if ((rc = launch_cross(h, h->planeB, h->mask, p.ksize_noise, p.C_noise, 0, n, list, count, st))) return rc;
@@ -619,10 +626,12 @@ int lt_launch_filter(lt_handle* h, int n, const LtAttemptParams& p, const int* l
         k_noise_combine<<<g, 32, 0, st>>>(h->planeB, h->mask, h->merged, d, p.noise_thresh, h->stream_plane,
                                           h->stream_mask, list, count);
         LT_LAUNCH_CHECK();
+        lt_prof_mark(h, ST_NOISE, st);
     }
     size_t smem = (size_t)(2 * OPEN_ROWS + 12) * d.mwords * sizeof(uint32_t);
     dim3 go(lt_div_up(d.bv_h, OPEN_ROWS), n);
     k_open5<<<go, 256, smem, st>>>(h->merged, h->mask, d, h->stream_mask, list, count);
     LT_LAUNCH_CHECK();
+    lt_prof_mark(h, ST_OPEN5, st);
     return 0;
 }

@@ -122,6 +122,17 @@ class BatchedLaneTracker:
     def set_capture(self, enable=True):
         check(self.lib.lt_set_capture(self._h, int(bool(enable))))
 
+    def profile_begin(self, max_calls):
+        """Arm in-stream CUDA-event timing of every stage of the next `max_calls` process() calls."""
+        check(self.lib.lt_profile_begin(self._h, int(max_calls)))
+
+    def profile_read(self):
+        """-> ({stage name: total ms}, calls); synchronises."""
+        ms = (C.c_double * _lib.LT_NSTAGES)()
+        calls = C.c_int32(0)
+        check(self.lib.lt_profile_read(self._h, ms, C.byref(calls)))
+        return {self.lib.lt_stage_name(i).decode(): float(ms[i]) for i in range(1, _lib.LT_NSTAGES)}, calls.value
+
     # -- hot path -----------------------------------------------------------
     def _check_frames(self, frames):
         w, h = self.img_size

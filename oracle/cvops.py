@@ -35,7 +35,7 @@ def undistort_map_q5(K, D, width, height):
     k1, k2, p1, p2 = D[0], D[1], D[2], D[3]
     k3 = D[4] if D.size > 4 else 0.0
     fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
-    iR = np.linalg.inv(K)
+    iR = invert3x3_cv(K)
     i = np.arange(height, dtype=np.float64)[:, None]
     j = np.arange(width, dtype=np.float64)[None, :]
     _x = (i * iR[0, 1] + iR[0, 2]) + j * iR[0, 0]
@@ -58,6 +58,24 @@ def undistort_map_q5(K, D, width, height):
             np.clip(V, INT_MIN, INT_MAX).astype(np.int64).astype(np.int32))
 
 
+def invert3x3_cv(a):
+    """``cv::invert`` of a 3x3 fp64 matrix: adjugate times 1/det, in OpenCV's operation order.
+
+    ``np.linalg.inv`` (LAPACK) differs in the last ulp, which is enough to flip one exact
+    half-way Q5 coordinate of the shipped ``Minv`` (frame pixel (707, 858)); see
+    tests/test_oracle_cvops.py::test_unwarp_tie_pixel_needs_cv_invert.
+    """
+    a = np.asarray(a, dtype=np.float64).ravel()
+    d = (a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) +
+         a[2] * (a[3] * a[7] - a[4] * a[6]))
+    d = 1.0 / d if d != 0.0 else 0.0
+    return np.array([(a[4] * a[8] - a[5] * a[7]) * d, (a[2] * a[7] - a[1] * a[8]) * d,
+                     (a[1] * a[5] - a[2] * a[4]) * d, (a[5] * a[6] - a[3] * a[8]) * d,
+                     (a[0] * a[8] - a[2] * a[6]) * d, (a[2] * a[3] - a[0] * a[5]) * d,
+                     (a[3] * a[7] - a[4] * a[6]) * d, (a[1] * a[6] - a[0] * a[7]) * d,
+                     (a[0] * a[4] - a[1] * a[3]) * d]).reshape(3, 3)
+
+
 def perspective_map_q5(M, dst_width, dst_height):
     """Q5 source coordinates of ``cv2.warpPerspective(src, M, (dw,dh))``.
 
@@ -65,7 +83,7 @@ def perspective_map_q5(M, dst_width, dst_height):
     3x3 matrix (no WARP_INVERSE_MAP), walks the destination in 64-column blocks
     and evaluates the homography in fp64 from the block origin.
     """
-    m = np.linalg.inv(np.asarray(M, dtype=np.float64).reshape(3, 3)).ravel()
+    m = invert3x3_cv(M).ravel()
     x = np.arange(dst_width, dtype=np.int64)[None, :]
     y = np.arange(dst_height, dtype=np.float64)[:, None]
     xb = ((x // 64) * 64).astype(np.float64)

@@ -34,6 +34,21 @@ def test_warp_and_unwarp(noise, bv):
                           cv2.warpPerspective(bv, MINV, (1280, 720)))
 
 
+def test_unwarp_tie_pixel_needs_cv_invert():
+    """Frame pixel (707, 858) maps to X = 18867.5 exactly with cv::invert's adjugate inverse of Minv
+    (rounds to even, 18868) but to 18867.49999999999 with LAPACK's; its row lies below the 1100-row
+    canvas, so only a taller source exposes which one OpenCV uses."""
+    Xc, Yc = cvops.perspective_map_q5(MINV, 1280, 720)
+    assert (Xc[707, 858], Yc[707, 858] >> 5) == (18868, 1107)
+    src = np.random.default_rng(0).integers(0, 256, (1300, 1080), dtype=np.uint8)
+    want = cv2.warpPerspective(src, MINV, (1280, 720), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
+    assert np.array_equal(cvops.bilinear_q5(src, Xc, Yc), want)
+    src = np.random.default_rng(1).integers(0, 256, (900, 1500), dtype=np.uint8)
+    Xm, Ym = cvops.perspective_map_q5(M, 1080, 1100)
+    want = cv2.warpPerspective(src, M, (1080, 1100), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
+    assert np.array_equal(cvops.bilinear_q5(src, Xm, Ym), want)
+
+
 def test_lab_b_exhaustive_slice():
     # every (r,g) pair for 16 blue levels = 1M colours; the full 2^24 was checked in the survey
     r, g, b = np.meshgrid(np.arange(256), np.arange(256), np.arange(0, 256, 17)[:16], indexing="ij")
