@@ -87,7 +87,7 @@ static void init_state(lt_handle* h, lt_state* s) {
 extern "C" int lt_destroy(lt_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->und_map, h->bv_map, h->ov_map, h->lab_gamma, h->lab_cbrt, h->und_roi, h->planeR, h->planeB,
+    void* ptrs[] = {h->und_map, h->bv_map, h->ov_map, h->bv_desc, h->lab_gamma, h->lab_cbrt, h->und_roi, h->planeR, h->planeB,
                     h->tmpR, h->tmpB, h->topR, h->topB, h->merged, h->mask, h->pixels, h->pix_counts, h->lane_rows,
                     h->avg_x, h->state, h->att, h->retry_list, h->retry_count, h->draw_flags, h->scratch_bv,
                     h->cap_pixels, h->cap_counts, h->cap_cents, h->cap_ncents};
@@ -115,6 +115,7 @@ extern "C" int lt_create(const lt_config* cfg, lt_handle** out) {
     memset(h, 0, sizeof(*h));
     h->cfg = *cfg;
     h->S = cfg->max_streams;
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
     LtDims& d = h->d;
     d.img_w = cfg->img_w; d.img_h = cfg->img_h; d.bv_w = cfg->bv_w; d.bv_h = cfg->bv_h;
     d.p2 = 32 * ((cfg->bv_w + 63) / 64);
@@ -157,6 +158,8 @@ extern "C" int lt_create(const lt_config* cfg, lt_handle** out) {
         if (o0 >= o1) { o0 = 0; o1 = 0; }
         d.ov0 = o0; d.ov1 = o1;
     }
+    A(bv_desc, nbv);
+    if (!rc) rc = lt_launch_build_desc(h, st);
     A(und_roi, S * (size_t)(d.roi1 - d.roi0) * d.img_w);
     A(planeR, S * h->stream_plane); A(planeB, S * h->stream_plane);
     A(tmpR, S * h->stream_plane); A(tmpB, S * h->stream_plane);

@@ -49,10 +49,12 @@ struct lt_handle {
     lt_config cfg;
     LtDims d;
     int S;                       // max streams
+    int sm_count;
     // shared tables
     int2* und_map;               // [img_h][img_w]
     int2* bv_map;                // [bv_h][bv_w]
     int2* ov_map;                // [img_h][img_w]
+    int2* bv_desc;               // [bv_h][bv_w] tap descriptors derived from bv_map and the ROI
     unsigned short* lab_gamma;   // [256]
     unsigned short* lab_cbrt;    // [3072]
     // per-stream buffers
@@ -109,6 +111,7 @@ void lt_set_error(const char* fmt, ...);
 // list[0..*count): CTAs whose stream slot is >= *count exit immediately.
 
 int lt_launch_build_maps(lt_handle* h, cudaStream_t st);
+int lt_launch_build_desc(lt_handle* h, cudaStream_t st);
 int lt_launch_undistort(lt_handle* h, const uint8_t* d_frames, int n, cudaStream_t st);
 int lt_launch_warp(lt_handle* h, uint8_t* d_bv_rgb, int n, cudaStream_t st);
 int lt_launch_planes_from_bv(lt_handle* h, const uint8_t* d_bv_rgb, int n, cudaStream_t st);

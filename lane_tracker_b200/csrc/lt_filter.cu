@@ -98,7 +98,6 @@ k_morph(const uint32_t* __restrict__ src_all, uint32_t* __restrict__ dst_all, co
     constexpr int NTAB = HAS32 ? 5 : 4;
     constexpr uint32_t PADL = IS_MAX ? 0u : 0xFFFFu;
     constexpr uint32_t PAD2 = PADL | (PADL << 16);
-    constexpr int NPF = (RB * TE + TW - 1) / TW;
 
     int slot = blockIdx.z;
     if (count != nullptr && slot >= *count) return;
@@ -124,14 +123,51 @@ k_morph(const uint32_t* __restrict__ src_all, uint32_t* __restrict__ dst_all, co
     const int r_begin = yb0 - R;
     const int r_end = yb1 + R;      // exclusive
     const int nblk = (r_end - r_begin + RB - 1) / RB;
+    const int xint = d.bv_w - d.p2; // packed columns < xint carry two real pixels
 
-    uint32_t pf[NPF];
+    // How to fetch packed column gx of a plane row: columns outside [0, p2) borrow the neighbouring strip's
+    // lane (the two strips are adjacent in the image) or the pad value.
+    struct ColDesc { int off; uint32_t sel; };
+    auto describe = [&](int i) -> ColDesc {
+        const int gx = x0 + i - R;
+        ColDesc c;
+        c.off = gx;
+        c.sel = 0x3210u;                                                    // both lanes from the loaded entry
+        if (gx < 0) { c.off = gx + d.p2; c.sel = 0x1054u; }                 // hi <- entry.lo, lo <- pad
+        else if (gx >= d.p2) { c.off = gx - d.p2; c.sel = (gx < d.bv_w) ? 0x5432u : 0x5454u; }   // lo <- entry.hi
+        else if (gx >= xint) c.sel = 0x5410u;                               // lo real, hi beyond the image
+        c.off = max(0, min(c.off, d.p2 - 1));
+        return c;
+    };
+    auto fetch = [&](int r, const ColDesc& c) -> uint32_t {
+        if ((unsigned)r >= (unsigned)d.bv_h) return PAD2;
+        return __byte_perm(__ldg(&src[(size_t)r * d.p2 + c.off]), PAD2, c.sel);
+    };
+    // Work split of a row block: every thread owns table column `tid` of all RB rows; the 2R halo columns of
+    // the RB rows (NX elements) are spread evenly, at most NXT per thread.
+    constexpr int NX = 2 * R * RB;
+    constexpr int NXT = (NX + TW - 1) / TW;
+    const ColDesc cmain = describe(tid);
+    ColDesc cx[NXT];
+    int xrow[NXT], xidx[NXT];
 #pragma unroll
-    for (int q = 0; q < NPF; ++q) {
-        int e = tid + q * TW;
-        int rr = e / TE, i = e - rr * TE;
-        pf[q] = (e < RB * TE) ? stage_elem<IS_MAX>(src, d, r_begin + rr, x0 + i - R) : PAD2;
+    for (int x = 0; x < NXT; ++x) {
+        int e = tid + x * TW;
+        bool ok = e < NX;
+        int rr = ok ? e / (2 * R) : 0, i = TW + (ok ? e - rr * 2 * R : 0);
+        xrow[x] = ok ? rr : -1;
+        xidx[x] = rr * TEA + i;
+        cx[x] = describe(i);
     }
+
+    uint32_t pf[RB + NXT];
+    auto prefetch = [&](int rbase) {
+#pragma unroll
+        for (int rr = 0; rr < RB; ++rr) pf[rr] = fetch(rbase + rr, cmain);
+#pragma unroll
+        for (int x = 0; x < NXT; ++x) pf[RB + x] = (xrow[x] >= 0) ? fetch(rbase + xrow[x], cx[x]) : PAD2;
+    };
+    prefetch(r_begin);
 
     uint32_t A[K];
 #pragma unroll
@@ -146,41 +182,38 @@ k_morph(const uint32_t* __restrict__ src_all, uint32_t* __restrict__ dst_all, co
         const int rb0 = r_begin + blk * RB;
         // publish the staged rows, then start fetching the next block
 #pragma unroll
-        for (int q = 0; q < NPF; ++q) {
-            int e = tid + q * TW;
-            int rr = e / TE, i = e - rr * TE;
-            if (e < RB * TE) T0[rr * TEA + i] = pf[q];
-        }
-        __syncthreads();
-        if (blk + 1 < nblk) {
+        for (int rr = 0; rr < RB; ++rr) T0[rr * TEA + tid] = pf[rr];
 #pragma unroll
-            for (int q = 0; q < NPF; ++q) {
-                int e = tid + q * TW;
-                int rr = e / TE, i = e - rr * TE;
-                pf[q] = (e < RB * TE) ? stage_elem<IS_MAX>(src, d, rb0 + RB + rr, x0 + i - R) : PAD2;
-            }
-        }
-        // window tables: T4 -> (T8, T16) -> T32
-        for (int e = tid; e < RB * TE; e += TW) {
-            int rr = e / TE, i = e - rr * TE;
-            const uint32_t* t = T0 + rr * TEA + i;
-            T4[rr * TEA + i] = op2<IS_MAX>(op3<IS_MAX>(t[0], t[1], t[2]), t[3]);
-        }
+        for (int x = 0; x < NXT; ++x) if (xrow[x] >= 0) T0[xidx[x]] = pf[RB + x];
         __syncthreads();
-        for (int e = tid; e < RB * TE; e += TW) {
-            int rr = e / TE, i = e - rr * TE;
-            const uint32_t* t = T4 + rr * TEA + i;
+        if (blk + 1 < nblk) prefetch(rb0 + RB);
+        // window tables: T4 -> (T8, T16) -> T32
+        auto build4 = [&](int idx) {
+            const uint32_t* t = T0 + idx;
+            T4[idx] = op2<IS_MAX>(op3<IS_MAX>(t[0], t[1], t[2]), t[3]);
+        };
+        auto build816 = [&](int idx) {
+            const uint32_t* t = T4 + idx;
             uint32_t v8 = op2<IS_MAX>(t[0], t[4]);
-            T8[rr * TEA + i] = v8;
-            T16[rr * TEA + i] = op3<IS_MAX>(v8, t[8], t[12]);
-        }
+            T8[idx] = v8;
+            T16[idx] = op3<IS_MAX>(v8, t[8], t[12]);
+        };
+        auto build32 = [&](int idx) { T32[idx] = op2<IS_MAX>(T16[idx], T16[idx + 16]); };
+#pragma unroll
+        for (int rr = 0; rr < RB; ++rr) build4(rr * TEA + tid);
+#pragma unroll
+        for (int x = 0; x < NXT; ++x) if (xrow[x] >= 0) build4(xidx[x]);
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < RB; ++rr) build816(rr * TEA + tid);
+#pragma unroll
+        for (int x = 0; x < NXT; ++x) if (xrow[x] >= 0) build816(xidx[x]);
         __syncthreads();
         if (HAS32) {
-            for (int e = tid; e < RB * TE; e += TW) {
-                int rr = e / TE, i = e - rr * TE;
-                const uint32_t* t = T16 + rr * TEA + i;
-                T32[rr * TEA + i] = op2<IS_MAX>(t[0], t[16]);
-            }
+#pragma unroll
+            for (int rr = 0; rr < RB; ++rr) build32(rr * TEA + tid);
+#pragma unroll
+            for (int x = 0; x < NXT; ++x) if (xrow[x] >= 0) build32(xidx[x]);
             __syncthreads();
         }
         // walk the RB rows of this block
@@ -196,7 +229,6 @@ k_morph(const uint32_t* __restrict__ src_all, uint32_t* __restrict__ dst_all, co
             uint32_t H[E::ND];
 #pragma unroll
             for (int u = 0; u < E::ND; ++u) {
-                constexpr int dummy = 0; (void)dummy;
                 const int w = E::uniq(u);
                 const int len = 2 * w + 1;
                 if (w == 0) {
@@ -277,10 +309,124 @@ __device__ __forceinline__ void warp_row_prefix(const uint32_t* __restrict__ pro
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(ROWK_WARPS * 32)
+// Horizontal half of the cross threshold.  A CTA stages 32 plane rows (zero-padded halo of k columns, the two
+// strips stitched) into shared memory as (lo, hi) byte pairs; thread (row = lane, segment = warp) then walks its
+// column segment with running window sums L, R in packed u16x2 registers and emits finished 32-column mask
+// words directly.  Rows sit in different banks (odd half-word pitch), so the walk is conflict-free.
+constexpr int CROSSH_ROWS = 32;
+constexpr int CROSSH_WARPS = 4;
+
+__device__ __forceinline__ uint32_t unpack_pair(uint32_t v16) {            // (hi<<8 | lo) -> hi<<16 | lo
+    return __byte_perm(v16, 0, 0x4140);
+}
+
+__global__ void __launch_bounds__(CROSSH_WARPS * 32)
 k_cross_h(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_all, LtDims d, int k, int C,
-          int accumulate, size_t plane_stride, size_t bits_stride, const int* __restrict__ list,
+          int accumulate, int pitch, size_t plane_stride, size_t bits_stride, const int* __restrict__ list,
           const int* __restrict__ count) {
+    int slot = blockIdx.y;
+    if (count != nullptr && slot >= *count) return;
+    int s = list ? list[slot] : slot;
+    extern __shared__ uint32_t smem[];
+    unsigned short* tile = reinterpret_cast<unsigned short*>(smem);     // [32][pitch], entry i <-> packed column i - k
+    const int y0 = blockIdx.x * CROSSH_ROWS;
+    const uint32_t* src = plane_all + (size_t)s * plane_stride;
+    const int ncol = d.p2 + 2 * k;
+    const int xint = d.bv_w - d.p2;
+    // packed column gx -> 16-bit (hi byte, lo byte) pair of one plane row; zero outside the image
+    auto fetch = [&](const uint32_t* __restrict__ row, int gx) -> uint32_t {
+        int off = gx, mode = 0;                                   // 0: both lanes, 1: hi <- entry.lo, 2: lo only, 3: lo <- entry.hi
+        if (gx < 0) { off = gx + d.p2; mode = 1; }
+        else if (gx >= d.p2) { off = gx - d.p2; mode = (gx < d.bv_w) ? 3 : 4; }
+        else if (gx >= xint) mode = 2;
+        if (mode == 4 || off < 0 || off >= d.p2) return 0u;
+        uint32_t e = __ldg(&row[off]);
+        if (mode == 0) return (e & 0xFFu) | ((e >> 8) & 0xFF00u);
+        if (mode == 1) return (e & 0xFFu) << 8;
+        if (mode == 2) return e & 0xFFu;
+        return (e >> 16) & 0xFFu;
+    };
+    const int xv = xint & ~3;                                    // [0, xv): both lanes real, 16-byte vector loads
+    for (int r = threadIdx.x >> 5; r < CROSSH_ROWS; r += CROSSH_WARPS) {
+        const int y = y0 + r;
+        unsigned short* trow_w = tile + r * pitch;
+        if (y >= d.bv_h) {
+            for (int i = threadIdx.x & 31; i < ncol; i += 32) trow_w[i] = 0;
+            continue;
+        }
+        const uint32_t* row = src + (size_t)y * d.p2;
+        for (int g0 = (threadIdx.x & 31) * 4; g0 < xv; g0 += 512) {          // 4 x 16 B in flight per lane
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (g0 + 128 * u < xv) v[u] = __ldg(reinterpret_cast<const uint4*>(row + g0 + 128 * u));
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (g0 + 128 * u < xv) {
+                    unsigned short* o = trow_w + k + g0 + 128 * u;
+                    o[0] = (unsigned short)__byte_perm(v[u].x, 0, 0x4420);
+                    o[1] = (unsigned short)__byte_perm(v[u].y, 0, 0x4420);
+                    o[2] = (unsigned short)__byte_perm(v[u].z, 0, 0x4420);
+                    o[3] = (unsigned short)__byte_perm(v[u].w, 0, 0x4420);
+                }
+        }
+        // halo columns and the tail where the high strip leaves the image: generic path
+        const int nrest = k + (ncol - k - xv);
+        for (int j = threadIdx.x & 31; j < nrest; j += 32) {
+            int i = j < k ? j : j - k + k + xv;
+            trow_w[i] = (unsigned short)fetch(row, i - k);
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int y = y0 + lane;
+    const int nw = d.p2 >> 5;                                            // words per strip
+    const int w0 = (warp * nw) / CROSSH_WARPS, w1 = ((warp + 1) * nw) / CROSSH_WARPS;
+    if (w0 >= w1) return;
+    const unsigned short* trow = tile + lane * pitch + k;                // trow[x] = packed column x
+    const uint32_t kk = (uint32_t)k;
+    const uint32_t bias = ((uint32_t)(C * k + 1)) * 0x00010001u;         // pass <=> k*p >= side + C*k + 1
+    int x = w0 * 32;
+    uint32_t L = 0, Rs = 0;
+    for (int i = 1; i <= k; ++i) { L += unpack_pair(trow[x - i]); Rs += unpack_pair(trow[x + i]); }
+    uint32_t p = unpack_pair(trow[x]);
+    uint32_t* brow = bits_all + (size_t)s * bits_stride + (size_t)min(y, d.bv_h - 1) * d.mwords;
+    for (int w = w0; w < w1; ++w) {
+        uint32_t wl = 0, wh = 0;
+#pragma unroll 4
+        for (int b = 0; b < 32; ++b, ++x) {
+            // lanes hold values < 2^15 (k <= 127): bit 15 of ((A | 0x8000) - B) is set iff A >= B, per lane
+            uint32_t T = (p * kk) | 0x80008000u;
+            uint32_t okL = T - (L + bias), okR = T - (Rs + bias);
+            uint32_t ok = okL & okR;
+            wl |= ((ok >> 15) & 1u) << b;
+            wh |= ((ok >> 31) & 1u) << b;
+            uint32_t pn = unpack_pair(trow[x + 1]);
+            L = L + p - unpack_pair(trow[x - k]);
+            Rs = Rs + unpack_pair(trow[x + k + 1]) - pn;
+            p = pn;
+        }
+        if (y < d.bv_h) {
+            // bits of columns >= bv_w in the high strip are forced to 0
+            int hbase = (d.p2 + w * 32);
+            uint32_t valid = hbase + 32 <= d.bv_w ? 0xFFFFFFFFu : (hbase >= d.bv_w ? 0u : ((1u << (d.bv_w - hbase)) - 1u));
+            wh &= valid;
+            if (accumulate) {
+                if (wl) atomicOr(&brow[w], wl);
+                if (wh) atomicOr(&brow[w + nw], wh);
+            } else {
+                brow[w] = wl;
+                brow[w + nw] = wh;
+            }
+        }
+    }
+}
+
+// generic fallback of the horizontal half for k > 127 (packed lanes would overflow 15 bits): prefix sums
+__global__ void __launch_bounds__(ROWK_WARPS * 32)
+k_cross_h_wide(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_all, LtDims d, int k, int C,
+               int accumulate, size_t plane_stride, size_t bits_stride, const int* __restrict__ list,
+               const int* __restrict__ count) {
     int slot = blockIdx.y;
     if (count != nullptr && slot >= *count) return;
     int s = list ? list[slot] : slot;
@@ -308,6 +454,12 @@ k_cross_h(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_al
     }
 }
 
+// Vertical half: one thread per packed column walks a band of rows with running sums U, D (packed u16x2);
+// the plane rows each step needs are fetched CV_CHUNK steps ahead so that the loads stay in flight.
+// PACKED: k*255 + C*k + 1 < 2^15, the compare is done on both lanes at once with a guard bit.
+constexpr int CV_CHUNK = 8;
+
+template <bool PACKED>
 __global__ void __launch_bounds__(32)
 k_cross_v(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_all, LtDims d, int k, int C,
           int band_rows, size_t plane_stride, size_t bits_stride, const int* __restrict__ list,
@@ -323,23 +475,48 @@ k_cross_v(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_al
     const bool hi_ok = x + d.p2 < d.bv_w;
     auto ld = [&](int r) -> uint32_t { return ((unsigned)r < (unsigned)d.bv_h) ? __ldg(&P[(size_t)r * d.p2]) : 0u; };
     uint32_t U = 0, D = 0;
-    for (int i = 1; i <= k; ++i) { U += ld(yb0 - i); D += ld(yb0 + i); }
-    const int Ck = C * k;
-    uint32_t p = ld(yb0);
-    for (int y = yb0; y < yb1; ++y) {
-        uint32_t pn = ld(y + 1);
-        int tl = k * (int)(p & 0xFFFFu) - Ck, th = k * (int)(p >> 16) - Ck;
-        bool pl = ((int)(U & 0xFFFFu) < tl) && ((int)(D & 0xFFFFu) < tl);
-        bool ph = hi_ok && ((int)(U >> 16) < th) && ((int)(D >> 16) < th);
-        uint32_t bl = __ballot_sync(0xFFFFFFFFu, pl), bh = __ballot_sync(0xFFFFFFFFu, ph);
-        if (lane == 0) {
-            uint32_t* brow = bits + (size_t)y * d.mwords;
-            brow[blockIdx.x] |= bl;
-            brow[blockIdx.x + (d.p2 >> 5)] |= bh;
+    for (int i0 = 1; i0 <= k; i0 += CV_CHUNK) {  // initial window sums, CV_CHUNK rows per side in flight
+        uint32_t a[CV_CHUNK], b[CV_CHUNK];
+#pragma unroll
+        for (int j = 0; j < CV_CHUNK; ++j) {
+            bool ok = i0 + j <= k;
+            a[j] = ok ? ld(yb0 - i0 - j) : 0u;
+            b[j] = ok ? ld(yb0 + i0 + j) : 0u;
         }
-        U = U + p - ld(y - k);                    // lanes stay in [0, 65535]: add first, then subtract
-        D = D + ld(y + k + 1) - pn;
-        p = pn;
+#pragma unroll
+        for (int j = 0; j < CV_CHUNK; ++j) { U += a[j]; D += b[j]; }
+    }
+    const int Ck = C * k;
+    const uint32_t kk = (uint32_t)k, bias = (uint32_t)(Ck + 1) * 0x00010001u;
+    uint32_t p = ld(yb0);
+    for (int yc = yb0; yc < yb1; yc += CV_CHUNK) {
+        uint32_t pc[CV_CHUNK], pu[CV_CHUNK], pd[CV_CHUNK];
+#pragma unroll
+        for (int j = 0; j < CV_CHUNK; ++j) { pc[j] = ld(yc + j + 1); pu[j] = ld(yc + j - k); pd[j] = ld(yc + j + k + 1); }
+#pragma unroll
+        for (int j = 0; j < CV_CHUNK; ++j) {
+            const int y = yc + j;
+            bool pl, ph;
+            if (PACKED) {
+                uint32_t T = (p * kk) | 0x80008000u;
+                uint32_t ok = (T - (U + bias)) & (T - (D + bias));
+                pl = (ok >> 15) & 1u;
+                ph = hi_ok && (ok >> 31);
+            } else {
+                int tl = k * (int)(p & 0xFFFFu) - Ck, th = k * (int)(p >> 16) - Ck;
+                pl = ((int)(U & 0xFFFFu) < tl) && ((int)(D & 0xFFFFu) < tl);
+                ph = hi_ok && ((int)(U >> 16) < th) && ((int)(D >> 16) < th);
+            }
+            uint32_t bl = __ballot_sync(0xFFFFFFFFu, pl), bh = __ballot_sync(0xFFFFFFFFu, ph);
+            if (lane == 0 && y < yb1) {
+                uint32_t* brow = bits + (size_t)y * d.mwords;     // fire-and-forget RED.OR: no load to wait for
+                if (bl) atomicOr(&brow[blockIdx.x], bl);
+                if (bh) atomicOr(&brow[blockIdx.x + (d.p2 >> 5)], bh);
+            }
+            U = U + p - pu[j];                    // lanes stay in [0, 65535]: add first, then subtract
+            D = D + pd[j] - pc[j];
+            p = pc[j];
+        }
     }
 }
 
@@ -554,20 +731,38 @@ int lt_launch_plane_to_u8(lt_handle* h, const uint32_t* plane, uint8_t* d_dst, i
 static int launch_cross(lt_handle* h, const uint32_t* plane, uint32_t* bits, int k, int C, int accumulate, int n,
                         const int* list, const int* count, cudaStream_t st) {
     const LtDims& d = h->d;
-    int wpad = (d.bv_w + 32) & ~31;
-    size_t smem = (size_t)ROWK_WARPS * 2 * wpad * sizeof(uint32_t);
-    static bool attr_done = false;
-    if (!attr_done && smem > 48 * 1024) {
-        LT_CUDA(cudaFuncSetAttribute(k_cross_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+    if (k <= 127 && C >= 0 && k * 255 + C * k + 1 < 32768) {   // packed u16 lanes must stay below 2^15
+        int pitch = d.p2 + 2 * k + 2;
+        while (((pitch >> 1) & 1) == 0 || (pitch & 1)) ++pitch;       // pitch = 2 * odd: rows land in distinct banks
+        size_t smem = (size_t)CROSSH_ROWS * pitch * sizeof(unsigned short);
+        static size_t cur = 0;
+        if (smem > cur && smem > 48 * 1024) {
+            LT_CUDA(cudaFuncSetAttribute(k_cross_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cur = smem;
+        }
+        dim3 gh(lt_div_up(d.bv_h, CROSSH_ROWS), n);
+        k_cross_h<<<gh, CROSSH_WARPS * 32, smem, st>>>(plane, bits, d, k, C, accumulate, pitch, h->stream_plane,
+                                                         h->stream_mask, list, count);
+        LT_LAUNCH_CHECK();
+    } else {
+        int wpad = (d.bv_w + 32) & ~31;
+        size_t smem = (size_t)ROWK_WARPS * 2 * wpad * sizeof(uint32_t);
+        static size_t cur = 0;
+        if (smem > cur && smem > 48 * 1024) {
+            LT_CUDA(cudaFuncSetAttribute(k_cross_h_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cur = smem;
+        }
+        dim3 gh(lt_div_up(d.bv_h, ROWK_WARPS), n);
+        k_cross_h_wide<<<gh, ROWK_WARPS * 32, smem, st>>>(plane, bits, d, k, C, accumulate, h->stream_plane,
+                                                            h->stream_mask, list, count);
+        LT_LAUNCH_CHECK();
     }
-    dim3 gh(lt_div_up(d.bv_h, ROWK_WARPS), n);
-    k_cross_h<<<gh, ROWK_WARPS * 32, smem, st>>>(plane, bits, d, k, C, accumulate, h->stream_plane, h->stream_mask,
-                                                  list, count);
-    LT_LAUNCH_CHECK();
-    int band_rows = 64;
+    int band_rows = 128;
     dim3 gv(d.p2 / 32, lt_div_up(d.bv_h, band_rows), n);
-    k_cross_v<<<gv, 32, 0, st>>>(plane, bits, d, k, C, band_rows, h->stream_plane, h->stream_mask, list, count);
+    if (k <= 127 && C >= 0 && k * 255 + C * k + 1 < 32768)
+        k_cross_v<true><<<gv, 32, 0, st>>>(plane, bits, d, k, C, band_rows, h->stream_plane, h->stream_mask, list, count);
+    else
+        k_cross_v<false><<<gv, 32, 0, st>>>(plane, bits, d, k, C, band_rows, h->stream_plane, h->stream_mask, list, count);
     LT_LAUNCH_CHECK();
     return 0;
 }
@@ -577,10 +772,10 @@ static int launch_box(lt_handle* h, const uint32_t* plane, uint32_t* hs, uint32_
     const LtDims& d = h->d;
     int wpad = (d.bv_w + 32) & ~31;
     size_t smem = (size_t)ROWK_WARPS * 2 * wpad * sizeof(uint32_t);
-    static bool attr_done = false;
-    if (!attr_done && smem > 48 * 1024) {
+    static size_t cur = 0;
+    if (smem > cur && smem > 48 * 1024) {
         LT_CUDA(cudaFuncSetAttribute(k_box_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        cur = smem;
     }
     int half = block / 2;
     dim3 gh(lt_div_up(d.bv_h, ROWK_WARPS), n);
@@ -600,9 +795,16 @@ int lt_launch_filter(lt_handle* h, int n, const LtAttemptParams& p, const int* l
     int rc;
     if (p.filter_type == 0) {
         // bands: enough CTAs to fill 148 SMs x 2 while keeping the 2R-row warm-up per band small
+        // bands: minimise (scheduling rounds) x (rows walked per CTA, incl. the 2R-row warm-up), 2 CTAs per SM
         int tiles = lt_div_up(d.p2, MORPH_TW);
         int bands = 1;
-        while (bands < 8 && n * tiles * bands < 296) ++bands;
+        double best = 1e30;
+        const int slots = 2 * (h->sm_count > 0 ? h->sm_count : 148);
+        for (int b = 1; b <= 32; ++b) {
+            int br = lt_div_up(d.bv_h, b), ctas = n * tiles * lt_div_up(d.bv_h, br);
+            double cost = (double)lt_div_up(ctas, slots) * (br + 54);
+            if (cost < best - 1e-9) { best = cost; bands = b; }
+        }
         if ((rc = launch_morph<55, false, false>(h, h->planeB, h->tmpB, nullptr, n, list, count, bands, st))) return rc;
         lt_prof_mark(h, ST_ERODE55, st);
         if ((rc = launch_morph<29, false, false>(h, h->planeR, h->tmpR, nullptr, n, list, count, bands, st))) return rc;

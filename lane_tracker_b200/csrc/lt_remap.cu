@@ -184,31 +184,68 @@ __device__ __forceinline__ int lab_b(uint32_t rgb, const unsigned short* __restr
     return max(0, min(255, b));
 }
 
-__device__ __forceinline__ uint32_t und_tap(const uchar4* __restrict__ und, const LtDims& d, int y, int x) {
-    if ((unsigned)y >= (unsigned)d.img_h || (unsigned)x >= (unsigned)d.img_w) return 0u;   // BORDER_CONSTANT
-    if (y < d.roi0 || y >= d.roi1) return 0u;   // cannot happen: the ROI covers every in-image tap
-    uchar4 v = __ldg(&und[(size_t)(y - d.roi0) * d.img_w + x]);
-    return (uint32_t)v.x | ((uint32_t)v.y << 8) | ((uint32_t)v.z << 16);
+// Per bird's-eye pixel tap descriptor, built once from bv_map: x = index of tap (sy, sx) in the undistorted ROI
+// buffer, y = fx | fy << 5 | in-image flags of the four taps << 10.  Saves the per-frame bounds logic.
+__global__ void k_build_bv_desc(const int2* __restrict__ map, int2* __restrict__ desc, LtDims d) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= d.bv_w) return;
+    Tap4 t = make_taps(map[(size_t)y * d.bv_w + x]);
+    int2 q = map[(size_t)y * d.bv_w + x];
+    auto ok = [&](int yy, int xx) {
+        return (unsigned)yy < (unsigned)d.img_h && (unsigned)xx < (unsigned)d.img_w && yy >= d.roi0 && yy < d.roi1;
+    };
+    uint32_t f = (uint32_t)(q.x & 31) | ((uint32_t)(q.y & 31) << 5);
+    f |= (ok(t.sy, t.sx) ? 1u : 0u) << 10 | (ok(t.sy, t.sx + 1) ? 1u : 0u) << 11 |
+         (ok(t.sy + 1, t.sx) ? 1u : 0u) << 12 | (ok(t.sy + 1, t.sx + 1) ? 1u : 0u) << 13;
+    long long idx = (long long)(t.sy - d.roi0) * d.img_w + t.sx;
+    if (!(f >> 10)) idx = 0;
+    desc[(size_t)y * d.bv_w + x] = make_int2((int)idx, (int)f);
+}
+
+int lt_launch_build_desc(lt_handle* h, cudaStream_t st) {
+    const LtDims& d = h->d;
+    dim3 g(lt_div_up(d.bv_w, 256), d.bv_h);
+    k_build_bv_desc<<<g, 256, 0, st>>>(h->bv_map, h->bv_desc, d);
+    LT_LAUNCH_CHECK();
+    return 0;
+}
+
+// bilinear blend of four RGBX taps, separable form: (t00*gx + t01*fx)*gy + (t10*gx + t11*fx)*fy, which is the
+// same integer as sum(tap * w) with OpenCV's weights; R and B ride in the two 16-bit halves for the x pass.
+__device__ __forceinline__ uint32_t blend_rgbx(uint32_t t00, uint32_t t01, uint32_t t10, uint32_t t11, uint32_t f) {
+    const uint32_t fx = f & 31u, fy = (f >> 5) & 31u, gx = 32u - fx, gy = 32u - fy;
+    uint32_t rb0 = (t00 & 0x00FF00FFu) * gx + (t01 & 0x00FF00FFu) * fx;      // lanes <= 255*32
+    uint32_t rb1 = (t10 & 0x00FF00FFu) * gx + (t11 & 0x00FF00FFu) * fx;
+    uint32_t g0 = ((t00 >> 8) & 0xFFu) * gx + ((t01 >> 8) & 0xFFu) * fx;
+    uint32_t g1 = ((t10 >> 8) & 0xFFu) * gx + ((t11 >> 8) & 0xFFu) * fx;
+    uint32_t R = ((rb0 & 0xFFFFu) * gy + (rb1 & 0xFFFFu) * fy + 512u) >> 10;
+    uint32_t B = ((rb0 >> 16) * gy + (rb1 >> 16) * fy + 512u) >> 10;
+    uint32_t G = (g0 * gy + g1 * fy + 512u) >> 10;
+    return R | (G << 8) | (B << 16);
 }
 
 __global__ void __launch_bounds__(256)
-k_warp_planes(const uchar4* __restrict__ und_all, const int2* __restrict__ map, uint32_t* __restrict__ planeR,
+k_warp_planes(const uchar4* __restrict__ und_all, const int2* __restrict__ desc, uint32_t* __restrict__ planeR,
               uint32_t* __restrict__ planeB, uint8_t* __restrict__ bv_rgb,
               const unsigned short* __restrict__ g, const unsigned short* __restrict__ cb, LtDims d) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y, s = blockIdx.z;
     if (x >= d.p2) return;
-    const uchar4* und = und_all + (size_t)s * (d.roi1 - d.roi0) * d.img_w;
+    const uint32_t* und = reinterpret_cast<const uint32_t*>(und_all) + (size_t)s * (d.roi1 - d.roi0) * d.img_w;
     uint32_t r2 = 0, b2 = 0;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         int px = x + half * d.p2;
         if (px < d.bv_w) {
-            Tap4 t = make_taps(__ldg(&map[(size_t)y * d.bv_w + px]));
-            uint32_t a = und_tap(und, d, t.sy, t.sx), b = und_tap(und, d, t.sy, t.sx + 1);
-            uint32_t c = und_tap(und, d, t.sy + 1, t.sx), e = und_tap(und, d, t.sy + 1, t.sx + 1);
-            uint32_t o = blend_rgb(a, b, c, e, t);
-            r2 |= (o & 255) << (16 * half);
+            int2 q = __ldg(&desc[(size_t)y * d.bv_w + px]);
+            const uint32_t* base = und + q.x;
+            const uint32_t f = (uint32_t)q.y;
+            uint32_t t00 = (f & (1u << 10)) ? __ldg(base) : 0u;               // BORDER_CONSTANT 0
+            uint32_t t01 = (f & (1u << 11)) ? __ldg(base + 1) : 0u;
+            uint32_t t10 = (f & (1u << 12)) ? __ldg(base + d.img_w) : 0u;
+            uint32_t t11 = (f & (1u << 13)) ? __ldg(base + d.img_w + 1) : 0u;
+            uint32_t o = blend_rgbx(t00, t01, t10, t11, f);
+            r2 |= (o & 255u) << (16 * half);
             b2 |= (uint32_t)lab_b(o, g, cb) << (16 * half);
             if (bv_rgb) {
                 uint8_t* p = bv_rgb + (((size_t)s * d.bv_h + y) * d.bv_w + px) * 3;
@@ -224,7 +261,7 @@ k_warp_planes(const uchar4* __restrict__ und_all, const int2* __restrict__ map, 
 int lt_launch_warp(lt_handle* h, uint8_t* d_bv_rgb, int n, cudaStream_t st) {
     const LtDims& d = h->d;
     dim3 g(lt_div_up(d.p2, 256), d.bv_h, n);
-    k_warp_planes<<<g, 256, 0, st>>>(h->und_roi, h->bv_map, h->planeR, h->planeB, d_bv_rgb, h->lab_gamma,
+    k_warp_planes<<<g, 256, 0, st>>>(h->und_roi, h->bv_desc, h->planeR, h->planeB, d_bv_rgb, h->lab_gamma,
                                      h->lab_cbrt, d);
     LT_LAUNCH_CHECK();
     return 0;
