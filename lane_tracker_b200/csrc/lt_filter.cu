@@ -56,7 +56,8 @@ template <int K> __host__ __device__ constexpr int ell_uidx(int w) {
 // the morphology kernel
 // ---------------------------------------------------------------------------
 
-constexpr int MORPH_TW = 288;       // packed columns per CTA (= threads)
+constexpr int MORPH_TW = 192;       // packed columns per CTA (= threads); 3 CTAs/SM x 6 warps leaves 112 registers/thread
+constexpr int MORPH_CTAS_PER_SM = 3;
 constexpr int MORPH_RB = 8;         // source rows per table build
 
 template <bool IS_MAX> __device__ __forceinline__ uint32_t op2(uint32_t a, uint32_t b) {
@@ -65,6 +66,13 @@ template <bool IS_MAX> __device__ __forceinline__ uint32_t op2(uint32_t a, uint3
 template <bool IS_MAX> __device__ __forceinline__ uint32_t op3(uint32_t a, uint32_t b, uint32_t c) {
     return IS_MAX ? __vimax3_u16x2(a, b, c) : __vimin3_u16x2(a, b, c);
 }
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 // One staged element: packed pixel pair at plane row r, packed column gx (may lie outside the plane).
 template <bool IS_MAX>
@@ -86,13 +94,17 @@ __device__ __forceinline__ uint32_t stage_elem(const uint32_t* __restrict__ src,
 }
 
 template <int K, bool IS_MAX, bool TOPHAT>
-__global__ void __launch_bounds__(MORPH_TW, 2)
+__global__ void __launch_bounds__(MORPH_TW, MORPH_CTAS_PER_SM)
 k_morph(const uint32_t* __restrict__ src_all, uint32_t* __restrict__ dst_all, const uint32_t* __restrict__ orig_all,
         LtDims d, int band_rows, size_t stream_stride, const int* __restrict__ list, const int* __restrict__ count) {
+    // Shared-memory tables hold ROW PAIRS: element (pair m, column c) is a uint2 {row 2m, row 2m+1}.  Every table
+    // access is one LDS.64/STS.64 serving two source rows, and the vertical pipeline advances two rows per step
+    // with a single three-input VIMNMX3 per accumulator:
+    //     A[j] <- op3(A[j+2], H_a[hw(j+1)], H_b[hw(j)])        (a, b = the two rows of the pair)
     using E = Ellipse<K>;
     constexpr int R = E::R;
-    constexpr int TW = MORPH_TW, RB = MORPH_RB;
-    constexpr int TE = TW + 2 * R;          // staged elements per row
+    constexpr int TW = MORPH_TW, RB = MORPH_RB, RP = RB / 2;
+    constexpr int TE = TW + 2 * R;          // staged columns per row
     constexpr int TEA = TE + 32;            // + slack that always holds PAD
     constexpr bool HAS32 = (2 * R + 1) >= 32;
     constexpr int NTAB = HAS32 ? 5 : 4;
@@ -104,11 +116,13 @@ k_morph(const uint32_t* __restrict__ src_all, uint32_t* __restrict__ dst_all, co
     int s = list ? list[slot] : slot;
 
     extern __shared__ uint32_t smem[];
-    uint32_t* T0 = smem;
-    uint32_t* T4 = T0 + RB * TEA;
-    uint32_t* T8 = T4 + RB * TEA;
-    uint32_t* T16 = T8 + RB * TEA;
-    uint32_t* T32 = T16 + RB * TEA;   // only touched when HAS32
+    uint2* T0 = reinterpret_cast<uint2*>(smem);
+    uint2* T4 = T0 + RP * TEA;
+    uint2* T8 = T4 + RP * TEA;
+    uint2* T16 = T8 + RP * TEA;
+    uint2* T32 = T16 + RP * TEA;      // only touched when HAS32
+    uint2* S = T0 + NTAB * RP * TEA;  // [RP][TE]   raw words of the next row block, filled by cp.async
+    uint2* OG = S + RP * TE;          // [2][RP][TW] original-plane rows for the top-hat epilogue (double buffered)
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * TW;
@@ -139,118 +153,158 @@ k_morph(const uint32_t* __restrict__ src_all, uint32_t* __restrict__ dst_all, co
         c.off = max(0, min(c.off, d.p2 - 1));
         return c;
     };
-    auto fetch = [&](int r, const ColDesc& c) -> uint32_t {
-        if ((unsigned)r >= (unsigned)d.bv_h) return PAD2;
-        return __byte_perm(__ldg(&src[(size_t)r * d.p2 + c.off]), PAD2, c.sel);
+    // Staging is asynchronous (cp.async straight into shared memory, no registers held across the walk); the
+    // raw words get their lane selection / padding (one PRMT) when the block is published into T0.
+    auto finish = [&](uint32_t raw, int r, const ColDesc& c) -> uint32_t {
+        return ((unsigned)r < (unsigned)d.bv_h) ? __byte_perm(raw, PAD2, c.sel) : PAD2;
     };
-    // Work split of a row block: every thread owns table column `tid` of all RB rows; the 2R halo columns of
-    // the RB rows (NX elements) are spread evenly, at most NXT per thread.
-    constexpr int NX = 2 * R * RB;
-    constexpr int NXT = (NX + TW - 1) / TW;
+    // Work split of a row block: every thread owns table column `tid` of all RP row pairs; the 2R halo columns
+    // of the RP pairs (NX pair-elements) go to the first NX threads.
+    constexpr int NX = 2 * R * RP;
+    constexpr int NXT = (NX + TW - 1) / TW;         // halo pair-elements per thread (1 or 2)
     const ColDesc cmain = describe(tid);
+    bool xok[NXT];
+    int xpair[NXT], xidx[NXT], xsidx[NXT];
     ColDesc cx[NXT];
-    int xrow[NXT], xidx[NXT];
 #pragma unroll
-    for (int x = 0; x < NXT; ++x) {
-        int e = tid + x * TW;
-        bool ok = e < NX;
-        int rr = ok ? e / (2 * R) : 0, i = TW + (ok ? e - rr * 2 * R : 0);
-        xrow[x] = ok ? rr : -1;
-        xidx[x] = rr * TEA + i;
-        cx[x] = describe(i);
+    for (int q = 0; q < NXT; ++q) {
+        const int e = tid + q * TW;
+        xok[q] = e < NX;
+        xpair[q] = xok[q] ? e / (2 * R) : 0;
+        const int xcol = TW + (xok[q] ? e - xpair[q] * 2 * R : 0);
+        xidx[q] = xpair[q] * TEA + xcol;
+        xsidx[q] = xpair[q] * TE + xcol;
+        cx[q] = describe(xcol);
     }
+    const int gx = x0 + tid;                       // this thread's packed column
+    const bool col_ok = gx < d.p2;
+    const uint32_t lane_mask = (gx + d.p2 < d.bv_w) ? 0xFFFFFFFFu : 0x0000FFFFu;
 
-    uint32_t pf[RB + NXT];
-    auto prefetch = [&](int rbase) {
+    auto stage_async = [&](int rbase, int buf) {
+        uint32_t* Sw = reinterpret_cast<uint32_t*>(S);
 #pragma unroll
-        for (int rr = 0; rr < RB; ++rr) pf[rr] = fetch(rbase + rr, cmain);
+        for (int rr = 0; rr < RB; ++rr) {
+            const int r = rbase + rr;
+            if ((unsigned)r < (unsigned)d.bv_h)
+                cp_async4(&Sw[2 * ((rr >> 1) * TE + tid) + (rr & 1)], &src[(size_t)r * d.p2 + cmain.off]);
+        }
 #pragma unroll
-        for (int x = 0; x < NXT; ++x) pf[RB + x] = (xrow[x] >= 0) ? fetch(rbase + xrow[x], cx[x]) : PAD2;
+        for (int q = 0; q < NXT; ++q) {
+            if (xok[q]) {
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int r = rbase + 2 * xpair[q] + t;
+                    if ((unsigned)r < (unsigned)d.bv_h)
+                        cp_async4(&Sw[2 * xsidx[q] + t], &src[(size_t)r * d.p2 + cx[q].off]);
+                }
+            }
+        }
+        if (TOPHAT && col_ok) {
+            uint32_t* Ow = reinterpret_cast<uint32_t*>(OG + buf * RP * TW);
+#pragma unroll
+            for (int rr = 0; rr < RB; ++rr) {
+                const int y = rbase - R + rr;       // output rows completed while this block is walked
+                if ((unsigned)y < (unsigned)d.bv_h)
+                    cp_async4(&Ow[2 * ((rr >> 1) * TW + tid) + (rr & 1)], &orig[(size_t)y * d.p2 + gx]);
+            }
+        }
+        cp_async_commit();
     };
-    prefetch(r_begin);
+    stage_async(r_begin, 0);
 
     uint32_t A[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) A[j] = PAD2;
 
-    const int gx = x0 + tid;                       // this thread's packed column
-    const bool col_ok = gx < d.p2;
-    const uint32_t lane_mask = (gx + d.p2 < d.bv_w) ? 0xFFFFFFFFu : 0x0000FFFFu;
-    __syncthreads();
+    auto o2 = [](uint2 a, uint2 b) { return make_uint2(op2<IS_MAX>(a.x, b.x), op2<IS_MAX>(a.y, b.y)); };
+    auto o3 = [](uint2 a, uint2 b, uint2 c) { return make_uint2(op3<IS_MAX>(a.x, b.x, c.x), op3<IS_MAX>(a.y, b.y, c.y)); };
 
     for (int blk = 0; blk < nblk; ++blk) {
         const int rb0 = r_begin + blk * RB;
-        // publish the staged rows, then start fetching the next block
-#pragma unroll
-        for (int rr = 0; rr < RB; ++rr) T0[rr * TEA + tid] = pf[rr];
-#pragma unroll
-        for (int x = 0; x < NXT; ++x) if (xrow[x] >= 0) T0[xidx[x]] = pf[RB + x];
+        // the staged block has landed: give the raw words their lanes / padding and publish them as T0
+        cp_async_wait_all();
         __syncthreads();
-        if (blk + 1 < nblk) prefetch(rb0 + RB);
+#pragma unroll
+        for (int m = 0; m < RP; ++m) {
+            const uint2 raw = S[m * TE + tid];
+            T0[m * TEA + tid] = make_uint2(finish(raw.x, rb0 + 2 * m, cmain), finish(raw.y, rb0 + 2 * m + 1, cmain));
+        }
+#pragma unroll
+        for (int q = 0; q < NXT; ++q)
+            if (xok[q]) {
+                const uint2 raw = S[xsidx[q]];
+                T0[xidx[q]] = make_uint2(finish(raw.x, rb0 + 2 * xpair[q], cx[q]), finish(raw.y, rb0 + 2 * xpair[q] + 1, cx[q]));
+            }
+        __syncthreads();
+        if (blk + 1 < nblk) stage_async(rb0 + RB, (blk + 1) & 1);     // S is free again: fetch the next block
         // window tables: T4 -> (T8, T16) -> T32
         auto build4 = [&](int idx) {
-            const uint32_t* t = T0 + idx;
-            T4[idx] = op2<IS_MAX>(op3<IS_MAX>(t[0], t[1], t[2]), t[3]);
+            const uint2* t = T0 + idx;
+            T4[idx] = o2(o3(t[0], t[1], t[2]), t[3]);
         };
         auto build816 = [&](int idx) {
-            const uint32_t* t = T4 + idx;
-            uint32_t v8 = op2<IS_MAX>(t[0], t[4]);
+            const uint2* t = T4 + idx;
+            uint2 v8 = o2(t[0], t[4]);
             T8[idx] = v8;
-            T16[idx] = op3<IS_MAX>(v8, t[8], t[12]);
+            T16[idx] = o3(v8, t[8], t[12]);
         };
-        auto build32 = [&](int idx) { T32[idx] = op2<IS_MAX>(T16[idx], T16[idx + 16]); };
+        auto build32 = [&](int idx) { T32[idx] = o2(T16[idx], T16[idx + 16]); };
 #pragma unroll
-        for (int rr = 0; rr < RB; ++rr) build4(rr * TEA + tid);
+        for (int m = 0; m < RP; ++m) build4(m * TEA + tid);
 #pragma unroll
-        for (int x = 0; x < NXT; ++x) if (xrow[x] >= 0) build4(xidx[x]);
+        for (int q = 0; q < NXT; ++q) if (xok[q]) build4(xidx[q]);
         __syncthreads();
 #pragma unroll
-        for (int rr = 0; rr < RB; ++rr) build816(rr * TEA + tid);
+        for (int m = 0; m < RP; ++m) build816(m * TEA + tid);
 #pragma unroll
-        for (int x = 0; x < NXT; ++x) if (xrow[x] >= 0) build816(xidx[x]);
+        for (int q = 0; q < NXT; ++q) if (xok[q]) build816(xidx[q]);
         __syncthreads();
         if (HAS32) {
 #pragma unroll
-            for (int rr = 0; rr < RB; ++rr) build32(rr * TEA + tid);
-#pragma unroll
-            for (int x = 0; x < NXT; ++x) if (xrow[x] >= 0) build32(xidx[x]);
+            for (int m = 0; m < RP; ++m) build32(m * TEA + tid);
+    #pragma unroll
+        for (int q = 0; q < NXT; ++q) if (xok[q]) build32(xidx[q]);
             __syncthreads();
         }
-        // walk the RB rows of this block
+        // walk the RP row pairs of this block
 #pragma unroll 1
-        for (int rr = 0; rr < RB; ++rr) {
-            const int r = rb0 + rr;
+        for (int m = 0; m < RP; ++m) {
+            const int r = rb0 + 2 * m;              // source rows r (a) and r+1 (b)
             if (r >= r_end) break;
-            const int y = r - R;                    // output row completed by source row r
-            uint32_t og = 0;
-            const bool emit = col_ok && y >= yb0;   // y < yb1 is implied by r < r_end
-            if (TOPHAT && emit) og = __ldg(&orig[(size_t)y * d.p2 + gx]);
-            const int base = rr * TEA + tid + R;    // index of this thread's column in the tables
-            uint32_t H[E::ND];
+            const int ya = r - R;                   // output rows completed by this pair: ya and ya+1
+            const bool emit_a = col_ok && ya >= yb0 && ya < yb1;
+            const bool emit_b = col_ok && ya + 1 >= yb0 && ya + 1 < yb1;
+            uint2 og = make_uint2(0u, 0u);
+            if (TOPHAT) og = OG[(blk & 1) * RP * TW + m * TW + tid];
+            const int base = m * TEA + tid + R;     // this thread's column in the tables
+            uint32_t Ha[E::ND], Hb[E::ND];
 #pragma unroll
             for (int u = 0; u < E::ND; ++u) {
                 const int w = E::uniq(u);
                 const int len = 2 * w + 1;
-                if (w == 0) {
-                    H[u] = T0[base];
-                } else if (len >= 32) {
-                    H[u] = op2<IS_MAX>(T32[base - w], T32[base + w - 31]);
-                } else if (len >= 16) {
-                    H[u] = op2<IS_MAX>(T16[base - w], T16[base + w - 15]);
-                } else {
-                    H[u] = op2<IS_MAX>(T8[base - w], T8[base + w - 7]);
-                }
+                uint2 h;
+                if (w == 0) h = T0[base];
+                else if (len >= 32) h = o2(T32[base - w], T32[base + w - 31]);
+                else if (len >= 16) h = o2(T16[base - w], T16[base + w - 15]);
+                else h = o2(T8[base - w], T8[base + w - 7]);
+                Ha[u] = h.x;
+                Hb[u] = h.y;
             }
+            const uint32_t out_a = op2<IS_MAX>(A[1], Ha[ell_uidx<K>(E::hw(0))]);
 #pragma unroll
-            for (int j = 0; j < K - 1; ++j) A[j] = op2<IS_MAX>(A[j + 1], H[ell_uidx<K>(E::hw(j))]);
-            A[K - 1] = H[ell_uidx<K>(E::hw(K - 1))];
-            if (emit) {
-                uint32_t v = A[0];
-                if (TOPHAT) v = og - v;             // open <= src per lane: no borrow between lanes
-                dst[(size_t)y * d.p2 + gx] = v & lane_mask;
+            for (int j = 0; j < K - 2; ++j)
+                A[j] = op3<IS_MAX>(A[j + 2], Ha[ell_uidx<K>(E::hw(j + 1))], Hb[ell_uidx<K>(E::hw(j))]);
+            A[K - 2] = op2<IS_MAX>(Ha[ell_uidx<K>(E::hw(K - 1))], Hb[ell_uidx<K>(E::hw(K - 2))]);
+            A[K - 1] = Hb[ell_uidx<K>(E::hw(K - 1))];
+            if (emit_a) {
+                uint32_t v = TOPHAT ? og.x - out_a : out_a;      // open <= src per lane: no borrow between lanes
+                dst[(size_t)ya * d.p2 + gx] = v & lane_mask;
+            }
+            if (emit_b) {
+                uint32_t v = TOPHAT ? og.y - A[0] : A[0];
+                dst[(size_t)(ya + 1) * d.p2 + gx] = v & lane_mask;
             }
         }
-        __syncthreads();
     }
 }
 
@@ -260,7 +314,7 @@ static int launch_morph(lt_handle* h, const uint32_t* src, uint32_t* dst, const 
     constexpr int R = Ellipse<K>::R;
     constexpr int TEA = MORPH_TW + 2 * R + 32;
     constexpr int NTAB = (2 * R + 1 >= 32) ? 5 : 4;
-    size_t smem = (size_t)NTAB * MORPH_RB * TEA * sizeof(uint32_t);
+    size_t smem = ((size_t)NTAB * MORPH_RB * TEA + (size_t)MORPH_RB * (MORPH_TW + 2 * R) + (TOPHAT ? 2 * MORPH_RB * MORPH_TW : 0)) * sizeof(uint32_t);
     static bool attr_done = false;
     if (!attr_done) {
         LT_CUDA(cudaFuncSetAttribute(k_morph<K, IS_MAX, TOPHAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -799,7 +853,7 @@ int lt_launch_filter(lt_handle* h, int n, const LtAttemptParams& p, const int* l
         int tiles = lt_div_up(d.p2, MORPH_TW);
         int bands = 1;
         double best = 1e30;
-        const int slots = 2 * (h->sm_count > 0 ? h->sm_count : 148);
+        const int slots = MORPH_CTAS_PER_SM * (h->sm_count > 0 ? h->sm_count : 148);
         for (int b = 1; b <= 32; ++b) {
             int br = lt_div_up(d.bv_h, b), ctas = n * tiles * lt_div_up(d.bv_h, br);
             double cost = (double)lt_div_up(ctas, slots) * (br + 54);
