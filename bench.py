@@ -298,8 +298,18 @@ def run_gpu_arm(args):
         dom = max(morph, key=morph.get)
         dom_ms_per_launch = morph[dom] / max(prof_calls, 1)
         achieved = S * MORPH_ALGO_BYTES_PER_FRAME / (dom_ms_per_launch * 1e-3) / 1e9 if dom_ms_per_launch > 0 else 0.0
-        roofline = {"bound": "hbm", "kernel": "k_morph<%s> (%s)" % ("55" if "55" in dom else "29", dom),
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        kname = "k_morph<%s, %s>" % ("55" if "55" in dom else "29", "1, 1" if "tophat" in dom else "0, 0")
+        traffic = None
+        try:    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes_per_launch"].get(kname)
+            if traffic is not None:
+                traffic = traffic * S / tj["streams"]
+        except Exception:
+            traffic = None
+        roofline = {"bound": "hbm", "kernel": "%s (%s)" % (kname, dom),
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "peak_source": peak_src, "ms_per_launch": dom_ms_per_launch,
                     "algorithmic_bytes_per_launch": S * MORPH_ALGO_BYTES_PER_FRAME,
                     "share_of_step": morph[dom] / total_stage if total_stage else None,
