@@ -226,7 +226,6 @@ def run_gpu_arm(args):
     pool_dev = pool_host.to(dev).permute(1, 0, 2, 3, 4).contiguous()   # [P, S, H, W, 3]: one contiguous batch per step
     host_batches = pool_host.permute(1, 0, 2, 3, 4).contiguous().pin_memory()
     out_dev = torch.empty_like(pool_dev[0])
-    out_host = torch.empty(out_dev.shape, dtype=torch.uint8).pin_memory()
 
     trk = BatchedLaneTracker(S, **synth.shipped_calibration(), device=local)
     lib = _lib.load()
@@ -265,22 +264,35 @@ def run_gpu_arm(args):
     band_frac = float((res["search_mode"] == 1).mean())
 
     # ---- end to end: pinned host frames in, annotated frames + results out, every step ----------
-    def e2e_step(i):
-        pool_dev[i % P].copy_(host_batches[i % P], non_blocking=True)
-        trk.process_async(pool_dev[i % P], out_dev)
-        out_host.copy_(out_dev, non_blocking=True)
-        trk._results_host.copy_(trk._results_dev, non_blocking=True)
+    # through the public HostPipeline API: H2D of step k+1, kernels of step k and D2H of step k-1 overlap
+    from lane_tracker_b200 import HostPipeline
+    trk.reset()
+    pipe = HostPipeline(trk, depth=3, overlay=True)
+    checks = []
+
+    def consume(batch):
+        out_h, res_h = batch
+        checks.append(int(res_h["counter"][0]))          # the host really reads every step's result
 
     for i in range(min(args.warmup, 3)):
-        e2e_step(i)
+        pipe.submit(host_batches[i % P])
+        for b in pipe.ready():
+            consume(b)
+    for b in pipe.drain():
+        consume(b)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record(stream)
+    f0.record(pipe.s_in)
     for i in range(args.steps):
-        e2e_step(i)
-    f1.record(stream)
+        pipe.submit(host_batches[i % P])
+        for b in pipe.ready():
+            consume(b)
+    for b in pipe.drain():
+        consume(b)
+    f1.record(pipe.s_out)
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    assert checks[-1] == min(args.warmup, 3) + args.steps, "e2e pipeline lost a step"
 
     if distributed:
         t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)

@@ -6,11 +6,11 @@ importing them without either raises.  ``lane_tracker_b200.synth`` (test/bench d
 """
 from .utils import load_camera_calib, load_warp_params  # noqa: F401
 
-__all__ = ["LaneTracker", "BatchedLaneTracker", "load_camera_calib", "load_warp_params"]
+__all__ = ["LaneTracker", "BatchedLaneTracker", "HostPipeline", "load_camera_calib", "load_warp_params"]
 
 
 def __getattr__(name):
-    if name in ("LaneTracker", "BatchedLaneTracker", "make_params", "RESULT_DTYPE"):
+    if name in ("LaneTracker", "BatchedLaneTracker", "HostPipeline", "make_params", "RESULT_DTYPE"):
         from . import tracker
         return getattr(tracker, name)
     raise AttributeError(name)

@@ -143,16 +143,20 @@ class BatchedLaneTracker:
             raise ValueError("got %d frames for %d streams" % (frames.shape[0], self.n_streams))
         return int(frames.shape[0])
 
-    def process_async(self, frames, out=None, params=None, **kw):
-        """Enqueue one frame per stream on the current CUDA stream; returns the device result buffer.
+    def process_async(self, frames, out=None, params=None, results_dev=None, **kw):
+        """Enqueue one frame per stream on the current CUDA stream; returns the number of streams.
 
-        frames: uint8 CUDA tensor [n, H, W, 3] (RGB).  out: same shape or None (fits-only mode)."""
+        frames: uint8 CUDA tensor [n, H, W, 3] (RGB).  out: same shape or None (fits-only mode).
+        results_dev: optional uint8 CUDA buffer of n * RESULT_DTYPE.itemsize bytes (default: internal)."""
         n = self._check_frames(frames)
         if out is not None and (out.shape != frames.shape or out.dtype != torch.uint8 or not out.is_cuda or
                                 not out.is_contiguous()):
             raise ValueError("out must match frames")
         p = params if params is not None else make_params(**kw)
-        check(self.lib.lt_process(self._h, _ptr(frames), _ptr(out), n, C.byref(p), _ptr(self._results_dev),
+        res = self._results_dev if results_dev is None else results_dev
+        if res.numel() < n * RESULT_DTYPE.itemsize or not res.is_cuda:
+            raise ValueError("results buffer too small")
+        check(self.lib.lt_process(self._h, _ptr(frames), _ptr(out), n, C.byref(p), _ptr(res),
                                   _stream_ptr(self.device)))
         return n
 
@@ -336,6 +340,100 @@ class BatchedLaneTracker:
             out = np.zeros((bh, bw), dtype=np.uint8)
         check(self.lib.lt_debug_read(self._h, code, int(stream_id), out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
+
+
+class HostPipeline:
+    """Host-to-host streaming through a ``BatchedLaneTracker``: pinned host frames in, annotated frames and
+    result records out, with the H2D copy of batch k+1, the kernels of batch k and the D2H copy of batch k-1
+    overlapped on three CUDA streams (`depth` buffer sets in flight).  Batches are processed in submission
+    order, so per-stream tracking state evolves exactly as with sequential ``process`` calls.
+
+        pipe = HostPipeline(tracker)
+        for batch in batches:                 # pinned uint8 [n, H, W, 3]
+            pipe.submit(batch)
+            for out, results in pipe.ready(): ...   # finished batches, oldest first
+        for out, results in pipe.drain(): ...
+    """
+
+    def __init__(self, tracker, depth=3, overlay=True, params=None):
+        self.t = tracker
+        self.depth = int(depth)
+        self.overlay = overlay
+        self.params = params if params is not None else make_params()
+        dev = tracker.device
+        w, h = tracker.img_size
+        S = tracker.n_streams
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.slots = []
+        for _ in range(self.depth):
+            self.slots.append(dict(
+                d_in=torch.empty((S, h, w, 3), dtype=torch.uint8, device=dev),
+                d_out=torch.empty((S, h, w, 3), dtype=torch.uint8, device=dev) if overlay else None,
+                d_res=torch.zeros(S * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev),
+                h_out=torch.empty((S, h, w, 3), dtype=torch.uint8).pin_memory() if overlay else None,
+                h_res=torch.zeros(S * RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory(),
+                e_in=torch.cuda.Event(), e_run=torch.cuda.Event(), e_out=torch.cuda.Event(), n=0, busy=False))
+        self.head = 0          # next slot to submit into
+        self.tail = 0          # oldest slot in flight
+        self.inflight = 0
+
+    def submit(self, host_frames):
+        if self.inflight == self.depth:
+            raise RuntimeError("pipeline full: collect a finished batch first")
+        if not (host_frames.dtype == torch.uint8 and host_frames.is_pinned() and host_frames.is_contiguous()):
+            raise ValueError("host_frames must be a contiguous pinned uint8 tensor")
+        sl = self.slots[self.head]
+        n = int(host_frames.shape[0])
+        sl["n"] = n
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(sl["e_run"])            # the kernels that last read this input buffer are done
+            sl["d_in"][:n].copy_(host_frames, non_blocking=True)
+            sl["e_in"].record(self.s_in)
+        with torch.cuda.stream(self.s_run):
+            self.s_run.wait_event(sl["e_in"])
+            self.s_run.wait_event(sl["e_out"])           # the previous D2H out of this output buffer is done
+            self.t.process_async(sl["d_in"][:n], sl["d_out"][:n] if self.overlay else None, params=self.params,
+                                 results_dev=sl["d_res"])
+            sl["e_run"].record(self.s_run)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(sl["e_run"])
+            if self.overlay:
+                sl["h_out"][:n].copy_(sl["d_out"][:n], non_blocking=True)
+            sl["h_res"].copy_(sl["d_res"], non_blocking=True)
+            sl["e_out"].record(self.s_out)
+        sl["busy"] = True
+        self.head = (self.head + 1) % self.depth
+        self.inflight += 1
+
+    def _collect(self, block):
+        sl = self.slots[self.tail]
+        if not sl["busy"]:
+            return None
+        if not block and not sl["e_out"].query():
+            return None
+        sl["e_out"].synchronize()
+        n = sl["n"]
+        res = sl["h_res"][:n * RESULT_DTYPE.itemsize].numpy().view(RESULT_DTYPE)
+        out = sl["h_out"][:n] if self.overlay else None
+        sl["busy"] = False
+        self.tail = (self.tail + 1) % self.depth
+        self.inflight -= 1
+        return out, res
+
+    def ready(self):
+        """Finished batches (views into the pipeline's pinned buffers: consume before the slot is reused)."""
+        while True:
+            if self.inflight < self.depth:
+                got = self._collect(block=False)
+            else:
+                got = self._collect(block=True)         # make room for the next submit
+            if got is None:
+                return
+            yield got
+
+    def drain(self):
+        while self.inflight:
+            yield self._collect(block=True)
 
 
 class LaneTracker:

@@ -387,3 +387,32 @@ def test_error_conventions(bt, torch_mod):
         lt.process(np.zeros((10, 10, 3), np.uint8))
     with pytest.raises(_lib.LaneTrackerError):
         bt.filter_lane_points(torch_mod.zeros((1, 1100, 1080, 3), dtype=torch_mod.uint8, device="cuda"), "neighborhood", 14, 5, 35, 5)
+
+
+def test_host_pipeline_matches_sequential_process(torch_mod):
+    """The overlapped host-to-host pipeline returns exactly what sequential process() calls return."""
+    from lane_tracker_b200 import BatchedLaneTracker, HostPipeline
+    S, T = 2, 7
+    vids = [synth.RoadVideo(10 + s) for s in range(S)]
+    batches = [torch_mod.from_numpy(np.stack([v.frame(t) for v in vids])).pin_memory() for t in range(T)]
+    a = BatchedLaneTracker(S, **CAL)
+    b = BatchedLaneTracker(S, **CAL)
+    want = []
+    for t in range(T):
+        d = batches[t].cuda()
+        out = torch_mod.empty_like(d)
+        res = a.process(d, out)
+        want.append((out.cpu().numpy(), res.copy()))
+    pipe = HostPipeline(b, depth=3)
+    got = []
+    for t in range(T):
+        pipe.submit(batches[t])
+        for out, res in pipe.ready():
+            got.append((out.numpy().copy(), res.copy()))
+    for out, res in pipe.drain():
+        got.append((out.numpy().copy(), res.copy()))
+    assert len(got) == T
+    for t in range(T):
+        assert np.array_equal(got[t][0], want[t][0]), t
+        assert got[t][1].tobytes() == want[t][1].tobytes(), t
+    a.close(); b.close()
