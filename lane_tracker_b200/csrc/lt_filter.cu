@@ -242,30 +242,24 @@ k_morph(const uint32_t* __restrict__ src_all, uint32_t* __restrict__ dst_all, co
             const uint2* t = T0 + idx;
             T4[idx] = o2(o3(t[0], t[1], t[2]), t[3]);
         };
-        auto build816 = [&](int idx) {
+        auto build81632 = [&](int idx) {
             const uint2* t = T4 + idx;
             uint2 v8 = o2(t[0], t[4]);
+            uint2 v16 = o3(v8, t[8], t[12]);
             T8[idx] = v8;
-            T16[idx] = o3(v8, t[8], t[12]);
+            T16[idx] = v16;
+            if (HAS32) T32[idx] = o3(v16, o2(t[16], t[20]), o2(t[24], t[28]));   // no extra barrier for T32
         };
-        auto build32 = [&](int idx) { T32[idx] = o2(T16[idx], T16[idx + 16]); };
 #pragma unroll
         for (int m = 0; m < RP; ++m) build4(m * TEA + tid);
 #pragma unroll
         for (int q = 0; q < NXT; ++q) if (xok[q]) build4(xidx[q]);
         __syncthreads();
 #pragma unroll
-        for (int m = 0; m < RP; ++m) build816(m * TEA + tid);
+        for (int m = 0; m < RP; ++m) build81632(m * TEA + tid);
 #pragma unroll
-        for (int q = 0; q < NXT; ++q) if (xok[q]) build816(xidx[q]);
+        for (int q = 0; q < NXT; ++q) if (xok[q]) build81632(xidx[q]);
         __syncthreads();
-        if (HAS32) {
-#pragma unroll
-            for (int m = 0; m < RP; ++m) build32(m * TEA + tid);
-    #pragma unroll
-        for (int q = 0; q < NXT; ++q) if (xok[q]) build32(xidx[q]);
-            __syncthreads();
-        }
         // walk the RP row pairs of this block
 #pragma unroll 1
         for (int m = 0; m < RP; ++m) {
@@ -401,34 +395,38 @@ k_cross_h(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_al
         return (e >> 16) & 0xFFu;
     };
     const int xv = xint & ~3;                                    // [0, xv): both lanes real, 16-byte vector loads
-    for (int r = threadIdx.x >> 5; r < CROSSH_ROWS; r += CROSSH_WARPS) {
-        const int y = y0 + r;
-        unsigned short* trow_w = tile + r * pitch;
-        if (y >= d.bv_h) {
-            for (int i = threadIdx.x & 31; i < ncol; i += 32) trow_w[i] = 0;
-            continue;
-        }
-        const uint32_t* row = src + (size_t)y * d.p2;
-        for (int g0 = (threadIdx.x & 31) * 4; g0 < xv; g0 += 512) {          // 4 x 16 B in flight per lane
-            uint4 v[4];
+    {
+        // each warp stages rows warp, warp+4, ...: one 16 B chunk of all its 8 rows in flight per lane
+        constexpr int RPW = CROSSH_ROWS / CROSSH_WARPS;
+        const int wq = threadIdx.x >> 5, ln = threadIdx.x & 31;
+        for (int g0 = ln * 4; g0 < xv; g0 += 128) {
+            uint4 v[RPW];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (g0 + 128 * u < xv) v[u] = __ldg(reinterpret_cast<const uint4*>(row + g0 + 128 * u));
+            for (int j = 0; j < RPW; ++j) {
+                const int y = y0 + wq + j * CROSSH_WARPS;
+                v[j] = (y < d.bv_h) ? __ldg(reinterpret_cast<const uint4*>(src + (size_t)y * d.p2 + g0)) : make_uint4(0, 0, 0, 0);
+            }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (g0 + 128 * u < xv) {
-                    unsigned short* o = trow_w + k + g0 + 128 * u;
-                    o[0] = (unsigned short)__byte_perm(v[u].x, 0, 0x4420);
-                    o[1] = (unsigned short)__byte_perm(v[u].y, 0, 0x4420);
-                    o[2] = (unsigned short)__byte_perm(v[u].z, 0, 0x4420);
-                    o[3] = (unsigned short)__byte_perm(v[u].w, 0, 0x4420);
-                }
+            for (int j = 0; j < RPW; ++j) {
+                unsigned short* o = tile + (wq + j * CROSSH_WARPS) * pitch + k + g0;
+                o[0] = (unsigned short)__byte_perm(v[j].x, 0, 0x4420);
+                o[1] = (unsigned short)__byte_perm(v[j].y, 0, 0x4420);
+                o[2] = (unsigned short)__byte_perm(v[j].z, 0, 0x4420);
+                o[3] = (unsigned short)__byte_perm(v[j].w, 0, 0x4420);
+            }
         }
-        // halo columns and the tail where the high strip leaves the image: generic path
+        // halo columns and the tail where the high strip leaves the image: generic path, all rows of the warp batched
         const int nrest = k + (ncol - k - xv);
-        for (int j = threadIdx.x & 31; j < nrest; j += 32) {
-            int i = j < k ? j : j - k + k + xv;
-            trow_w[i] = (unsigned short)fetch(row, i - k);
+        for (int j0 = ln; j0 < nrest; j0 += 32) {
+            const int i = j0 < k ? j0 : j0 + xv;
+            uint32_t v[RPW];
+#pragma unroll
+            for (int j = 0; j < RPW; ++j) {
+                const int y = y0 + wq + j * CROSSH_WARPS;
+                v[j] = (y < d.bv_h) ? fetch(src + (size_t)y * d.p2, i - k) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < RPW; ++j) tile[(wq + j * CROSSH_WARPS) * pitch + i] = (unsigned short)v[j];
         }
     }
     __syncthreads();
@@ -581,39 +579,41 @@ k_cross_v(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_al
 
 __global__ void __launch_bounds__(ROWK_WARPS * 32)
 k_box_h(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ hs_all, LtDims d, int half,
-        size_t plane_stride, const int* __restrict__ list, const int* __restrict__ count) {
-    int slot = blockIdx.y;
-    if (count != nullptr && slot >= *count) return;
-    int s = list ? list[slot] : slot;
+        size_t plane_stride, const int* __restrict__ list, const int* __restrict__ count, int nslots) {
     extern __shared__ uint32_t smem[];
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int y = blockIdx.x * ROWK_WARPS + warp;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int y = blockIdx.x * ROWK_WARPS + warp;
     if (y >= d.bv_h) return;
-    int wpad = (d.bv_w + 32) & ~31;
+    const int wpad = (d.bv_w + 32) & ~31;
     uint32_t* lin = smem + (size_t)warp * 2 * wpad;
     uint32_t* E = lin + wpad;
-    warp_row_prefix(plane_all + (size_t)s * plane_stride + (size_t)y * d.p2, d, lin, E, lane);
-    uint32_t* hrow = hs_all + (size_t)s * plane_stride + (size_t)y * d.p2;
-    const int W = d.bv_w;
-    const uint32_t first = lin[0], last = lin[W - 1];
-    auto rowsum = [&](int c) -> uint32_t {
-        uint32_t v = E[min(c + half + 1, W)] - E[max(c - half, 0)];
-        v += (uint32_t)max(half - c, 0) * first + (uint32_t)max(c + half - (W - 1), 0) * last;
-        return v;
-    };
-    for (int x = lane; x < d.p2; x += 32) {
-        uint32_t lo = rowsum(x), hi = (x + d.p2 < W) ? rowsum(x + d.p2) : 0u;
-        hrow[x] = lo | (hi << 16);
+    const int nsl = count ? *count : nslots;          // attempt-2 launches loop over the (usually empty) retry list
+    for (int slot = blockIdx.y; slot < nsl; slot += gridDim.y) {
+        const int s = list ? list[slot] : slot;
+        warp_row_prefix(plane_all + (size_t)s * plane_stride + (size_t)y * d.p2, d, lin, E, lane);
+        uint32_t* hrow = hs_all + (size_t)s * plane_stride + (size_t)y * d.p2;
+        const int W = d.bv_w;
+        const uint32_t first = lin[0], last = lin[W - 1];
+        auto rowsum = [&](int c) -> uint32_t {
+            uint32_t v = E[min(c + half + 1, W)] - E[max(c - half, 0)];
+            v += (uint32_t)max(half - c, 0) * first + (uint32_t)max(c + half - (W - 1), 0) * last;
+            return v;
+        };
+        for (int x = lane; x < d.p2; x += 32) {
+            uint32_t lo = rowsum(x), hi = (x + d.p2 < W) ? rowsum(x + d.p2) : 0u;
+            hrow[x] = lo | (hi << 16);
+        }
+        __syncwarp();
     }
 }
 
 __global__ void __launch_bounds__(32)
 k_box_v(const uint32_t* __restrict__ plane_all, const uint32_t* __restrict__ hs_all, uint32_t* __restrict__ bits_all,
         LtDims d, int half, int c, int accumulate, int band_rows, size_t plane_stride, size_t bits_stride,
-        const int* __restrict__ list, const int* __restrict__ count) {
-    int slot = blockIdx.z;
-    if (count != nullptr && slot >= *count) return;
-    int s = list ? list[slot] : slot;
+        const int* __restrict__ list, const int* __restrict__ count, int nslots) {
+    const int nsl = count ? *count : nslots;
+    for (int slot = blockIdx.z; slot < nsl; slot += gridDim.z) {
+    const int s = list ? list[slot] : slot;
     int lane = threadIdx.x;
     int x = blockIdx.x * 32 + lane;
     int yb0 = blockIdx.y * band_rows, yb1 = min(yb0 + band_rows, d.bv_h);
@@ -640,6 +640,7 @@ k_box_v(const uint32_t* __restrict__ plane_all, const uint32_t* __restrict__ hs_
         uint32_t a = ldh(y + half + 1), b = ldh(y - half);
         Sl += (a & 0xFFFFu) - (b & 0xFFFFu);
         Sh += (a >> 16) - (b >> 16);
+    }
     }
 }
 
@@ -678,10 +679,10 @@ __device__ __forceinline__ uint32_t shr_bits(uint32_t cur, uint32_t next, int n)
 
 __global__ void __launch_bounds__(256)
 k_open5(const uint32_t* __restrict__ in_all, uint32_t* __restrict__ out_all, LtDims d, size_t bits_stride,
-        const int* __restrict__ list, const int* __restrict__ count) {
-    int slot = blockIdx.y;
-    if (count != nullptr && slot >= *count) return;
-    int s = list ? list[slot] : slot;
+        const int* __restrict__ list, const int* __restrict__ count, int nslots) {
+    const int nsl = count ? *count : nslots;
+    for (int slot = blockIdx.y; slot < nsl; slot += gridDim.y) {
+    const int s = list ? list[slot] : slot;
     extern __shared__ uint32_t smem[];
     const int mw = d.mwords;
     const int y0 = blockIdx.x * OPEN_ROWS;
@@ -728,6 +729,8 @@ k_open5(const uint32_t* __restrict__ in_all, uint32_t* __restrict__ out_all, LtD
         }
         uint32_t valid = (w * 32 + 32 <= d.bv_w) ? 0xFFFFFFFFu : (w * 32 >= d.bv_w ? 0u : ((1u << (d.bv_w - w * 32)) - 1u));
         out[(size_t)y * mw + w] = res & valid;
+    }
+    __syncthreads();
     }
 }
 
@@ -832,13 +835,14 @@ static int launch_box(lt_handle* h, const uint32_t* plane, uint32_t* hs, uint32_
         cur = smem;
     }
     int half = block / 2;
-    dim3 gh(lt_div_up(d.bv_h, ROWK_WARPS), n);
-    k_box_h<<<gh, ROWK_WARPS * 32, smem, st>>>(plane, hs, d, half, h->stream_plane, list, count);
+    const int zs = list ? (n < 8 ? n : 8) : n;      // retry-list launches: few slots, each CTA loops over the list
+    dim3 gh(lt_div_up(d.bv_h, ROWK_WARPS), zs);
+    k_box_h<<<gh, ROWK_WARPS * 32, smem, st>>>(plane, hs, d, half, h->stream_plane, list, count, n);
     LT_LAUNCH_CHECK();
     int band_rows = 64;
-    dim3 gv(d.p2 / 32, lt_div_up(d.bv_h, band_rows), n);
+    dim3 gv(d.p2 / 32, lt_div_up(d.bv_h, band_rows), zs);
     k_box_v<<<gv, 32, 0, st>>>(plane, hs, bits, d, half, c, accumulate, band_rows, h->stream_plane, h->stream_mask,
-                               list, count);
+                               list, count, n);
     LT_LAUNCH_CHECK();
     return 0;
 }
@@ -885,8 +889,8 @@ int lt_launch_filter(lt_handle* h, int n, const LtAttemptParams& p, const int* l
         lt_prof_mark(h, ST_NOISE, st);
     }
     size_t smem = (size_t)(2 * OPEN_ROWS + 12) * d.mwords * sizeof(uint32_t);
-    dim3 go(lt_div_up(d.bv_h, OPEN_ROWS), n);
-    k_open5<<<go, 256, smem, st>>>(h->merged, h->mask, d, h->stream_mask, list, count);
+    dim3 go(lt_div_up(d.bv_h, OPEN_ROWS), list ? (n < 8 ? n : 8) : n);
+    k_open5<<<go, 256, smem, st>>>(h->merged, h->mask, d, h->stream_mask, list, count, n);
     LT_LAUNCH_CHECK();
     lt_prof_mark(h, ST_OPEN5, st);
     return 0;
