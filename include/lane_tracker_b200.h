@@ -214,8 +214,8 @@ int lt_set_state(lt_handle* h, int32_t stream_id, const lt_state* h_state, const
  * what: 0 undistort map (int32 [img_h][img_w][2]), 1 bird's-eye map (int32 [bv_h][bv_w][2]),
  *       2 overlay map (int32 [img_h][img_w][2]), 3 R plane u8 [bv_h][bv_w], 4 LAB-b plane,
  *       5 R top-hat, 6 b top-hat, 7 mask u8 {0,255}, 8 merged (pre-open) mask,
- *       9 lane row spans int32 [bv_h][2], 10 geometry int32[6] = {undistorted ROI first,last+1, overlay rows
- *       first,last+1, pair-plane width, mask words per row}.
+ *       9 lane row spans int32 [bv_h][2], 10 geometry int32[7] = {undistorted ROI first,last+1, overlay rows
+ *       first,last+1, pair-plane width, mask words per row, pixel-list capacity of lt_read_capture}.
  * Copies to HOST memory; synchronous. Returns bytes written or <0. */
 int64_t lt_debug_read(lt_handle* h, int32_t what, int32_t stream_id, void* h_dst, int64_t capacity);
 

@@ -122,7 +122,7 @@ extern "C" int lt_create(const lt_config* cfg, lt_handle** out) {
     d.mwords = 2 * d.p2 / 32;
     h->stream_plane = (size_t)d.bv_h * d.p2;
     h->stream_mask = (size_t)d.bv_h * d.mwords;
-    h->pix_cap = LT_PIX_CAP_DEFAULT;
+    h->pix_cap = LT_PIX_CAP_DEFAULT > 64 * d.bv_h ? LT_PIX_CAP_DEFAULT : 64 * d.bv_h;   // >= rows x widest window
     const size_t S = h->S, npx = (size_t)d.img_w * d.img_h, nbv = (size_t)d.bv_w * d.bv_h;
     int rc = 0;
 #define A(ptr, n) if (!rc) rc = dev_alloc(&h->ptr, (n))
@@ -557,7 +557,7 @@ extern "C" int64_t lt_debug_read(lt_handle* h, int32_t what, int32_t id, void* d
         }
         case 9: src = h->lane_rows + (size_t)id * d.bv_h; bytes = (size_t)d.bv_h * sizeof(int2); break;
         case 10: {
-            int v[6] = {d.roi0, d.roi1, d.ov0, d.ov1, d.p2, d.mwords};
+            int v[7] = {d.roi0, d.roi1, d.ov0, d.ov1, d.p2, d.mwords, h->pix_cap};
             if (cap < (int64_t)sizeof(v)) { lt_set_error("buffer too small"); return -1; }
             memcpy(dst, v, sizeof(v));
             return sizeof(v);

@@ -95,10 +95,10 @@ class BatchedLaneTracker:
         S = self.n_streams
         self._results_dev = torch.zeros(S * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
         self._results_host = torch.zeros(S * RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
-        geo = np.zeros(6, dtype=np.int32)
+        geo = np.zeros(7, dtype=np.int32)
         check(self.lib.lt_debug_read(self._h, 10, 0, geo.ctypes.data_as(C.c_void_p), geo.nbytes))
         self.geometry = dict(roi_rows=(int(geo[0]), int(geo[1])), overlay_rows=(int(geo[2]), int(geo[3])),
-                             plane_width=int(geo[4]), mask_words=int(geo[5]))
+                             plane_width=int(geo[4]), mask_words=int(geo[5]), pixel_capacity=int(geo[6]))
 
     # -- lifetime -----------------------------------------------------------
     def close(self):
@@ -211,8 +211,9 @@ class BatchedLaneTracker:
         return out, cnt
 
     def sliding_window_search(self, mask, window_width, window_height, search_range, mu, no_success_limit,
-                              start_slice=0.25, ignore_sides=360, ignore_bottom=30, partial=1, capacity=65536):
+                              start_slice=0.25, ignore_sides=360, ignore_bottom=30, partial=1, capacity=None):
         n = int(mask.shape[0])
+        capacity = capacity or self.geometry["pixel_capacity"]
         pixels = torch.empty((n, 2, capacity), dtype=torch.int32, device=self.device)
         counts = torch.zeros((n, 2), dtype=torch.int32, device=self.device)
         cents = torch.zeros((n, 2, LT_MAX_LEVELS), dtype=torch.int32, device=self.device)
@@ -228,8 +229,9 @@ class BatchedLaneTracker:
         cent_lists = [[list(map(int, c[s, side, :nc[s, side]])) for side in range(2)] for s in range(n)]
         return px, cent_lists, det.cpu().numpy().astype(bool)
 
-    def band_search(self, mask, coeffs, bandwidth, ignore_bottom=30, partial=1, capacity=65536):
+    def band_search(self, mask, coeffs, bandwidth, ignore_bottom=30, partial=1, capacity=None):
         n = int(mask.shape[0])
+        capacity = capacity or self.geometry["pixel_capacity"]
         cf = torch.as_tensor(np.asarray(coeffs, dtype=np.float64).reshape(n, 2, 3)).to(self.device)
         pixels = torch.empty((n, 2, capacity), dtype=torch.int32, device=self.device)
         counts = torch.zeros((n, 2), dtype=torch.int32, device=self.device)
@@ -306,7 +308,7 @@ class BatchedLaneTracker:
 
     def read_capture(self, stream_id, attempt):
         """Ordered pixel sets [(ly, lx), (ry, rx)] and centroid lists of one attempt of the last process()."""
-        cap = 65536
+        cap = self.geometry["pixel_capacity"]
         sides, cents = [], []
         for side in range(2):
             buf = np.zeros(cap, dtype=np.uint32)

@@ -416,3 +416,54 @@ def test_host_pipeline_matches_sequential_process(torch_mod):
         assert np.array_equal(got[t][0], want[t][0]), t
         assert got[t][1].tobytes() == want[t][1].tobytes(), t
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("scale", [1.5, 3.0])
+def test_scaled_geometry_matches_oracle(torch_mod, scale):
+    """BASELINE.json config 5: 1920x1080 / 3840x2160 frames with rescaled calibration.  The
+    reference's pixel-valued constants do not scale, so every frame takes both attempts + sliding-window search."""
+    warnings.simplefilter("ignore")
+    from lane_tracker_b200 import BatchedLaneTracker
+    cal = synth.shipped_calibration(scale)
+    vid = synth.RoadVideo(4, scale=scale)
+    frame = vid.frame(2)
+    o = OracleLaneTracker(**cal, backend="cv2")
+    want = o.process(frame.copy(), n_tries=2)
+    b = BatchedLaneTracker(1, **cal)
+    b.set_capture(True)
+    d = torch_mod.as_tensor(frame[None]).cuda()
+    out = torch_mod.empty_like(d)
+    res = b.process(d, out)[0]
+    att = o.trace["attempts"]
+    assert int(res["attempts"]) == len(att)
+    assert _mism(b.debug_read("mask", 0), att[-1]["mask"]) == 0
+    assert bool(res["detected_pixels"]) == att[-1]["detected"] and bool(res["valid_lane_lines"]) == att[-1]["valid"]
+    if att[-1]["detected"]:
+        sides, _ = b.read_capture(0, len(att) - 1)
+        assert np.array_equal(sides[0][0], att[-1]["left_y"]) and np.array_equal(sides[0][1], att[-1]["left_x"])
+        assert np.array_equal(sides[1][0], att[-1]["right_y"]) and np.array_equal(sides[1][1], att[-1]["right_x"])
+        np.testing.assert_allclose(res["left_fit"], att[-1]["left_fit"], rtol=FIT_RTOL)
+        np.testing.assert_allclose(res["right_fit"], att[-1]["right_fit"], rtol=FIT_RTOL)
+    assert _mism(out.cpu().numpy()[0], want) == 0
+    # first attempt ('bilateral' filter) mask as well
+    m1 = b.filter_lane_points(None, "bilateral", 15, 8, 35, 5).cpu().numpy()[0]
+    assert _mism(m1, att[0]["mask"]) == 0
+    b.close()
+
+
+def test_sliding_window_adversarial_masks(bt, torch_mod):
+    import _masks
+    masks = _masks.random_masks(36, seed=5)
+    for i in range(0, len(masks), 4):
+        batch = np.stack(masks[i:i + 4])
+        for nsl, partial, mu in ((8, 1.0, 0.1), (50, 1.0, 0.1), (8, 0.5, 0.35)):
+            px, cents, det = bt.sliding_window_search(torch_mod.as_tensor(batch).cuda(), 30, 40, 20, mu, nsl, 0.25, 360,
+                                                      30, partial)
+            for j in range(batch.shape[0]):
+                o = _oracle_sws(batch[j], nsl, partial, mu=mu)
+                assert bool(det[j]) == o.detected_pixels, (i + j, nsl)
+                assert cents[j][0] == o.trace["sws_centroids"][0] and cents[j][1] == o.trace["sws_centroids"][1], (i + j, nsl)
+                if o.detected_pixels:
+                    (ly, lx), (ry, rx) = px[j]
+                    assert np.array_equal(ly, o.left_y) and np.array_equal(lx, o.left_x), (i + j, nsl)
+                    assert np.array_equal(ry, o.right_y) and np.array_equal(rx, o.right_x), (i + j, nsl)

@@ -27,3 +27,25 @@ def test_process_matches_live_reference_on_a_sequence():
             assert np.array_equal(getattr(ref, nm), getattr(orc, nm)), nm
         assert ref.average_curve_radius == orc.average_curve_radius
         assert ref.eccentricity == orc.eccentricity
+
+
+def test_sliding_window_restatement_on_adversarial_masks():
+    """The integer restatement of sliding_window_search equals the reference on masks built to hit the quirks:
+    windows leaving the frame (NumPy slice wrap-around), one-sided masks, coupling fallback, limits 8 and 50."""
+    import _masks
+    ref = _liveref.make_tracker()
+    orc = OracleLaneTracker(**synth.shipped_calibration())
+    n_detected = 0
+    for i, m in enumerate(_masks.random_masks(36, seed=5)):
+        for nsl, partial, mu in ((8, 1.0, 0.1), (50, 1.0, 0.1), (8, 0.5, 0.35)):
+            ref.detected_pixels = orc.detected_pixels = False
+            _liveref.quiet(ref.sliding_window_search, m, 30, 40, 20, mu, nsl, 0.25, 360, 30, partial)
+            orc.sliding_window_search(m, 30, 40, 20, mu, nsl, 0.25, 360, 30, partial)
+            assert ref.detected_pixels == orc.detected_pixels, (i, nsl)
+            if ref.detected_pixels:
+                n_detected += 1
+                for nm in ("left_x", "left_y", "right_x", "right_y"):
+                    assert np.array_equal(getattr(ref, nm), getattr(orc, nm)), (i, nsl, nm)
+                assert list(ref.left_window_centroids) == list(orc.left_window_centroids), (i, nsl)
+                assert list(ref.right_window_centroids) == list(orc.right_window_centroids), (i, nsl)
+    assert n_detected > 20
