@@ -103,6 +103,13 @@ typedef struct lt_state {
     double  eccentricity;
 } lt_state;
 
+/* Acceptance windows of check_validity (lane_tracker.py:588-593, 617).  The reference hard-codes them as local
+ * constants and documents other sets per demo video (tracker_settings.md); lt_create installs the shipped ones
+ * (150/230, 110/230, 80/200, 0.25). */
+typedef struct lt_validity {
+    double min_dist_y1, max_dist_y1, min_dist_y2, max_dist_y2, min_dist_y3, max_dist_y3, tangent_thresh;
+} lt_validity;
+
 /* ---- lifetime ------------------------------------------------------------ */
 
 /* LaneTracker.__init__ (lane_tracker.py:101-176) for `max_streams` streams.
@@ -111,6 +118,8 @@ int lt_create(const lt_config* cfg, lt_handle** out);
 int lt_destroy(lt_handle* h);
 /* Re-zero the state of the listed streams (ids == NULL: all). Synchronous. */
 int lt_reset(lt_handle* h, const int32_t* ids, int32_t n);
+int lt_set_validity(lt_handle* h, const lt_validity* v);     /* NULL restores the shipped constants */
+int lt_get_validity(lt_handle* h, lt_validity* v);
 const char* lt_last_error(void);
 int lt_abi_version(void);
 void lt_default_params(lt_params* p);            /* lane_tracker.py:876-900 */

@@ -57,12 +57,19 @@ class lt_state(C.Structure):
                 ("radii", i32 * LT_MAX_AVERAGE), ("average_curve_radius", i32), ("eccentricity", f64)]
 
 
+class lt_validity(C.Structure):
+    _fields_ = [("min_dist_y1", f64), ("max_dist_y1", f64), ("min_dist_y2", f64), ("max_dist_y2", f64),
+                ("min_dist_y3", f64), ("max_dist_y3", f64), ("tangent_thresh", f64)]
+
+
 # every symbol include/lane_tracker_b200.h declares: (restype, argtypes)
 P = C.c_void_p
 SIGNATURES = {
     "lt_create": (C.c_int, [C.POINTER(lt_config), C.POINTER(P)]),
     "lt_destroy": (C.c_int, [P]),
     "lt_reset": (C.c_int, [P, C.POINTER(i32), i32]),
+    "lt_set_validity": (C.c_int, [P, C.POINTER(lt_validity)]),
+    "lt_get_validity": (C.c_int, [P, C.POINTER(lt_validity)]),
     "lt_last_error": (C.c_char_p, []),
     "lt_abi_version": (C.c_int, []),
     "lt_default_params": (None, [C.POINTER(lt_params)]),

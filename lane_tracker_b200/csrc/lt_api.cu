@@ -79,6 +79,19 @@ template <typename T> static int dev_alloc(T** p, size_t n) {
     return 0;
 }
 
+static const lt_validity SHIPPED_VALIDITY = {150.0, 230.0, 110.0, 230.0, 80.0, 200.0, 0.25};   // lane_tracker.py:588-593, 617
+
+extern "C" int lt_set_validity(lt_handle* h, const lt_validity* v) {
+    if (!h) { lt_set_error("null handle"); return -1; }
+    h->val = v ? *v : SHIPPED_VALIDITY;
+    return 0;
+}
+extern "C" int lt_get_validity(lt_handle* h, lt_validity* v) {
+    if (!h || !v) { lt_set_error("null argument"); return -1; }
+    *v = h->val;
+    return 0;
+}
+
 static void init_state(lt_handle* h, lt_state* s) {
     memset(s, 0, sizeof(*s));
     s->last_detection = h->cfg.n_reset + 1;     // lane_tracker.py:140
@@ -115,6 +128,7 @@ extern "C" int lt_create(const lt_config* cfg, lt_handle** out) {
     memset(h, 0, sizeof(*h));
     h->cfg = *cfg;
     h->S = cfg->max_streams;
+    h->val = SHIPPED_VALIDITY;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
     LtDims& d = h->d;
     d.img_w = cfg->img_w; d.img_h = cfg->img_h; d.bv_w = cfg->bv_w; d.bv_h = cfg->bv_h;

@@ -49,6 +49,7 @@ struct lt_handle {
     lt_config cfg;
     LtDims d;
     int S;                       // max streams
+    lt_validity val;             // check_validity windows
     int sm_count;
     // shared tables
     int2* und_map;               // [img_h][img_w]

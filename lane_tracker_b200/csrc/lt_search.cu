@@ -197,7 +197,7 @@ __device__ void fit_from_moments(const long long* mom, double yc, double sc, int
 }
 
 // check_validity (lane_tracker.py:561-627); nL/nR = lengths returned by get_poly_points(l, r, 1)
-__device__ int validity(const double* l, const double* r, int nL, int nR, int W, double* diffs) {
+__device__ int validity(const double* l, const double* r, int nL, int nR, int W, double* diffs, const lt_validity& V) {
     int n = min(nL, nR);
     int y1 = W - 1, y2 = W - (int)mul64((double)n, 0.35), y3 = W - (int)mul64((double)n, 0.75);
     auto f = [&](const double* c, int y) {
@@ -205,10 +205,11 @@ __device__ int validity(const double* l, const double* r, int nL, int nR, int W,
     };
     double d1 = fabs(sub64(f(l, y1), f(r, y1))), d2 = fabs(sub64(f(l, y2), f(r, y2))), d3 = fabs(sub64(f(l, y3), f(r, y3)));
     diffs[0] = d1; diffs[1] = d2; diffs[2] = d3;
-    if ((d1 < 150.0) | (d1 > 230.0) | (d2 < 110.0) | (d2 > 230.0) | (d3 < 80.0) | (d3 > 200.0)) return 0;
+    if ((d1 < V.min_dist_y1) | (d1 > V.max_dist_y1) | (d2 < V.min_dist_y2) | (d2 > V.max_dist_y2) |
+        (d3 < V.min_dist_y3) | (d3 > V.max_dist_y3)) return 0;
     auto g = [&](const double* c, int y) { return add64(mul64(mul64(2.0, c[0]), (double)y), c[1]); };
     double t1 = fabs(sub64(g(l, y1), g(r, y1))), t3 = fabs(sub64(g(l, y3), g(r, y3)));
-    if ((t1 >= 0.25) | (t3 >= 0.25)) return 0;
+    if ((t1 >= V.tangent_thresh) | (t3 >= V.tangent_thresh)) return 0;
     return 1;
 }
 
@@ -253,7 +254,7 @@ __device__ int poly_points(const double* cf, double partial, int W, int H, int* 
 // ---------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(SEARCH_THREADS)
-k_search(LtDims d, LtAttemptParams p, LtSearchArgs a, const LtDevState* __restrict__ state, int n_reset,
+k_search(LtDims d, LtAttemptParams p, LtSearchArgs a, const LtDevState* __restrict__ state, int n_reset, lt_validity V,
          size_t bits_stride, const int* __restrict__ list, const int* __restrict__ count) {
     int slot = blockIdx.x;
     if (count != nullptr && slot >= *count) return;
@@ -498,7 +499,7 @@ k_search(LtDims d, LtAttemptParams p, LtSearchArgs a, const LtDevState* __restri
         int nR = poly_points(fit[1], 1.0, W, H, nullptr, flags, scratch);
         if (tid == 0 && out) {
             double diffs[3] = {0, 0, 0};
-            out->valid = validity(fit[0], fit[1], nL, nR, W, diffs);
+            out->valid = validity(fit[0], fit[1], nL, nR, W, diffs, V);
             for (int j = 0; j < 3; ++j) { out->fit[0][j] = fit[0][j]; out->fit[1][j] = fit[1][j]; out->diffs[j] = diffs[j]; }
             out->rank_def = rankdef[0] | (rankdef[1] << 1);
         }
@@ -525,7 +526,7 @@ int lt_launch_search(lt_handle* h, int n, const LtAttemptParams& p, const LtSear
         cur = smem;
     }
     if (p.window_width < 1 || p.window_height < 1) { lt_set_error("window size must be positive"); return -1; }
-    k_search<<<n, SEARCH_THREADS, smem, st>>>(h->d, p, a, h->state, h->cfg.n_reset, h->stream_mask, list, count);
+    k_search<<<n, SEARCH_THREADS, smem, st>>>(h->d, p, a, h->state, h->cfg.n_reset, h->val, h->stream_mask, list, count);
     LT_LAUNCH_CHECK();
     return 0;
 }
@@ -829,7 +830,7 @@ int lt_launch_fit_pixels(lt_handle* h, const uint32_t* d_pixels, int cap, const 
 }
 
 __global__ void __launch_bounds__(SEARCH_THREADS)
-k_validity(LtDims d, const double* __restrict__ fits, int* __restrict__ valid, double* __restrict__ diffs) {
+k_validity(LtDims d, const double* __restrict__ fits, int* __restrict__ valid, double* __restrict__ diffs, lt_validity V) {
     const int s = blockIdx.x;
     extern __shared__ unsigned char smem_raw[];
     int* flags = reinterpret_cast<int*>(smem_raw);
@@ -841,13 +842,13 @@ k_validity(LtDims d, const double* __restrict__ fits, int* __restrict__ valid, d
     int nR = poly_points(cf[1], 1.0, d.bv_w, d.bv_h, nullptr, flags, scratch);
     if (threadIdx.x == 0) {
         double dd[3];
-        valid[s] = validity(cf[0], cf[1], nL, nR, d.bv_w, dd);
+        valid[s] = validity(cf[0], cf[1], nL, nR, d.bv_w, dd, V);
         if (diffs) for (int j = 0; j < 3; ++j) diffs[(size_t)s * 3 + j] = dd[j];
     }
 }
 
 int lt_launch_validity(lt_handle* h, const double* d_fits, int n, int* d_valid, double* d_diffs, cudaStream_t st) {
-    k_validity<<<n, SEARCH_THREADS, (size_t)h->d.bv_h * sizeof(int), st>>>(h->d, d_fits, d_valid, d_diffs);
+    k_validity<<<n, SEARCH_THREADS, (size_t)h->d.bv_h * sizeof(int), st>>>(h->d, d_fits, d_valid, d_diffs, h->val);
     LT_LAUNCH_CHECK();
     return 0;
 }

@@ -119,6 +119,20 @@ class BatchedLaneTracker:
             arr = (C.c_int32 * len(ids))(*[int(i) for i in ids])
             check(self.lib.lt_reset(self._h, arr, len(ids)))
 
+    def set_validity(self, **kw):
+        """Override the acceptance windows of check_validity (lane_tracker.py:588-593, 617); no arguments restores
+        the shipped constants.  Keys: min/max_dist_y1..y3, tangent_thresh (see lane_tracker_b200.presets)."""
+        if not kw:
+            check(self.lib.lt_set_validity(self._h, None))
+            return
+        v = _lib.lt_validity()
+        check(self.lib.lt_get_validity(self._h, C.byref(v)))
+        for k, val in kw.items():
+            if not hasattr(v, k):
+                raise TypeError("unknown validity option %r" % k)
+            setattr(v, k, float(val))
+        check(self.lib.lt_set_validity(self._h, C.byref(v)))
+
     def set_capture(self, enable=True):
         check(self.lib.lt_set_capture(self._h, int(bool(enable))))
 
@@ -489,6 +503,10 @@ class LaneTracker:
 
     def get_success_ratio(self):
         return self.success / self.counter, self.success, self.counter
+
+    def set_validity(self, **kw):
+        """Extension: the check_validity windows the reference hard-codes (lane_tracker.py:588-593, 617)."""
+        self._bt.set_validity(**kw)
 
     # ------------------------------------------------------------ helpers
     def _upload(self, arr, shape):

@@ -77,6 +77,7 @@ class OracleLaneTracker:
         self.n_fail, self.n_reset, self.n_average = n_fail, n_reset, n_average
         self.print_frame_count = print_frame_count
         self.backend = backend
+        self.validity = dict(VALIDITY)    # per-instance copy: tests may install the other documented windows
         if backend == "cv2":
             import cv2  # noqa: F401  (third-party kernel library of the reference)
             self._cv2 = cv2
@@ -326,7 +327,7 @@ class OracleLaneTracker:
         def f(c, y):
             return c[0] * (y ** 2) + c[1] * y + c[2]
         d1, d2, d3 = abs(f(l, y1) - f(r, y1)), abs(f(l, y2) - f(r, y2)), abs(f(l, y3) - f(r, y3))
-        V = VALIDITY
+        V = self.validity
         self.trace["validity"] = (d1, d2, d3)
         if (d1 < V["min_d1"]) | (d1 > V["max_d1"]) | (d2 < V["min_d2"]) | (d2 > V["max_d2"]) | \
                 (d3 < V["min_d3"]) | (d3 > V["max_d3"]):

@@ -467,3 +467,54 @@ def test_sliding_window_adversarial_masks(bt, torch_mod):
                     (ly, lx), (ry, rx) = px[j]
                     assert np.array_equal(ly, o.left_y) and np.array_equal(lx, o.left_x), (i + j, nsl)
                     assert np.array_equal(ry, o.right_y) and np.array_equal(rx, o.right_x), (i + j, nsl)
+
+
+def test_demo1_preset_on_bundled_frames(torch_mod):
+    """Extra coverage (clearly labelled, not the headline parity): with the Demo-1 windows of
+    tracker_settings.md:28-34 nine of the eleven bundled frames validate, so real photographs reach band search,
+    mask_noise and the success branch.  Three passes of every frame, all 11 batched as independent streams."""
+    warnings.simplefilter("ignore")
+    from lane_tracker_b200 import BatchedLaneTracker, presets
+    names = fx.frame_names()
+    frames = np.stack([fx.load_frame(n) for n in names])
+    V = presets.DEMO_1["validity"]
+    oracles = []
+    for _ in names:
+        o = OracleLaneTracker(**CAL, backend="cv2")
+        o.validity = dict(min_d1=V["min_dist_y1"], max_d1=V["max_dist_y1"], min_d2=V["min_dist_y2"],
+                          max_d2=V["max_dist_y2"], min_d3=V["min_dist_y3"], max_d3=V["max_dist_y3"],
+                          tan=V["tangent_thresh"])
+        oracles.append(o)
+    b = BatchedLaneTracker(len(names), **CAL)
+    b.set_validity(**V)
+    b.set_capture(True)
+    d = torch_mod.as_tensor(frames).cuda()
+    n_valid = n_band = 0
+    for it in range(3):
+        out = torch_mod.empty_like(d)
+        res = b.process(d, out, **presets.DEMO_1["process"])
+        out = out.cpu().numpy()
+        for i, o in enumerate(oracles):
+            want = o.process(frames[i].copy(), **presets.DEMO_1["process"])
+            att = o.trace["attempts"]
+            assert int(res[i]["attempts"]) == len(att), (names[i], it)
+            assert bool(res[i]["valid_lane_lines"]) == o.valid_lane_lines, (names[i], it)
+            assert int(res[i]["search_mode"]) == (1 if att[-1]["mode"] == "bs" else 0)
+            assert int(res[i]["last_detection"]) == o.last_detection
+            assert _mism(out[i], want) == 0, (names[i], it)
+            if att[-1]["detected"]:
+                sides, _ = b.read_capture(i, len(att) - 1)
+                assert np.array_equal(sides[0][1], att[-1]["left_x"]) and np.array_equal(sides[1][0], att[-1]["right_y"])
+                np.testing.assert_allclose(res[i]["left_fit"], att[-1]["left_fit"], rtol=FIT_RTOL)
+                np.testing.assert_allclose(res[i]["right_fit"], att[-1]["right_fit"], rtol=FIT_RTOL)
+            if o.valid_lane_lines:
+                n_valid += 1
+                n_band += att[-1]["mode"] == "bs"
+                assert int(res[i]["average_curve_radius"]) == o.average_curve_radius
+                assert float(res[i]["eccentricity"]) == pytest.approx(o.eccentricity, rel=1e-12, abs=1e-15)
+    assert n_valid == 27 and n_band == 18
+    b.set_validity()            # back to the shipped constants: nothing validates any more
+    b.reset()
+    res = b.process(d, None)
+    assert not res["valid_lane_lines"].any()
+    b.close()

@@ -1,0 +1,23 @@
+#!/usr/bin/env python3
+"""Small workload for compute-sanitizer (memcheck / racecheck): two streams, three frames, both filter paths."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lane_tracker_b200 import BatchedLaneTracker, synth  # noqa: E402
+
+cal = synth.shipped_calibration()
+t = BatchedLaneTracker(2, **cal)
+t.set_capture(True)
+vid = synth.RoadVideo(0)
+noise = np.random.default_rng(0).integers(0, 256, (720, 1280, 3), dtype=np.uint8)
+for i in range(3):
+    fr = np.stack([vid.frame(i), noise])            # stream 1 always fails -> attempt 2 path
+    d = torch.from_numpy(fr).cuda()
+    out = torch.empty_like(d)
+    res = t.process(d, out, mask_noise=bool(i == 2))
+print("ok", res["valid_lane_lines"], res["attempts"])
+t.close()
