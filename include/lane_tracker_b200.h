@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define LT_ABI_VERSION 1
+#define LT_ABI_VERSION 2
 #define LT_MAX_AVERAGE 8          /* capacity of the n_average rings */
 
 typedef struct lt_handle lt_handle;
@@ -73,11 +73,14 @@ typedef struct lt_result {
     int32_t drew_lane;            /* 1: lane polygon blended, 0: failure frame */
     int32_t n_left, n_right;      /* lane pixels of the last attempt */
     int32_t n_left_avg, n_right_avg; /* vertices of the averaged polylines */
-    int32_t left_curve_radius, right_curve_radius, average_curve_radius;
     int32_t success;
     int32_t fit_rank_deficient;   /* bit0 left, bit1 right: <3 distinct rows */
     int32_t first_detected, first_valid;      /* outcome of attempt 1 (== final when attempts == 1) */
     int32_t first_n_left, first_n_right;
+    int32_t reserved0;
+    /* radii are Python ints in the reference (int() of an unbounded float, lane_tracker.py:539-549): 64 bits here,
+     * saturated at +-2^63 */
+    int64_t left_curve_radius, right_curve_radius, average_curve_radius;
     double  left_fit[3], right_fit[3];   /* last attempt's np.polyfit equivalents */
     double  left_avg[3], right_avg[3];
     double  eccentricity;
@@ -98,8 +101,8 @@ typedef struct lt_state {
     double  left_avg[3], right_avg[3];
     int32_t n_left_avg, n_right_avg;              /* polyline vertex counts */
     int32_t radii_len;
-    int32_t radii[LT_MAX_AVERAGE];
-    int32_t average_curve_radius;
+    int64_t radii[LT_MAX_AVERAGE];
+    int64_t average_curve_radius;
     double  eccentricity;
 } lt_state;
 

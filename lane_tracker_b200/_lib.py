@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "liblane_tracker_b200.so")
 
 LT_MAX_AVERAGE = 8
 LT_MAX_LEVELS = 128
-LT_ABI_VERSION = 1
+LT_ABI_VERSION = 2
 LT_NSTAGES = 16
 
 i32, f64 = C.c_int32, C.c_double
@@ -39,9 +39,10 @@ class lt_result(C.Structure):
     _fields_ = [("counter", i32), ("attempts", i32), ("search_mode", i32), ("detected_pixels", i32),
                 ("valid_lane_lines", i32), ("last_detection", i32), ("drew_lane", i32),
                 ("n_left", i32), ("n_right", i32), ("n_left_avg", i32), ("n_right_avg", i32),
-                ("left_curve_radius", i32), ("right_curve_radius", i32), ("average_curve_radius", i32),
                 ("success", i32), ("fit_rank_deficient", i32),
                 ("first_detected", i32), ("first_valid", i32), ("first_n_left", i32), ("first_n_right", i32),
+                ("reserved0", i32),
+                ("left_curve_radius", C.c_int64), ("right_curve_radius", C.c_int64), ("average_curve_radius", C.c_int64),
                 ("left_fit", f64 * 3), ("right_fit", f64 * 3), ("left_avg", f64 * 3), ("right_avg", f64 * 3),
                 ("eccentricity", f64), ("validity_d", f64 * 3),
                 ("first_left_fit", f64 * 3), ("first_right_fit", f64 * 3)]
@@ -54,7 +55,7 @@ class lt_state(C.Structure):
                 ("has_last", i32), ("last_left", f64 * 3), ("last_right", f64 * 3),
                 ("has_avg", i32), ("left_avg", f64 * 3), ("right_avg", f64 * 3),
                 ("n_left_avg", i32), ("n_right_avg", i32), ("radii_len", i32),
-                ("radii", i32 * LT_MAX_AVERAGE), ("average_curve_radius", i32), ("eccentricity", f64)]
+                ("radii", C.c_int64 * LT_MAX_AVERAGE), ("average_curve_radius", C.c_int64), ("eccentricity", f64)]
 
 
 class lt_validity(C.Structure):

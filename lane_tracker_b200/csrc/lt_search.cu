@@ -716,19 +716,23 @@ k_update_state(LtDims d, lt_config cfg, LtDevState* __restrict__ state, const Lt
             st.n_left_avg = nkeep[0]; st.n_right_avg = nkeep[1];
             // get_curve_radius (lane_tracker.py:530-549): the metric refit of the same pixels is the
             // analytic rescaling a' = a*mpph/mppv^2, b' = b*mpph/mppv of this frame's fit
-            int rad[2];
+            long long rad[2];
             for (int side = 0; side < 2; ++side) {
                 double am = a.fit[side][0] * cfg.mpph / (cfg.mppv * cfg.mppv), bm = a.fit[side][1] * cfg.mpph / cfg.mppv;
                 double g = 2.0 * am * (double)H * cfg.mppv + bm;
                 double r = pow(1.0 + g * g, 1.5) / fabs(2.0 * am);
-                rad[side] = (r >= 2147483647.0 || !(r == r)) ? 2147483647 : (int)r;
+                rad[side] = (!(r == r) || r >= 9.2233720368547758e18) ? 0x7FFFFFFFFFFFFFFFLL : (long long)r;   // int(float)
             }
-            int avr = (int)(0.5 * ((double)rad[0] + (double)rad[1]));
+            long long avr = (long long)(0.5 * (double)(rad[0] + rad[1]));           // int(0.5 * (l + r))
             if (st.radii_len == nav) { for (int i = 1; i < nav; ++i) st.radii[i - 1] = st.radii[i]; st.radii_len = nav - 1; }
             st.radii[st.radii_len++] = avr;
-            long long sum = 0; int c = 0;
-            for (int i = 0; i < st.radii_len; ++i) if (st.radii[i] > 0) { sum += st.radii[i]; ++c; }
-            st.average_curve_radius = c ? (int)((double)sum / (double)c) : -1;
+            // int(np.average(radii > 0)): float64 accumulation in NumPy's order (pairwise unrolled by 8 for n == 8)
+            double v[LT_MAX_AVERAGE]; int c = 0;
+            for (int i = 0; i < st.radii_len; ++i) if (st.radii[i] > 0) v[c++] = (double)st.radii[i];
+            double sum = 0.0;
+            if (c == 8) sum = add64(add64(add64(v[0], v[1]), add64(v[2], v[3])), add64(add64(v[4], v[5]), add64(v[6], v[7])));
+            else for (int i = 0; i < c; ++i) sum = i ? add64(sum, v[i]) : v[0];
+            st.average_curve_radius = c ? (long long)__ddiv_rn(sum, (double)c) : -1;
             results[s].left_curve_radius = rad[0]; results[s].right_curve_radius = rad[1];
             // get_eccentricity (lane_tracker.py:551-559)
             if (nkeep[0] > 0 && nkeep[1] > 0) {

@@ -88,9 +88,10 @@ class RoadVideo:
         """BV x of the left/right line centre on every BV row (float64 [bh])."""
         s = self.scale
         y = (np.arange(self.bh, dtype=np.float64) - (self.bh - 1)) / s
-        a = 6e-5 * np.sin(t / 60.0)
-        b = -0.05 * np.sin(t / 90.0)
-        c0 = 450.0 + 15.0 * np.sin(t / 45.0)
+        a = 6e-5 * np.sin((t + 11.0) / 60.0)      # phase offsets: never an exactly straight line (a = b = 0 makes
+        b = -0.05 * np.sin((t + 5.0) / 90.0)      # the reference's curve radius 1/|2a| a pure round-off product)
+        c0 = 450.37 + 15.0 * np.sin(t / 45.0)     # never pixel-symmetric: an exactly integral fit makes the
+                                                  # int() truncations downstream depend on fp64 round-off
         xl = (a * y * y + b * y + c0) * s
         return xl, xl + self.separation
 

@@ -66,7 +66,7 @@ def _mism(a, b):
 def test_library_loaded_is_in_tree():
     from lane_tracker_b200 import _lib
     lib = _lib.load()
-    assert "lane_tracker_b200/liblane_tracker_b200.so" in _lib.LIB_PATH and lib.lt_abi_version() == 1
+    assert "lane_tracker_b200/liblane_tracker_b200.so" in _lib.LIB_PATH and lib.lt_abi_version() == 2
 
 
 def test_coordinate_tables(bt):
@@ -518,3 +518,46 @@ def test_demo1_preset_on_bundled_frames(torch_mod):
     res = b.process(d, None)
     assert not res["valid_lane_lines"].any()
     b.close()
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_process_randomised_options_and_state_machine(torch_mod, case):
+    """Constructor options (n_fail, n_reset, n_average) and process() keyword options drawn at random; a short
+    sequence with an outage; every frame compared with the oracle (outputs, decisions, pixel sets, state)."""
+    warnings.simplefilter("ignore")
+    from lane_tracker_b200 import LaneTracker
+    rng = np.random.default_rng(100 + case)
+    ctor = dict(n_fail=int(rng.integers(1, 6)), n_reset=int(rng.integers(0, 4)), n_average=int(rng.integers(1, 6)))
+    kw = dict(ksize_r=int(rng.integers(8, 25)), C_r=int(rng.integers(3, 10)), ksize_b=int(rng.integers(20, 45)),
+              C_b=int(rng.integers(3, 8)), mask_noise=bool(rng.integers(0, 2)), noise_thresh=int(rng.integers(130, 150)),
+              window_width=int(rng.choice([24, 30, 36])), window_height=int(rng.choice([30, 40, 50])),
+              search_range=int(rng.integers(12, 30)), mu=float(rng.choice([0.0, 0.1, 0.3])),
+              no_success_limit=int(rng.integers(3, 12)), bandwidth=int(rng.integers(15, 40)),
+              partial=float(rng.choice([1.0, 0.5, 0.8])), n_tries=int(rng.choice([1, 2])))
+    vid = synth.RoadVideo(20 + case)
+    blank = np.full((720, 1280, 3), 90, np.uint8)
+    plan = [0, 1, 2, 3, "x", "x", "x", "x", "x", "x", 4, 5, 6] if case % 2 == 0 else [0, "x", 1, 2, "x", "x", 3, 4, 5]
+    gpu = LaneTracker(**CAL, **ctor)
+    ref = OracleLaneTracker(**CAL, **ctor, backend="cv2")
+    for step, item in enumerate(plan):
+        frame = blank if item == "x" else vid.frame(item)
+        out = gpu.process(frame, **kw)
+        want = ref.process(frame.copy(), **kw)
+        tag = (case, step, ctor, kw)
+        assert gpu.valid_lane_lines == ref.valid_lane_lines, tag
+        assert gpu.detected_pixels == ref.detected_pixels, tag
+        assert gpu.last_detection == ref.last_detection and gpu.success == ref.success, tag
+        assert _mism(out, want) == 0, tag
+        assert gpu.average_curve_radii == ref.average_curve_radii, tag
+        assert len(gpu.left_fit_coeffs) == len(ref.left_fit_coeffs), tag
+        for a, b in zip(gpu.left_fit_coeffs + gpu.right_fit_coeffs, ref.left_fit_coeffs + ref.right_fit_coeffs):
+            assert a.size == b.size, tag
+            if a.size:
+                np.testing.assert_allclose(a, b, rtol=FIT_RTOL)
+        if ref.left_avg_coeffs is not None:
+            np.testing.assert_allclose(gpu.left_avg_coeffs, ref.left_avg_coeffs, rtol=FIT_RTOL)
+            assert np.array_equal(gpu.left_avg_x, ref.left_avg_x) and np.array_equal(gpu.right_avg_x, ref.right_avg_x), tag
+            assert np.array_equal(gpu.left_avg_y, ref.left_avg_y), tag
+            assert gpu.average_curve_radius == ref.average_curve_radius, tag
+        if ref.left_x is not None and ref.detected_pixels:
+            assert np.array_equal(gpu.left_x, ref.left_x) and np.array_equal(gpu.right_y, ref.right_y), tag
