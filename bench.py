@@ -32,7 +32,7 @@ FRAME_POOL = 4                       # pre-rendered frames per stream, cycled
 FRAME_BYTES = 1280 * 720 * 3
 ALGO_BYTES_PER_FRAME = 2 * FRAME_BYTES + 128          # frame in + annotated frame out + results
 PLANE_PIXELS = 1080 * 1100
-MORPH_ALGO_BYTES_PER_FRAME = 2 * PLANE_PIXELS         # one u8 plane read + one u8 plane written per morphology launch
+MORPH_ALGO_BYTES_PER_FRAME = 4 * PLANE_PIXELS         # per morphology launch: two u8 planes (R, Lab-b) read + two written
 
 
 def measured_peak_hbm():
@@ -306,11 +306,12 @@ def run_gpu_arm(args):
         peak, peak_src = measured_peak_hbm()
         top = max(stage_ms, key=stage_ms.get)
         total_stage = sum(stage_ms.values())
-        morph = {k: stage_ms[k] for k in ("erode55", "tophat55", "erode29", "tophat29")}
+        # one launch erodes both planes (stage "erode55"), one dilates both and subtracts (stage "tophat55")
+        morph = {k: stage_ms[k] for k in ("erode55", "tophat55")}
         dom = max(morph, key=morph.get)
         dom_ms_per_launch = morph[dom] / max(prof_calls, 1)
         achieved = S * MORPH_ALGO_BYTES_PER_FRAME / (dom_ms_per_launch * 1e-3) / 1e9 if dom_ms_per_launch > 0 else 0.0
-        kname = "k_morph<%s, %s>" % ("55" if "55" in dom else "29", "1, 1" if "tophat" in dom else "0, 0")
+        kname = "k_morph_pair<%s>" % ("1, 1" if dom == "tophat55" else "0, 0")
         traffic = None
         try:    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
             with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
@@ -320,7 +321,7 @@ def run_gpu_arm(args):
                 traffic = traffic * S / tj["streams"]
         except Exception:
             traffic = None
-        roofline = {"bound": "hbm", "kernel": "%s (%s)" % (kname, dom),
+        roofline = {"bound": "hbm", "kernel": "%s (%s)" % (kname, "dilate 55x55 + 29x29 and top-hat" if dom == "tophat55" else "erode 55x55 + 29x29"),
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "peak_source": peak_src, "ms_per_launch": dom_ms_per_launch,
                     "algorithmic_bytes_per_launch": S * MORPH_ALGO_BYTES_PER_FRAME,

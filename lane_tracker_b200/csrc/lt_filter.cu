@@ -10,6 +10,9 @@
 // the row from two table reads each, and folds them into a K-deep register pipeline
 // A[j] = op(A[j+1], Hop_{hw[j]}) whose head is a finished output row.  All min/max are
 // single VIMNMX(3).U16x2 instructions.
+#include <algorithm>
+#include <functional>
+#include <vector>
 #include "lt_common.cuh"
 
 // ---------------------------------------------------------------------------
@@ -94,9 +97,9 @@ __device__ __forceinline__ uint32_t stage_elem(const uint32_t* __restrict__ src,
 }
 
 template <int K, bool IS_MAX, bool TOPHAT>
-__global__ void __launch_bounds__(MORPH_TW, MORPH_CTAS_PER_SM)
-k_morph(const uint32_t* __restrict__ src_all, uint32_t* __restrict__ dst_all, const uint32_t* __restrict__ orig_all,
-        LtDims d, int band_rows, size_t stream_stride, const int* __restrict__ list, const int* __restrict__ count) {
+__device__ __forceinline__ void
+morph_body(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const uint32_t* __restrict__ orig,
+           const LtDims& d, int band_rows, int tile, int band) {
     // Shared-memory tables hold ROW PAIRS: element (pair m, column c) is a uint2 {row 2m, row 2m+1}.  Every table
     // access is one LDS.64/STS.64 serving two source rows, and the vertical pipeline advances two rows per step
     // with a single three-input VIMNMX3 per accumulator:
@@ -111,10 +114,6 @@ k_morph(const uint32_t* __restrict__ src_all, uint32_t* __restrict__ dst_all, co
     constexpr uint32_t PADL = IS_MAX ? 0u : 0xFFFFu;
     constexpr uint32_t PAD2 = PADL | (PADL << 16);
 
-    int slot = blockIdx.z;
-    if (count != nullptr && slot >= *count) return;
-    int s = list ? list[slot] : slot;
-
     extern __shared__ uint32_t smem[];
     uint2* T0 = reinterpret_cast<uint2*>(smem);
     uint2* T4 = T0 + RP * TEA;
@@ -125,12 +124,9 @@ k_morph(const uint32_t* __restrict__ src_all, uint32_t* __restrict__ dst_all, co
     uint2* OG = S + RP * TE;          // [2][RP][TW] original-plane rows for the top-hat epilogue (double buffered)
 
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TW;
-    const int yb0 = blockIdx.y * band_rows;
+    const int x0 = tile * TW;
+    const int yb0 = band * band_rows;
     const int yb1 = min(yb0 + band_rows, d.bv_h);
-    const uint32_t* src = src_all + (size_t)s * stream_stride;
-    uint32_t* dst = dst_all + (size_t)s * stream_stride;
-    const uint32_t* orig = TOPHAT ? orig_all + (size_t)s * stream_stride : nullptr;
 
     for (int i = tid; i < NTAB * RB * TEA; i += TW) smem[i] = PAD2;
 
@@ -302,23 +298,91 @@ k_morph(const uint32_t* __restrict__ src_all, uint32_t* __restrict__ dst_all, co
     }
 }
 
-template <int K, bool IS_MAX, bool TOPHAT>
-static int launch_morph(lt_handle* h, const uint32_t* src, uint32_t* dst, const uint32_t* orig, int n,
-                        const int* list, const int* count, int bands, cudaStream_t st) {
+// One launch erodes (or dilates) BOTH planes: the 55x55 work items of the Lab-b plane come first, the lighter
+// 29x29 items of the R plane fill the slots they leave free, so the grid packs the SMs without a second wave.
+struct MorphJob {
+    const uint32_t* src; uint32_t* dst; const uint32_t* orig;
+    int bands, band_rows;
+};
+
+template <int K>
+constexpr size_t morph_smem_bytes(bool tophat) {
     constexpr int R = Ellipse<K>::R;
     constexpr int TEA = MORPH_TW + 2 * R + 32;
     constexpr int NTAB = (2 * R + 1 >= 32) ? 5 : 4;
-    size_t smem = ((size_t)NTAB * MORPH_RB * TEA + (size_t)MORPH_RB * (MORPH_TW + 2 * R) + (TOPHAT ? 2 * MORPH_RB * MORPH_TW : 0)) * sizeof(uint32_t);
+    return ((size_t)NTAB * MORPH_RB * TEA + (size_t)MORPH_RB * (MORPH_TW + 2 * R) +
+            (tophat ? 2 * MORPH_RB * MORPH_TW : 0)) * sizeof(uint32_t);
+}
+
+template <bool IS_MAX, bool TOPHAT>
+__global__ void __launch_bounds__(MORPH_TW, MORPH_CTAS_PER_SM)
+k_morph_pair(MorphJob j55, MorphJob j29, LtDims d, int tiles, int n, size_t stream_stride,
+             const int* __restrict__ list, const int* __restrict__ count) {
+    int item = blockIdx.x;
+    const int n55 = n * tiles * j55.bands;
+    const bool big = item < n55;
+    const MorphJob& j = big ? j55 : j29;
+    if (!big) item -= n55;
+    const int slot = item % n;                 // stream slot fastest: neighbouring CTAs share the shared tables' L2 lines
+    const int tb = item / n;
+    const int tile = tb % tiles, band = tb / tiles;
+    if (count != nullptr && slot >= *count) return;
+    const int s = list ? list[slot] : slot;
+    const uint32_t* src = j.src + (size_t)s * stream_stride;
+    uint32_t* dst = j.dst + (size_t)s * stream_stride;
+    const uint32_t* orig = TOPHAT ? j.orig + (size_t)s * stream_stride : nullptr;
+    if (big) morph_body<55, IS_MAX, TOPHAT>(src, dst, orig, d, j.band_rows, tile, band);
+    else morph_body<29, IS_MAX, TOPHAT>(src, dst, orig, d, j.band_rows, tile, band);
+}
+
+// Pick the band counts of the two jobs by simulating list scheduling of the combined grid on `slots` CTA slots.
+// Per-row costs are the measured relative walk costs of the two structuring elements (profiles/, round 1).
+static void choose_bands(int n, int tiles, int H, int slots, int* b55, int* b29) {
+    static int cache_n = -1, cache_h = -1, cache_slots = -1, c55 = 1, c29 = 1;
+    if (n == cache_n && H == cache_h && slots == cache_slots) { *b55 = c55; *b29 = c29; return; }
+    double best = 1e300;
+    std::vector<double> freeat;
+    for (int a = 1; a <= 24; ++a)
+        for (int b = 1; b <= 24; ++b) {
+            int ra = lt_div_up(H, a), rb = lt_div_up(H, b);
+            int na = n * tiles * lt_div_up(H, ra), nb = n * tiles * lt_div_up(H, rb);
+            double ta = (ra + 54) * 0.735, tb = (rb + 28) * 0.412;
+            freeat.assign(slots, 0.0);
+            // CTAs start in grid order on the earliest free slot
+            std::make_heap(freeat.begin(), freeat.end(), std::greater<double>());
+            double makespan = 0.0;
+            for (int i = 0; i < na + nb; ++i) {
+                std::pop_heap(freeat.begin(), freeat.end(), std::greater<double>());
+                double t = freeat.back() + (i < na ? ta : tb);
+                freeat.back() = t;
+                std::push_heap(freeat.begin(), freeat.end(), std::greater<double>());
+                if (t > makespan) makespan = t;
+            }
+            if (makespan < best - 1e-9) { best = makespan; c55 = a; c29 = b; }
+        }
+    cache_n = n; cache_h = H; cache_slots = slots;
+    *b55 = c55; *b29 = c29;
+}
+
+template <bool IS_MAX, bool TOPHAT>
+static int launch_morph_pair(lt_handle* h, MorphJob j55, MorphJob j29, int n, const int* list, const int* count,
+                             cudaStream_t st) {
+    size_t smem = morph_smem_bytes<55>(TOPHAT) > morph_smem_bytes<29>(TOPHAT) ? morph_smem_bytes<55>(TOPHAT)
+                                                                               : morph_smem_bytes<29>(TOPHAT);
     static bool attr_done = false;
     if (!attr_done) {
-        LT_CUDA(cudaFuncSetAttribute(k_morph<K, IS_MAX, TOPHAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
+        LT_CUDA(cudaFuncSetAttribute(k_morph_pair<IS_MAX, TOPHAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
     const LtDims& d = h->d;
-    int band_rows = lt_div_up(d.bv_h, bands);
-    dim3 g(lt_div_up(d.p2, MORPH_TW), lt_div_up(d.bv_h, band_rows), n);
-    k_morph<K, IS_MAX, TOPHAT><<<g, MORPH_TW, smem, st>>>(src, dst, orig, d, band_rows, h->stream_plane, list, count);
+    const int tiles = lt_div_up(d.p2, MORPH_TW);
+    const int slots = MORPH_CTAS_PER_SM * (h->sm_count > 0 ? h->sm_count : 148);
+    int b55, b29;
+    choose_bands(n, tiles, d.bv_h, slots, &b55, &b29);
+    j55.band_rows = lt_div_up(d.bv_h, b55); j55.bands = lt_div_up(d.bv_h, j55.band_rows);
+    j29.band_rows = lt_div_up(d.bv_h, b29); j29.bands = lt_div_up(d.bv_h, j29.band_rows);
+    const int grid = n * tiles * (j55.bands + j29.bands);
+    k_morph_pair<IS_MAX, TOPHAT><<<grid, MORPH_TW, smem, st>>>(j55, j29, d, tiles, n, h->stream_plane, list, count);
     LT_LAUNCH_CHECK();
     return 0;
 }
@@ -852,25 +916,12 @@ int lt_launch_filter(lt_handle* h, int n, const LtAttemptParams& p, const int* l
     const LtDims& d = h->d;
     int rc;
     if (p.filter_type == 0) {
-        // bands: enough CTAs to fill 148 SMs x 2 while keeping the 2R-row warm-up per band small
-        // bands: minimise (scheduling rounds) x (rows walked per CTA, incl. the 2R-row warm-up), 2 CTAs per SM
-        int tiles = lt_div_up(d.p2, MORPH_TW);
-        int bands = 1;
-        double best = 1e30;
-        const int slots = MORPH_CTAS_PER_SM * (h->sm_count > 0 ? h->sm_count : 148);
-        for (int b = 1; b <= 32; ++b) {
-            int br = lt_div_up(d.bv_h, b), ctas = n * tiles * lt_div_up(d.bv_h, br);
-            double cost = (double)lt_div_up(ctas, slots) * (br + 54);
-            if (cost < best - 1e-9) { best = cost; bands = b; }
-        }
-        if ((rc = launch_morph<55, false, false>(h, h->planeB, h->tmpB, nullptr, n, list, count, bands, st))) return rc;
-        lt_prof_mark(h, ST_ERODE55, st);
-        if ((rc = launch_morph<29, false, false>(h, h->planeR, h->tmpR, nullptr, n, list, count, bands, st))) return rc;
-        lt_prof_mark(h, ST_ERODE29, st);
-        if ((rc = launch_morph<55, true, true>(h, h->tmpB, h->topB, h->planeB, n, list, count, bands, st))) return rc;
-        lt_prof_mark(h, ST_TOPHAT55, st);
-        if ((rc = launch_morph<29, true, true>(h, h->tmpR, h->topR, h->planeR, n, list, count, bands, st))) return rc;
-        lt_prof_mark(h, ST_TOPHAT29, st);
+        MorphJob e55 = {h->planeB, h->tmpB, nullptr, 0, 0}, e29 = {h->planeR, h->tmpR, nullptr, 0, 0};
+        if ((rc = launch_morph_pair<false, false>(h, e55, e29, n, list, count, st))) return rc;
+        lt_prof_mark(h, ST_ERODE55, st);            // both erosions (55x55 on Lab-b, 29x29 on R) in one launch
+        MorphJob t55 = {h->tmpB, h->topB, h->planeB, 0, 0}, t29 = {h->tmpR, h->topR, h->planeR, 0, 0};
+        if ((rc = launch_morph_pair<true, true>(h, t55, t29, n, list, count, st))) return rc;
+        lt_prof_mark(h, ST_TOPHAT55, st);           // both dilations + top-hat epilogues in one launch
         if ((rc = launch_cross(h, h->topR, h->merged, p.ksize_r, p.C_r, 0, n, list, count, st))) return rc;
         lt_prof_mark(h, ST_CROSS_R, st);
         if ((rc = launch_cross(h, h->topB, h->merged, p.ksize_b, p.C_b, 1, n, list, count, st))) return rc;
