@@ -133,7 +133,8 @@ int64_t lt_launch_count(void);
 
 /* LaneTracker.process (lane_tracker.py:876-1209) for streams 0..n_streams-1.
  *   d_frames : [n_streams][img_h][img_w][3]
- *   d_out    : same shape, or NULL for fits-only mode (no overlay rendered)
+ *   d_out    : same shape, NULL for fits-only mode (no overlay rendered), or == d_frames to annotate in place
+ *              (only the rows the lane overlay can reach are rewritten)
  *   params   : one lt_params for all streams (the reference's defaults-are-the-
  *              config convention, README.md:34)
  *   d_results: [n_streams] lt_result, device memory (copy back asynchronously)
@@ -151,6 +152,12 @@ int lt_set_capture(lt_handle* h, int32_t enable);
  * h_count: true count; h_centroids: LT_MAX_LEVELS ints (sliding-window search only). Synchronous. */
 int lt_read_capture(lt_handle* h, int32_t stream_id, int32_t attempt, int32_t side, uint32_t* h_pixels,
                     int32_t capacity, int32_t* h_count, int32_t* h_centroids, int32_t* h_ncentroids);
+
+/* Copy frame rows [row0, row1) of n_frames frames between a host (pinned) and a device batch of full frames
+ * (one cudaMemcpy2DAsync: pitch = frame size).  to_device: 1 host->device, 0 device->host.  Used to move only
+ * the rows the tracker reads / the overlay can change (lt_debug_read geometry) across PCIe. */
+int lt_memcpy_rows(lt_handle* h, void* dst, const void* src, int32_t n_frames, int32_t row0, int32_t row1,
+                   int32_t to_device, void* stream);
 
 /* ---- in-stream stage timing (bench.py's roofline figures) --------------------
  * lt_profile_begin arms CUDA-event recording at every stage boundary of the next `max_calls`
@@ -226,8 +233,9 @@ int lt_set_state(lt_handle* h, int32_t stream_id, const lt_state* h_state, const
  * what: 0 undistort map (int32 [img_h][img_w][2]), 1 bird's-eye map (int32 [bv_h][bv_w][2]),
  *       2 overlay map (int32 [img_h][img_w][2]), 3 R plane u8 [bv_h][bv_w], 4 LAB-b plane,
  *       5 R top-hat, 6 b top-hat, 7 mask u8 {0,255}, 8 merged (pre-open) mask,
- *       9 lane row spans int32 [bv_h][2], 10 geometry int32[7] = {undistorted ROI first,last+1, overlay rows
- *       first,last+1, pair-plane width, mask words per row, pixel-list capacity of lt_read_capture}.
+ *       9 lane row spans int32 [bv_h][2], 10 geometry int32[9] = {undistorted ROI first,last+1, overlay rows
+ *       first,last+1, pair-plane width, mask words per row, pixel-list capacity of lt_read_capture, frame rows the
+ *       tracker reads first,last+1}.
  * Copies to HOST memory; synchronous. Returns bytes written or <0. */
 int64_t lt_debug_read(lt_handle* h, int32_t what, int32_t stream_id, void* h_dst, int64_t capacity);
 

@@ -160,6 +160,18 @@ extern "C" int lt_create(const lt_config* cfg, lt_handle** out) {
         }
         if (r0 >= r1) { r0 = 0; r1 = 1; }
         d.roi0 = r0; d.roi1 = r1;
+        {   // frame rows read by the undistort of the ROI rows (for partial host->device transfers)
+            std::vector<int2> u((size_t)(r1 - r0) * d.img_w);
+            cudaMemcpy(u.data(), h->und_map + (size_t)r0 * d.img_w, u.size() * sizeof(int2), cudaMemcpyDeviceToHost);
+            int s0 = d.img_h, s1 = 0;
+            for (size_t i = 0; i < u.size(); ++i) {
+                int sy = u[i].y >> 5;
+                for (int yy = sy; yy <= sy + 1; ++yy)
+                    if (yy >= 0 && yy < d.img_h) { s0 = yy < s0 ? yy : s0; s1 = yy + 1 > s1 ? yy + 1 : s1; }
+            }
+            if (s0 >= s1) { s0 = 0; s1 = d.img_h; }
+            h->src0 = s0; h->src1 = s1;
+        }
         std::vector<int2> o(npx);
         cudaMemcpy(o.data(), h->ov_map, npx * sizeof(int2), cudaMemcpyDeviceToHost);
         int o0 = d.img_h, o1 = 0;
@@ -234,7 +246,6 @@ extern "C" int lt_process(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out,
     int rc;
     if ((rc = check_n(h, n))) return rc;
     if (!d_frames || !params || !d_results) { lt_set_error("null argument"); return -1; }
-    if (d_out == d_frames) { lt_set_error("d_out must not alias d_frames"); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
     LtAttemptParams p1 = attempt_from(*params), p2 = second_attempt();
     if ((rc = check_params(h, p1))) return rc;
@@ -321,6 +332,17 @@ extern "C" int lt_profile_read(lt_handle* h, double* ms, int32_t* calls) {
     }
     *calls = h->prof_calls;
     h->prof_active = 0;
+    return 0;
+}
+
+extern "C" int lt_memcpy_rows(lt_handle* h, void* dst, const void* src, int32_t n, int32_t row0, int32_t row1,
+                              int32_t to_device, void* stream) {
+    if (!h || !dst || !src || n < 1 || row0 < 0 || row1 > h->d.img_h || row0 >= row1) { lt_set_error("bad argument"); return -1; }
+    const size_t row_bytes = (size_t)h->d.img_w * 3, frame_bytes = row_bytes * h->d.img_h;
+    const char* s = (const char*)src + (size_t)row0 * row_bytes;
+    char* d = (char*)dst + (size_t)row0 * row_bytes;
+    LT_CUDA(cudaMemcpy2DAsync(d, frame_bytes, s, frame_bytes, (size_t)(row1 - row0) * row_bytes, (size_t)n,
+                              to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return 0;
 }
 
@@ -487,7 +509,7 @@ extern "C" int lt_draw_lane(lt_handle* h, const uint8_t* d_frames, uint8_t* d_ou
                             const int32_t* d_counts, void* stream) {
     int rc;
     if ((rc = check_n(h, n))) return rc;
-    if (!d_frames || !d_out || !d_x || !d_counts || d_out == d_frames) { lt_set_error("null or aliased argument"); return -1; }
+    if (!d_frames || !d_out || !d_x || !d_counts) { lt_set_error("null argument"); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = lt_launch_lane_rows(h, d_x, d_counts, n, st))) return rc;
     return lt_launch_overlay(h, d_frames, d_out, n, h->draw_flags, st);
@@ -571,7 +593,7 @@ extern "C" int64_t lt_debug_read(lt_handle* h, int32_t what, int32_t id, void* d
         }
         case 9: src = h->lane_rows + (size_t)id * d.bv_h; bytes = (size_t)d.bv_h * sizeof(int2); break;
         case 10: {
-            int v[7] = {d.roi0, d.roi1, d.ov0, d.ov1, d.p2, d.mwords, h->pix_cap};
+            int v[9] = {d.roi0, d.roi1, d.ov0, d.ov1, d.p2, d.mwords, h->pix_cap, h->src0, h->src1};
             if (cap < (int64_t)sizeof(v)) { lt_set_error("buffer too small"); return -1; }
             memcpy(dst, v, sizeof(v));
             return sizeof(v);

@@ -51,6 +51,7 @@ struct lt_handle {
     int S;                       // max streams
     lt_validity val;             // check_validity windows
     int sm_count;
+    int src0, src1;              // frame rows the undistort of the ROI reads: [src0, src1)
     // shared tables
     int2* und_map;               // [img_h][img_w]
     int2* bv_map;                // [bv_h][bv_w]

@@ -310,16 +310,17 @@ __device__ __forceinline__ int lane_tap(const int2* __restrict__ rows, const LtD
 }
 
 __global__ void __launch_bounds__(256)
-k_overlay(const uint8_t* __restrict__ frames, uint8_t* __restrict__ out, const int2* __restrict__ map,
-          const int2* __restrict__ lane_rows, const int* __restrict__ draw, LtDims d) {
-    // one thread = 4 pixels = 12 bytes (three aligned 32-bit words); img_w % 4 == 0 is checked at create
+k_overlay(const uint8_t* frames, uint8_t* out, const int2* __restrict__ map,
+          const int2* __restrict__ lane_rows, const int* __restrict__ draw, LtDims d, int row0) {
+    // one thread = 4 pixels = 12 bytes (three aligned 32-bit words); img_w % 4 == 0 is checked at create.
+    // `out` may alias `frames` (in-place annotation): every thread reads and writes only its own 12 bytes.
     int q = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y, s = blockIdx.z;
+    int y = row0 + blockIdx.y, s = blockIdx.z;
     int qw = d.img_w >> 2;
     if (q >= qw) return;
     size_t base = (((size_t)s * d.img_h + y) * d.img_w + (size_t)q * 4) * 3;
     const uint32_t* src = reinterpret_cast<const uint32_t*>(frames + base);
-    uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+    uint32_t w0 = src[0], w1 = src[1], w2 = src[2];
     if (draw[s] && y >= d.ov0 && y < d.ov1) {
         const int2* rows = lane_rows + (size_t)s * d.bv_h;
         uint32_t gch[4] = {(w0 >> 8) & 255, w1 & 255, (w1 >> 24) & 255, (w2 >> 16) & 255};
@@ -343,11 +344,48 @@ k_overlay(const uint8_t* __restrict__ frames, uint8_t* __restrict__ out, const i
     dst[0] = w0; dst[1] = w1; dst[2] = w2;
 }
 
+// rows the overlay cannot touch are a plain copy: 16-byte vectors, four in flight per thread
+__global__ void __launch_bounds__(256)
+k_copy_rows(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t frame_vec, size_t a_vec, size_t b_off,
+            size_t b_vec) {
+    const size_t total = a_vec + b_vec;
+    const uint4* fs = src + (size_t)blockIdx.y * frame_vec;
+    uint4* fd = dst + (size_t)blockIdx.y * frame_vec;
+    size_t i0 = ((size_t)blockIdx.x * blockDim.x) * 4 + threadIdx.x;
+    uint4 v[4];
+    size_t idx[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        size_t i = i0 + (size_t)u * blockDim.x;
+        idx[u] = i < a_vec ? i : b_off + (i - a_vec);
+        if (i < total) v[u] = __ldg(&fs[idx[u]]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (i0 + (size_t)u * blockDim.x < total) fd[idx[u]] = v[u];
+}
+
 int lt_launch_overlay(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int n, const int* d_draw,
                       cudaStream_t st) {
     const LtDims& d = h->d;
-    dim3 g(lt_div_up(d.img_w / 4, 256), d.img_h, n);
-    k_overlay<<<g, 256, 0, st>>>(d_frames, d_out, h->ov_map, h->lane_rows, d_draw, d);
-    LT_LAUNCH_CHECK();
+    const size_t row_bytes = (size_t)d.img_w * 3, frame_bytes = row_bytes * d.img_h;
+    int r0 = d.ov0, r1 = d.ov1;
+    if (r0 >= r1) { r0 = 0; r1 = 0; }
+    const bool inplace = (d_out == d_frames);
+    const bool vec_ok = (row_bytes % 16 == 0) && (((uintptr_t)d_frames | (uintptr_t)d_out) % 16 == 0);
+    if (!inplace && !vec_ok) { r0 = 0; r1 = d.img_h; }            // generic path copies every row itself
+    if (!inplace && vec_ok && (r0 > 0 || r1 < d.img_h)) {
+        const size_t a_vec = (size_t)r0 * row_bytes / 16, b_off = (size_t)r1 * row_bytes / 16;
+        const size_t b_vec = (size_t)(d.img_h - r1) * row_bytes / 16;
+        dim3 g((unsigned)((a_vec + b_vec + 1023) / 1024), n);
+        k_copy_rows<<<g, 256, 0, st>>>(reinterpret_cast<const uint4*>(d_frames), reinterpret_cast<uint4*>(d_out),
+                                        frame_bytes / 16, a_vec, b_off, b_vec);
+        LT_LAUNCH_CHECK();
+    }
+    if (r1 > r0) {
+        dim3 g(lt_div_up(d.img_w / 4, 256), r1 - r0, n);
+        k_overlay<<<g, 256, 0, st>>>(d_frames, d_out, h->ov_map, h->lane_rows, d_draw, d, r0);
+        LT_LAUNCH_CHECK();
+    }
     return 0;
 }

@@ -95,10 +95,11 @@ class BatchedLaneTracker:
         S = self.n_streams
         self._results_dev = torch.zeros(S * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
         self._results_host = torch.zeros(S * RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
-        geo = np.zeros(7, dtype=np.int32)
+        geo = np.zeros(9, dtype=np.int32)
         check(self.lib.lt_debug_read(self._h, 10, 0, geo.ctypes.data_as(C.c_void_p), geo.nbytes))
         self.geometry = dict(roi_rows=(int(geo[0]), int(geo[1])), overlay_rows=(int(geo[2]), int(geo[3])),
-                             plane_width=int(geo[4]), mask_words=int(geo[5]), pixel_capacity=int(geo[6]))
+                             plane_width=int(geo[4]), mask_words=int(geo[5]), pixel_capacity=int(geo[6]),
+                             source_rows=(int(geo[7]), int(geo[8])))
 
     # -- lifetime -----------------------------------------------------------
     def close(self):
@@ -132,6 +133,13 @@ class BatchedLaneTracker:
                 raise TypeError("unknown validity option %r" % k)
             setattr(v, k, float(val))
         check(self.lib.lt_set_validity(self._h, C.byref(v)))
+
+    def copy_rows(self, dst, src, row0, row1, to_device):
+        """Copy frame rows [row0, row1) of a batch of full frames between pinned host and device tensors on the
+        current stream (strided 2-D copy, no staging)."""
+        n = int(src.shape[0])
+        check(self.lib.lt_memcpy_rows(self._h, _ptr(dst), _ptr(src), n, int(row0), int(row1), int(bool(to_device)),
+                                      _stream_ptr(self.device)))
 
     def set_capture(self, enable=True):
         check(self.lib.lt_set_capture(self._h, int(bool(enable))))
@@ -371,10 +379,21 @@ class HostPipeline:
         for out, results in pipe.drain(): ...
     """
 
-    def __init__(self, tracker, depth=3, overlay=True, params=None):
+    def __init__(self, tracker, depth=3, overlay=True, params=None, inplace=False):
+        """inplace=True: annotate the caller's pinned frames in place.  Only the frame rows the tracker reads
+        (geometry['source_rows'] + overlay rows) go host->device and only the rows the overlay can change
+        (geometry['overlay_rows']) come back, written into the submitted tensor; every other row of the frame is
+        already identical to the annotated frame, so the host ends up with the same image as overlay mode while
+        about a third of the bytes cross PCIe."""
         self.t = tracker
         self.depth = int(depth)
         self.overlay = overlay
+        self.inplace = bool(inplace)
+        if self.inplace and not overlay:
+            raise ValueError('inplace needs overlay=True')
+        g = tracker.geometry
+        self.rows_in = (min(g['source_rows'][0], g['overlay_rows'][0]), max(g['source_rows'][1], g['overlay_rows'][1]))
+        self.rows_out = g['overlay_rows']
         self.params = params if params is not None else make_params()
         dev = tracker.device
         w, h = tracker.img_size
@@ -384,9 +403,9 @@ class HostPipeline:
         for _ in range(self.depth):
             self.slots.append(dict(
                 d_in=torch.empty((S, h, w, 3), dtype=torch.uint8, device=dev),
-                d_out=torch.empty((S, h, w, 3), dtype=torch.uint8, device=dev) if overlay else None,
+                d_out=torch.empty((S, h, w, 3), dtype=torch.uint8, device=dev) if (overlay and not inplace) else None,
                 d_res=torch.zeros(S * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev),
-                h_out=torch.empty((S, h, w, 3), dtype=torch.uint8).pin_memory() if overlay else None,
+                h_out=torch.empty((S, h, w, 3), dtype=torch.uint8).pin_memory() if (overlay and not inplace) else None,
                 h_res=torch.zeros(S * RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory(),
                 e_in=torch.cuda.Event(), e_run=torch.cuda.Event(), e_out=torch.cuda.Event(), n=0, busy=False))
         self.head = 0          # next slot to submit into
@@ -403,17 +422,26 @@ class HostPipeline:
         sl["n"] = n
         with torch.cuda.stream(self.s_in):
             self.s_in.wait_event(sl["e_run"])            # the kernels that last read this input buffer are done
-            sl["d_in"][:n].copy_(host_frames, non_blocking=True)
+            if self.inplace:
+                a, b = self.rows_in
+                self.t.copy_rows(sl["d_in"], host_frames, a, b, True)
+                sl["frames"] = host_frames
+            else:
+                sl["d_in"][:n].copy_(host_frames, non_blocking=True)
             sl["e_in"].record(self.s_in)
         with torch.cuda.stream(self.s_run):
             self.s_run.wait_event(sl["e_in"])
             self.s_run.wait_event(sl["e_out"])           # the previous D2H out of this output buffer is done
-            self.t.process_async(sl["d_in"][:n], sl["d_out"][:n] if self.overlay else None, params=self.params,
-                                 results_dev=sl["d_res"])
+            d_out = sl["d_in"][:n] if self.inplace else (sl["d_out"][:n] if self.overlay else None)
+            self.t.process_async(sl["d_in"][:n], d_out, params=self.params, results_dev=sl["d_res"])
             sl["e_run"].record(self.s_run)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(sl["e_run"])
-            if self.overlay:
+            if self.inplace:
+                a, b = self.rows_out
+                if b > a:
+                    self.t.copy_rows(host_frames, sl["d_in"][:n], a, b, False)
+            elif self.overlay:
                 sl["h_out"][:n].copy_(sl["d_out"][:n], non_blocking=True)
             sl["h_res"].copy_(sl["d_res"], non_blocking=True)
             sl["e_out"].record(self.s_out)
@@ -430,7 +458,7 @@ class HostPipeline:
         sl["e_out"].synchronize()
         n = sl["n"]
         res = sl["h_res"][:n * RESULT_DTYPE.itemsize].numpy().view(RESULT_DTYPE)
-        out = sl["h_out"][:n] if self.overlay else None
+        out = sl.pop("frames") if self.inplace else (sl["h_out"][:n] if self.overlay else None)
         sl["busy"] = False
         self.tail = (self.tail + 1) % self.depth
         self.inflight -= 1

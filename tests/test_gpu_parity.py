@@ -561,3 +561,44 @@ def test_process_randomised_options_and_state_machine(torch_mod, case):
             assert gpu.average_curve_radius == ref.average_curve_radius, tag
         if ref.left_x is not None and ref.detected_pixels:
             assert np.array_equal(gpu.left_x, ref.left_x) and np.array_equal(gpu.right_y, ref.right_y), tag
+
+
+def test_inplace_annotation_and_roi_pipeline(torch_mod):
+    """d_out == d_frames rewrites only the rows the overlay can reach; HostPipeline(inplace=True) moves only the
+    rows the tracker reads / the overlay changes across PCIe and leaves the same image in the caller's buffer."""
+    from lane_tracker_b200 import BatchedLaneTracker, HostPipeline
+    S, T = 2, 6
+    vids = [synth.RoadVideo(30 + s) for s in range(S)]
+    frames = [np.stack([v.frame(t) for v in vids]) for t in range(T)]
+    a = BatchedLaneTracker(S, **CAL)
+    b = BatchedLaneTracker(S, **CAL)
+    c = BatchedLaneTracker(S, **CAL)
+    g = a.geometry
+    assert 0 <= g["source_rows"][0] < g["source_rows"][1] <= 720
+    assert 0 < g["overlay_rows"][0] < g["overlay_rows"][1] <= 720
+    want = []
+    for t in range(T):
+        d = torch_mod.as_tensor(frames[t]).cuda()
+        out = torch_mod.empty_like(d)
+        res = a.process(d, out)
+        want.append((out.cpu().numpy(), res.copy()))
+        d2 = d.clone()
+        res2 = b.process(d2, d2)                       # in place on the device
+        assert np.array_equal(d2.cpu().numpy(), want[-1][0]) and res2.tobytes() == res.tobytes(), t
+    assert (want[-1][0] != frames[-1]).any()           # the overlay really changed pixels
+    pipe = HostPipeline(c, depth=3, inplace=True)
+    host = [torch_mod.from_numpy(f.copy()).pin_memory() for f in frames]
+    got = []
+    for t in range(T):
+        pipe.submit(host[t])
+        for fr, res in pipe.ready():
+            got.append((fr, res.copy()))
+    for fr, res in pipe.drain():
+        got.append((fr, res.copy()))
+    assert len(got) == T
+    for t in range(T):
+        assert got[t][0] is host[t]
+        assert np.array_equal(host[t].numpy(), want[t][0]), t
+        assert got[t][1].tobytes() == want[t][1].tobytes(), t
+    for x in (a, b, c):
+        x.close()
