@@ -262,6 +262,22 @@ def run_gpu_arm(args):
     valid_frac = float(res["valid_lane_lines"].mean())
     band_frac = float((res["search_mode"] == 1).mean())
 
+    # ---- separately reported variant: fused single-resample remap (not bit-exact; stated mask-IoU tolerance) ----
+    trk.set_remap_mode("fused")
+    trk.reset()
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    h1.record(stream)
+    barrier()
+    ms_fused = h0.elapsed_time(h1)
+    fused_valid = float(trk.fetch_results(S)["valid_lane_lines"].mean())
+    trk.set_remap_mode("exact")
+
     # ---- end to end: pinned host frames in, annotated frames + results out, every step ----------
     # through the public HostPipeline API: H2D of step k+1, kernels of step k and D2H of step k-1 overlap
     from lane_tracker_b200 import HostPipeline
@@ -321,9 +337,9 @@ def run_gpu_arm(args):
     rows_out = pipe2.rows_out[1] - pipe2.rows_out[0]
 
     if distributed:
-        t = torch.tensor([ms, ms_e2e, ms_inplace], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, ms_e2e, ms_inplace, ms_fused], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_inplace = float(t[0]), float(t[1]), float(t[2])
+        ms, ms_e2e, ms_inplace, ms_fused = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     frames_total = world * S * args.steps
     value = frames_total / (ms * 1e-3)
     e2e_value = frames_total / (ms_e2e * 1e-3)
@@ -372,6 +388,11 @@ def run_gpu_arm(args):
                             "d2h_bytes_per_step": (S * rows_out * 1280 * 3 + trk._results_dev.numel()) * world,
                             "ms_per_step": ms_inplace / args.steps,
                             "note": "HostPipeline(inplace=True): frames annotated in the caller's pinned buffers"},
+            "fused_remap_variant": {"value": frames_total / (ms_fused * 1e-3), "unit": "frames/s",
+                                    "ms_per_step": ms_fused / args.steps, "valid_fraction_last_step": fused_valid,
+                                    "tolerance": "not bit-exact: mask IoU vs the exact remap >= 0.6 per frame and >= 0.8 "
+                                                 "mean on the 11 bundled frames (measured 0.886-0.946, mean 0.915; "
+                                                 "tests/test_gpu_parity.py::test_fused_remap_variant)"},
             "gpu_launches": int(launches), "clocks": clocks,
             "tracking": {"valid_fraction_last_step": valid_frac, "band_search_fraction_last_step": band_frac},
             "render_s": t_render,

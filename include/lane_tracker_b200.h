@@ -153,6 +153,12 @@ int lt_set_capture(lt_handle* h, int32_t enable);
 int lt_read_capture(lt_handle* h, int32_t stream_id, int32_t attempt, int32_t side, uint32_t* h_pixels,
                     int32_t capacity, int32_t* h_count, int32_t* h_centroids, int32_t* h_ncentroids);
 
+/* Remap variant.  0 (default): exact two-stage cv2.undistort + cv2.warpPerspective, bit-exact bird's-eye view.
+ * 1: fused single resample (lens distortion and homography composed in fp64, one bilinear interpolation from the
+ * raw frame).  Mode 1 is NOT bit-exact; its stated tolerance against mode 0 on the reference's bundled frames is
+ * mask IoU >= 0.6 per frame and >= 0.8 on average (measured: tests/test_gpu_parity.py::test_fused_remap_variant). */
+int lt_set_remap_mode(lt_handle* h, int32_t mode);
+
 /* Copy frame rows [row0, row1) of n_frames frames between a host (pinned) and a device batch of full frames
  * (one cudaMemcpy2DAsync: pitch = frame size).  to_device: 1 host->device, 0 device->host.  Used to move only
  * the rows the tracker reads / the overlay can change (lt_debug_read geometry) across PCIe. */

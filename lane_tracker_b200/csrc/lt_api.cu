@@ -100,7 +100,7 @@ static void init_state(lt_handle* h, lt_state* s) {
 extern "C" int lt_destroy(lt_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->und_map, h->bv_map, h->ov_map, h->bv_desc, h->lab_gamma, h->lab_cbrt, h->und_roi, h->planeR, h->planeB,
+    void* ptrs[] = {h->und_map, h->bv_map, h->ov_map, h->bv_desc, h->fused_desc, h->lab_gamma, h->lab_cbrt, h->und_roi, h->planeR, h->planeB,
                     h->tmpR, h->tmpB, h->topR, h->topB, h->merged, h->mask, h->pixels, h->pix_counts, h->lane_rows,
                     h->avg_x, h->state, h->att, h->retry_list, h->retry_count, h->draw_flags, h->scratch_bv,
                     h->cap_pixels, h->cap_counts, h->cap_cents, h->cap_ncents};
@@ -253,9 +253,13 @@ extern "C" int lt_process(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out,
     // find_lane_points (lane_tracker.py:795-874), first attempt, all streams
     if (h->prof_active && h->prof_calls >= h->prof_max_calls) h->prof_active = 0;
     lt_prof_mark(h, ST_BEGIN, st);
-    if ((rc = lt_launch_undistort(h, d_frames, n, st))) return rc;
-    lt_prof_mark(h, ST_UNDISTORT, st);
-    if ((rc = lt_launch_warp(h, nullptr, n, st))) return rc;
+    if (h->remap_mode == 1) {
+        if ((rc = lt_launch_warp_fused(h, d_frames, nullptr, n, st))) return rc;
+    } else {
+        if ((rc = lt_launch_undistort(h, d_frames, n, st))) return rc;
+        lt_prof_mark(h, ST_UNDISTORT, st);
+        if ((rc = lt_launch_warp(h, nullptr, n, st))) return rc;
+    }
     lt_prof_mark(h, ST_WARP, st);
     if ((rc = lt_launch_filter(h, n, p1, nullptr, nullptr, st))) return rc;
     LtSearchArgs sa;
@@ -335,6 +339,19 @@ extern "C" int lt_profile_read(lt_handle* h, double* ms, int32_t* calls) {
     return 0;
 }
 
+extern "C" int lt_set_remap_mode(lt_handle* h, int32_t mode) {
+    if (!h || (mode != 0 && mode != 1)) { lt_set_error("remap mode must be 0 (exact) or 1 (fused single resample)"); return -1; }
+    LT_CUDA(cudaSetDevice(h->cfg.device));
+    if (mode == 1 && !h->fused_desc) {
+        int rc = dev_alloc(&h->fused_desc, (size_t)h->d.bv_w * h->d.bv_h);
+        if (rc) return rc;
+        if ((rc = lt_launch_build_fused_desc(h, 0))) return rc;
+        LT_CUDA(cudaDeviceSynchronize());
+    }
+    h->remap_mode = mode;
+    return 0;
+}
+
 extern "C" int lt_memcpy_rows(lt_handle* h, void* dst, const void* src, int32_t n, int32_t row0, int32_t row1,
                               int32_t to_device, void* stream) {
     if (!h || !dst || !src || n < 1 || row0 < 0 || row1 > h->d.img_h || row0 >= row1) { lt_set_error("bad argument"); return -1; }
@@ -395,6 +412,7 @@ extern "C" int lt_remap(lt_handle* h, const uint8_t* d_frames, uint8_t* d_bv_rgb
     if ((rc = check_n(h, n))) return rc;
     if (!d_frames) { lt_set_error("null argument"); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
+    if (h->remap_mode == 1) return lt_launch_warp_fused(h, d_frames, d_bv_rgb, n, st);
     if ((rc = lt_launch_undistort(h, d_frames, n, st))) return rc;
     return lt_launch_warp(h, d_bv_rgb, n, st);
 }

@@ -57,6 +57,8 @@ struct lt_handle {
     int2* bv_map;                // [bv_h][bv_w]
     int2* ov_map;                // [img_h][img_w]
     int2* bv_desc;               // [bv_h][bv_w] tap descriptors derived from bv_map and the ROI
+    int2* fused_desc;            // [bv_h][bv_w] single-resample variant (lazily built by lt_set_remap_mode)
+    int remap_mode;              // 0 exact two-stage (default), 1 fused single resample
     unsigned short* lab_gamma;   // [256]
     unsigned short* lab_cbrt;    // [3072]
     // per-stream buffers
@@ -114,6 +116,8 @@ void lt_set_error(const char* fmt, ...);
 
 int lt_launch_build_maps(lt_handle* h, cudaStream_t st);
 int lt_launch_build_desc(lt_handle* h, cudaStream_t st);
+int lt_launch_build_fused_desc(lt_handle* h, cudaStream_t st);
+int lt_launch_warp_fused(lt_handle* h, const uint8_t* d_frames, uint8_t* d_bv_rgb, int n, cudaStream_t st);
 int lt_launch_undistort(lt_handle* h, const uint8_t* d_frames, int n, cudaStream_t st);
 int lt_launch_warp(lt_handle* h, uint8_t* d_bv_rgb, int n, cudaStream_t st);
 int lt_launch_planes_from_bv(lt_handle* h, const uint8_t* d_bv_rgb, int n, cudaStream_t st);

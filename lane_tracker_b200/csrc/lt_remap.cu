@@ -267,6 +267,108 @@ int lt_launch_warp(lt_handle* h, uint8_t* d_bv_rgb, int n, cudaStream_t st) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Fused single-resample variant (BASELINE.json north_star (1)): homography and lens
+// distortion composed in fp64, ONE bilinear interpolation straight from the raw frame.  Not bit-exact with the
+// two-stage OpenCV pipeline (no intermediate 8-bit rounding); reported separately under a mask-IoU tolerance.
+// fused_desc: x = byte index of tap (sy, sx) in the raw frame / 3 (pixel index), y = fx | fy<<5 | flags<<10.
+// ---------------------------------------------------------------------------
+
+__global__ void k_build_fused_desc(int2* __restrict__ desc, LtDims d, Mat9 mm, UndistortCoef c) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= d.bv_w) return;
+    const double* m = mm.m;
+    // undistorted-image coordinates of this bird's-eye pixel (same arithmetic as k_build_perspective_map, unrounded)
+    double xb = (double)((x >> 6) << 6), x1 = (double)(x & 63), dy = (double)y;
+    double X0 = add64(add64(mul64(m[0], xb), mul64(m[1], dy)), m[2]);
+    double Y0 = add64(add64(mul64(m[3], xb), mul64(m[4], dy)), m[5]);
+    double W0 = add64(add64(mul64(m[6], xb), mul64(m[7], dy)), m[8]);
+    double W = add64(W0, mul64(m[6], x1));
+    W = (W != 0.0) ? __ddiv_rn(1.0, W) : 0.0;
+    double xu = mul64(add64(X0, mul64(m[0], x1)), W), yu = mul64(add64(Y0, mul64(m[3], x1)), W);
+    uint32_t f = 0;
+    long long idx = 0;
+    if (xu > -1.0 && xu < (double)d.img_w && yu > -1.0 && yu < (double)d.img_h) {
+        // distorted (raw-frame) coordinates of that point: the undistort model at a non-integer position
+        double _x = add64(add64(mul64(yu, c.iR[1]), c.iR[2]), mul64(xu, c.iR[0]));
+        double _y = add64(add64(mul64(yu, c.iR[4]), c.iR[5]), mul64(xu, c.iR[3]));
+        double _w = add64(add64(mul64(yu, c.iR[7]), c.iR[8]), mul64(xu, c.iR[6]));
+        double px = __ddiv_rn(_x, _w), py = __ddiv_rn(_y, _w);
+        double x2 = mul64(px, px), y2 = mul64(py, py), r2 = add64(x2, y2), _2xy = mul64(mul64(2.0, px), py);
+        double kr = add64(1.0, mul64(add64(mul64(add64(mul64(c.k3, r2), c.k2), r2), c.k1), r2));
+        double xd = add64(add64(mul64(px, kr), mul64(c.p1, _2xy)), mul64(c.p2, add64(r2, mul64(2.0, x2))));
+        double yd = add64(add64(mul64(py, kr), mul64(c.p1, add64(r2, mul64(2.0, y2)))), mul64(c.p2, _2xy));
+        int U = round_sat_i32(mul64(add64(mul64(c.fx, xd), c.cx), 32.0));
+        int V = round_sat_i32(mul64(add64(mul64(c.fy, yd), c.cy), 32.0));
+        Tap4 t = make_taps(make_int2(U, V));
+        auto ok = [&](int yy, int xx) { return (unsigned)yy < (unsigned)d.img_h && (unsigned)xx < (unsigned)d.img_w; };
+        f = (uint32_t)(U & 31) | ((uint32_t)(V & 31) << 5);
+        f |= (ok(t.sy, t.sx) ? 1u : 0u) << 10 | (ok(t.sy, t.sx + 1) ? 1u : 0u) << 11 |
+             (ok(t.sy + 1, t.sx) ? 1u : 0u) << 12 | (ok(t.sy + 1, t.sx + 1) ? 1u : 0u) << 13;
+        if (f >> 10) idx = (long long)t.sy * d.img_w + t.sx;
+        else f = 0;
+    }
+    desc[(size_t)y * d.bv_w + x] = make_int2((int)idx, (int)f);
+}
+
+int lt_launch_build_fused_desc(lt_handle* h, cudaStream_t st) {
+    const lt_config& c = h->cfg;
+    UndistortCoef uc;
+    invert3x3(c.cam_matrix, uc.iR);
+    uc.k1 = c.dist_coeffs[0]; uc.k2 = c.dist_coeffs[1]; uc.p1 = c.dist_coeffs[2];
+    uc.p2 = c.dist_coeffs[3]; uc.k3 = c.dist_coeffs[4];
+    uc.fx = c.cam_matrix[0]; uc.fy = c.cam_matrix[4]; uc.cx = c.cam_matrix[2]; uc.cy = c.cam_matrix[5];
+    Mat9 mi;
+    invert3x3(c.M, mi.m);
+    dim3 g(lt_div_up(c.bv_w, 256), c.bv_h);
+    k_build_fused_desc<<<g, 256, 0, st>>>(h->fused_desc, h->d, mi, uc);
+    LT_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_warp_planes_fused(const uint8_t* __restrict__ frames, const int2* __restrict__ desc, uint32_t* __restrict__ planeR,
+                    uint32_t* __restrict__ planeB, uint8_t* __restrict__ bv_rgb,
+                    const unsigned short* __restrict__ g, const unsigned short* __restrict__ cb, LtDims d) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y, s = blockIdx.z;
+    if (x >= d.p2) return;
+    const uint8_t* img = frames + (size_t)s * d.img_w * d.img_h * 3;
+    uint32_t r2 = 0, b2 = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        int px = x + half * d.p2;
+        if (px < d.bv_w) {
+            int2 q = __ldg(&desc[(size_t)y * d.bv_w + px]);
+            const uint32_t f = (uint32_t)q.y;
+            auto tap = [&](int bit, int off) -> uint32_t {
+                if (!(f & (1u << bit))) return 0u;
+                const uint8_t* p = img + ((size_t)q.x + off) * 3;
+                return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+            };
+            uint32_t o = blend_rgbx(tap(10, 0), tap(11, 1), tap(12, d.img_w), tap(13, d.img_w + 1), f);
+            r2 |= (o & 255u) << (16 * half);
+            b2 |= (uint32_t)lab_b(o, g, cb) << (16 * half);
+            if (bv_rgb) {
+                uint8_t* p = bv_rgb + (((size_t)s * d.bv_h + y) * d.bv_w + px) * 3;
+                p[0] = o & 255; p[1] = (o >> 8) & 255; p[2] = (o >> 16) & 255;
+            }
+        }
+    }
+    size_t o = ((size_t)s * d.bv_h + y) * d.p2 + x;
+    planeR[o] = r2;
+    planeB[o] = b2;
+}
+
+int lt_launch_warp_fused(lt_handle* h, const uint8_t* d_frames, uint8_t* d_bv_rgb, int n, cudaStream_t st) {
+    const LtDims& d = h->d;
+    dim3 g(lt_div_up(d.p2, 256), d.bv_h, n);
+    k_warp_planes_fused<<<g, 256, 0, st>>>(d_frames, h->fused_desc, h->planeR, h->planeB, d_bv_rgb, h->lab_gamma,
+                                           h->lab_cbrt, d);
+    LT_LAUNCH_CHECK();
+    return 0;
+}
+
 // planes from a caller-supplied bird's-eye RGB image (filter_lane_points API, lane_tracker.py:207-208)
 __global__ void __launch_bounds__(256)
 k_planes_from_bv(const uint8_t* __restrict__ bv_rgb, uint32_t* __restrict__ planeR, uint32_t* __restrict__ planeB,

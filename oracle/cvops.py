@@ -450,3 +450,50 @@ def add_weighted_03(img, lane):
     """``cv2.addWeighted(img, 1, lane, 0.3, 0)`` (lane_tracker.py:662): float32."""
     f = img.astype(np.float32) + lane.astype(np.float32) * np.float32(0.3)
     return np.clip(np.rint(f), 0, 255).astype(np.uint8)
+
+
+# --------------------------------------------------------------------------
+# Fused single-resample variant of the remap (not part of the reference: BASELINE.json north_star (1) asks for it
+# as a separately reported, non-bit-exact variant).  Restated here only so that the CUDA variant can be checked
+# for determinism; its agreement with the exact pipeline is a mask-IoU statement, not bit parity.
+# --------------------------------------------------------------------------
+
+
+def fused_bird_view(frame, K, D, M, bv_width, bv_height):
+    """One bilinear interpolation from the raw frame through homography o lens distortion (fp64 maps)."""
+    K = np.asarray(K, dtype=np.float64).reshape(3, 3)
+    Dv = np.asarray(D, dtype=np.float64).ravel()
+    k1, k2, p1, p2 = Dv[0], Dv[1], Dv[2], Dv[3]
+    k3 = Dv[4] if Dv.size > 4 else 0.0
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    iR = invert3x3_cv(K)
+    m = invert3x3_cv(M).ravel()
+    h, w = frame.shape[:2]
+    x = np.arange(bv_width, dtype=np.int64)[None, :]
+    y = np.arange(bv_height, dtype=np.float64)[:, None]
+    xb = ((x // 64) * 64).astype(np.float64)
+    x1 = (x % 64).astype(np.float64)
+    X0 = (m[0] * xb + m[1] * y) + m[2]
+    Y0 = (m[3] * xb + m[4] * y) + m[5]
+    W0 = (m[6] * xb + m[7] * y) + m[8]
+    W = W0 + m[6] * x1
+    with np.errstate(divide="ignore", invalid="ignore"):
+        Wi = np.where(W != 0.0, 1.0 / W, 0.0)
+    xu = (X0 + m[0] * x1) * Wi
+    yu = (Y0 + m[3] * x1) * Wi
+    inside = (xu > -1.0) & (xu < w) & (yu > -1.0) & (yu < h)
+    _x = (yu * iR[0, 1] + iR[0, 2]) + xu * iR[0, 0]
+    _y = (yu * iR[1, 1] + iR[1, 2]) + xu * iR[1, 0]
+    _w = (yu * iR[2, 1] + iR[2, 2]) + xu * iR[2, 0]
+    px, py = _x / _w, _y / _w
+    x2, y2 = px * px, py * py
+    r2 = x2 + y2
+    _2xy = 2.0 * px * py
+    kr = 1.0 + ((k3 * r2 + k2) * r2 + k1) * r2
+    xd = px * kr + p1 * _2xy + p2 * (r2 + 2.0 * x2)
+    yd = py * kr + p1 * (r2 + 2.0 * y2) + p2 * _2xy
+    U = np.rint(np.clip((fx * xd + cx) * 32.0, INT_MIN, INT_MAX)).astype(np.int64)
+    V = np.rint(np.clip((fy * yd + cy) * 32.0, INT_MIN, INT_MAX)).astype(np.int64)
+    out = bilinear_q5(frame, U.astype(np.int32), V.astype(np.int32))
+    out[~inside] = 0
+    return out
