@@ -637,3 +637,61 @@ def test_fused_remap_variant(torch_mod):
     b.set_remap_mode("exact")
     assert _mism(b.remap(d).cpu().numpy(), exact_bv) == 0
     b.close()
+
+
+def test_abi_error_paths_partial_batches_and_lifetime(torch_mod):
+    import ctypes as C
+    from lane_tracker_b200 import BatchedLaneTracker, _lib
+    lib = _lib.load()
+    # constructor validation (no exceptions cross the ABI: negative return + message)
+    bad = dict(CAL, img_size=(1281, 720))
+    with pytest.raises(_lib.LaneTrackerError, match="unsupported geometry"):
+        BatchedLaneTracker(1, **bad)
+    with pytest.raises(_lib.LaneTrackerError, match="n_average"):
+        BatchedLaneTracker(1, **CAL, n_average=9)
+    with pytest.raises(ValueError):
+        BatchedLaneTracker(1, **dict(CAL, dist_coeffs=np.array([0.1] * 8)))
+    free0 = torch_mod.cuda.mem_get_info()[0]
+    S = 3
+    b = BatchedLaneTracker(S, **CAL)
+    vids = [synth.RoadVideo(40 + s) for s in range(S)]
+    f0 = torch_mod.as_tensor(np.stack([v.frame(0) for v in vids])).cuda()
+    with pytest.raises(ValueError):
+        b.process(torch_mod.zeros((S + 1, 720, 1280, 3), dtype=torch_mod.uint8, device="cuda"))
+    with pytest.raises(ValueError):
+        b.process(f0.cpu())
+    with pytest.raises(TypeError):
+        b.process(f0, bogus_option=1)
+    with pytest.raises(_lib.LaneTrackerError, match="window_width"):
+        b.process(f0, window_width=65)
+    # partial batch: only streams 0..1 advance
+    n0 = lib.lt_launch_count()
+    r = b.process(f0[:2].contiguous())
+    assert len(r) == 2 and (r["counter"] == 1).all()
+    assert 10 <= lib.lt_launch_count() - n0 <= 30
+    assert b.get_state(2)[0].counter == 0 and b.get_state(1)[0].counter == 1
+    b.process(f0)
+    assert [b.get_state(s)[0].counter for s in range(S)] == [2, 2, 1]
+    b.reset([1])
+    assert [b.get_state(s)[0].counter for s in range(S)] == [2, 0, 1]
+    assert b.get_state(1)[0].last_detection == 5
+    with pytest.raises(_lib.LaneTrackerError):
+        b.reset([7])
+    # in-stream profiling adds up
+    b.profile_begin(2)
+    b.process(f0); b.process(f0)
+    stages, calls = b.profile_read()
+    assert calls == 2 and stages["erode55"] > 0 and stages["tophat55"] > 0 and stages["warp"] > 0
+    b.close()
+    b.close()                                     # idempotent
+    f2 = f0[:2].contiguous()
+    torch_mod.cuda.synchronize()
+    free1 = torch_mod.cuda.mem_get_info()[0]      # kernels loaded, torch's cache warm
+    for _ in range(8):                            # handles release their device memory
+        t = BatchedLaneTracker(2, **CAL)
+        t.set_capture(True)
+        t.process(f2)
+        t.close()
+    torch_mod.cuda.synchronize()
+    assert abs(torch_mod.cuda.mem_get_info()[0] - free1) < 16 << 20
+    assert free0 > 0
