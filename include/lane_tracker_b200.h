@@ -138,8 +138,8 @@ int64_t lt_launch_count(void);
  *   params   : one lt_params for all streams (the reference's defaults-are-the-
  *              config convention, README.md:34)
  *   d_results: [n_streams] lt_result, device memory (copy back asynchronously)
- * Stream s uses and updates state slot s.  Putative text overlays (putText,
- * lane_tracker.py:653-659, 668-672) are not rendered. */
+ * Stream s uses and updates state slot s.  The putText overlays (lane_tracker.py:653-659, 668-672) are drawn
+ * when glyph sprites are installed (lt_set_text_sprites). */
 int lt_process(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int32_t n_streams,
                const lt_params* params, lt_result* d_results, void* stream);
 
@@ -152,6 +152,15 @@ int lt_set_capture(lt_handle* h, int32_t enable);
  * h_count: true count; h_centroids: LT_MAX_LEVELS ints (sliding-window search only). Synchronous. */
 int lt_read_capture(lt_handle* h, int32_t stream_id, int32_t attempt, int32_t side, uint32_t* h_pixels,
                     int32_t capacity, int32_t* h_count, int32_t* h_centroids, int32_t* h_ncentroids);
+
+/* Text overlays of draw_lane / print_failure (cv2.putText, FONT_HERSHEY_SIMPLEX, scale 1, white, thickness 2,
+ * LINE_AA; lane_tracker.py:653-659, 668-672).  The glyph data (per-character pixel lists and 256-entry
+ * background->output tables, tools/make_text_sprites.py) is supplied by the host, like the calibration; all
+ * pointers are HOST memory and are copied.  Without sprites (or with h_tables == NULL) no text is drawn.
+ * Strings are formatted on the device from the per-stream state. */
+int lt_set_text_sprites(lt_handle* h, const uint8_t* h_tables, int32_t n_tables, const int32_t* h_char_start,
+                        int32_t n_chars, const int16_t* h_dy, const int16_t* h_dx, const uint16_t* h_lut,
+                        int32_t n_pixels, const int32_t* h_advance, int32_t first_char);
 
 /* Remap variant.  0 (default): exact two-stage cv2.undistort + cv2.warpPerspective, bit-exact bird's-eye view.
  * 1: fused single resample (lens distortion and homography composed in fp64, one bilinear interpolation from the

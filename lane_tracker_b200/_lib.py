@@ -78,6 +78,7 @@ SIGNATURES = {
     "lt_process": (C.c_int, [P, P, P, i32, C.POINTER(lt_params), P, P]),
     "lt_set_capture": (C.c_int, [P, i32]),
     "lt_read_capture": (C.c_int, [P, i32, i32, i32, P, i32, C.POINTER(i32), P, C.POINTER(i32)]),
+    "lt_set_text_sprites": (C.c_int, [P, P, i32, P, i32, P, P, P, i32, P, i32]),
     "lt_set_remap_mode": (C.c_int, [P, i32]),
     "lt_memcpy_rows": (C.c_int, [P, P, P, i32, i32, i32, i32, P]),
     "lt_profile_begin": (C.c_int, [P, i32]),

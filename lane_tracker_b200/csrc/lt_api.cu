@@ -103,7 +103,9 @@ extern "C" int lt_destroy(lt_handle* h) {
     void* ptrs[] = {h->und_map, h->bv_map, h->ov_map, h->bv_desc, h->fused_desc, h->lab_gamma, h->lab_cbrt, h->und_roi, h->planeR, h->planeB,
                     h->tmpR, h->tmpB, h->topR, h->topB, h->merged, h->mask, h->pixels, h->pix_counts, h->lane_rows,
                     h->avg_x, h->state, h->att, h->retry_list, h->retry_count, h->draw_flags, h->scratch_bv,
-                    h->cap_pixels, h->cap_counts, h->cap_cents, h->cap_ncents};
+                    h->cap_pixels, h->cap_counts, h->cap_cents, h->cap_ncents,
+                    h->txt_tables, h->txt_char_start, h->txt_dy, h->txt_dx, h->txt_lut, h->txt_advance, h->txt_pair_overlap,
+                    h->txt_bitmaps};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < h->prof_cap; ++i) cudaEventDestroy(h->prof_ev[i]);
     delete[] h->prof_ev; delete[] h->prof_stage;
@@ -290,6 +292,7 @@ extern "C" int lt_process(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out,
     lt_prof_mark(h, ST_UPDATE, st);
     if (d_out) {
         if ((rc = lt_launch_overlay(h, d_frames, d_out, n, h->draw_flags, st))) return rc;
+        if ((rc = lt_launch_text(h, d_out, n, st))) return rc;
         lt_prof_mark(h, ST_OVERLAY, st);
     }
     if (h->prof_active) h->prof_calls++;
@@ -336,6 +339,88 @@ extern "C" int lt_profile_read(lt_handle* h, double* ms, int32_t* calls) {
     }
     *calls = h->prof_calls;
     h->prof_active = 0;
+    return 0;
+}
+
+extern "C" int lt_set_text_sprites(lt_handle* h, const uint8_t* tables, int32_t n_tables, const int32_t* char_start,
+                                   int32_t n_chars, const int16_t* dy, const int16_t* dx, const uint16_t* lut,
+                                   int32_t n_pixels, const int32_t* advance, int32_t first_char) {
+    if (!h) { lt_set_error("null handle"); return -1; }
+    LT_CUDA(cudaSetDevice(h->cfg.device));
+    LT_CUDA(cudaDeviceSynchronize());
+    void* old[] = {h->txt_tables, h->txt_char_start, h->txt_dy, h->txt_dx, h->txt_lut, h->txt_advance, h->txt_pair_overlap, h->txt_bitmaps};
+    for (void* p : old) if (p) cudaFree(p);
+    h->txt_pair_overlap = nullptr; h->txt_bitmaps = nullptr;
+    h->txt_tables = nullptr; h->txt_char_start = nullptr; h->txt_dy = nullptr; h->txt_dx = nullptr;
+    h->txt_lut = nullptr; h->txt_advance = nullptr; h->txt_nchars = 0;
+    if (!tables) return 0;
+    if (n_tables < 1 || n_chars < 1 || n_pixels < 0 || !char_start || !dy || !dx || !lut || !advance ||
+        first_char > '?' || first_char + n_chars <= '?') { lt_set_error("bad sprite data"); return -1; }
+    for (int i = 0; i < n_chars; ++i)
+        if (char_start[i] > char_start[i + 1] || char_start[i + 1] > n_pixels) { lt_set_error("bad sprite index"); return -1; }
+    for (int i = 0; i < n_pixels; ++i)
+        if (lut[i] >= n_tables) { lt_set_error("bad sprite table index"); return -1; }
+    int rc = 0;
+    if (!rc) rc = dev_alloc(&h->txt_tables, (size_t)n_tables * 256);
+    if (!rc) rc = dev_alloc(&h->txt_char_start, (size_t)n_chars + 1);
+    if (!rc) rc = dev_alloc(&h->txt_dy, (size_t)(n_pixels > 0 ? n_pixels : 1));
+    if (!rc) rc = dev_alloc(&h->txt_dx, (size_t)(n_pixels > 0 ? n_pixels : 1));
+    if (!rc) rc = dev_alloc(&h->txt_lut, (size_t)(n_pixels > 0 ? n_pixels : 1));
+    if (!rc) rc = dev_alloc(&h->txt_advance, (size_t)n_chars);
+    if (rc) return rc;
+    LT_CUDA(cudaMemcpy(h->txt_tables, tables, (size_t)n_tables * 256, cudaMemcpyHostToDevice));
+    LT_CUDA(cudaMemcpy(h->txt_char_start, char_start, ((size_t)n_chars + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    LT_CUDA(cudaMemcpy(h->txt_dy, dy, (size_t)n_pixels * sizeof(short), cudaMemcpyHostToDevice));
+    LT_CUDA(cudaMemcpy(h->txt_dx, dx, (size_t)n_pixels * sizeof(short), cudaMemcpyHostToDevice));
+    LT_CUDA(cudaMemcpy(h->txt_lut, lut, (size_t)n_pixels * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    LT_CUDA(cudaMemcpy(h->txt_advance, advance, (size_t)n_chars * sizeof(int), cudaMemcpyHostToDevice));
+    h->txt_nchars = n_chars; h->txt_first = first_char;
+    // The three text lines (baselines 35 rows apart) may be drawn concurrently iff no glyph of the strings this
+    // library formats reaches the rows of the neighbouring line.
+    {
+        const char* alphabet = "Curve Radius: -0123456789mEccentricity.FrameLaneLineDetectionFailed";
+        int lo = 0, hi = 0;
+        for (const char* p = alphabet; *p; ++p) {
+            int c = *p - first_char;
+            if (c < 0 || c >= n_chars) continue;
+            for (int i = char_start[c]; i < char_start[c + 1]; ++i) { lo = dy[i] < lo ? dy[i] : lo; hi = dy[i] > hi ? dy[i] : hi; }
+        }
+        h->txt_parallel_lines = (hi - lo) < 35 ? 1 : 0;
+    }
+    {   // ordered glyph pairs that share pixels, and whether a glyph can reach beyond its immediate neighbour
+        std::vector<unsigned char> ov((size_t)n_chars * n_chars, 0);
+        int min_dx = 0, max_reach = 0, min_adv = 1 << 30;
+        std::vector<std::vector<unsigned long long>> bm(n_chars, std::vector<unsigned long long>(64, 0ull));   // dy+32 rows, dx+8 bits
+        bool fits = true;
+        for (int c = 0; c < n_chars; ++c) {
+            min_adv = advance[c] < min_adv ? advance[c] : min_adv;
+            for (int i = char_start[c]; i < char_start[c + 1]; ++i) {
+                int yy = dy[i] + 32, xx = dx[i] + 8;
+                if (yy < 0 || yy >= 64 || xx < 0 || xx >= 64) { fits = false; continue; }
+                bm[c][yy] |= 1ull << xx;
+                min_dx = dx[i] < min_dx ? dx[i] : min_dx;
+                int reach = dx[i] - advance[c];
+                max_reach = reach > max_reach ? reach : max_reach;
+            }
+        }
+        for (int a = 0; a < n_chars && fits; ++a)
+            for (int b = 0; b < n_chars; ++b)
+                for (int i = char_start[b]; i < char_start[b + 1]; ++i) {
+                    int yy = dy[i] + 32, xx = dx[i] + advance[a] + 8;
+                    if (yy >= 0 && yy < 64 && xx >= 0 && xx < 64 && ((bm[a][yy] >> xx) & 1ull)) { ov[(size_t)a * n_chars + b] = 1; break; }
+                }
+        const bool neighbours_only = fits && (max_reach - min_dx) < min_adv;
+        if (h->txt_pair_overlap) { cudaFree(h->txt_pair_overlap); h->txt_pair_overlap = nullptr; }
+        if (h->txt_bitmaps) { cudaFree(h->txt_bitmaps); h->txt_bitmaps = nullptr; }
+        if (neighbours_only) {
+            if (dev_alloc(&h->txt_pair_overlap, ov.size())) return -2;
+            LT_CUDA(cudaMemcpy(h->txt_pair_overlap, ov.data(), ov.size(), cudaMemcpyHostToDevice));
+            std::vector<unsigned long long> flat((size_t)n_chars * 64);
+            for (int c = 0; c < n_chars; ++c) for (int r = 0; r < 64; ++r) flat[(size_t)c * 64 + r] = bm[c][r];
+            if (dev_alloc(&h->txt_bitmaps, flat.size())) return -2;
+            LT_CUDA(cudaMemcpy(h->txt_bitmaps, flat.data(), flat.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+        }
+    }
     return 0;
 }
 

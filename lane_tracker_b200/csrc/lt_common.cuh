@@ -81,6 +81,11 @@ struct lt_handle {
     int* cap_counts;             // [2][S][2]
     int* cap_cents;              // [2][S][2][LT_MAX_LEVELS]
     int* cap_ncents;             // [2][S][2]
+    // text sprites (lt_set_text_sprites)
+    uint8_t* txt_tables; int* txt_char_start; short* txt_dy; short* txt_dx; unsigned short* txt_lut; int* txt_advance;
+    int txt_nchars, txt_first, txt_parallel_lines;
+    unsigned long long* txt_bitmaps;   // [nchars][64] rows of 64 bits: glyph pixel (dy + 32, dx + 8)
+    unsigned char* txt_pair_overlap;   // [nchars][nchars]: glyph b drawn right after glyph a shares pixels with it
     cudaEvent_t* prof_ev; int* prof_stage; int prof_cap, prof_n, prof_active, prof_calls, prof_max_calls;
     uint8_t* scratch_bv;         // lazily allocated [S][bv_h][bv_w][3] for stage calls
     size_t stream_plane;         // entries per stream in a pair plane
@@ -150,6 +155,7 @@ int lt_launch_validity(lt_handle* h, const double* d_fits, int n, int* d_valid, 
 int lt_launch_poly_points(lt_handle* h, const double* d_fits, int n, double partial, int* d_x, int* d_counts,
                           cudaStream_t st);
 int lt_launch_lane_rows(lt_handle* h, const int* d_x, const int* d_counts, int n, cudaStream_t st);
+int lt_launch_text(lt_handle* h, uint8_t* d_out, int n, cudaStream_t st);
 
 enum LtStage { ST_BEGIN = 0, ST_UNDISTORT, ST_WARP, ST_ERODE55, ST_ERODE29, ST_TOPHAT55, ST_TOPHAT29, ST_CROSS_R,
                ST_CROSS_B, ST_BOX, ST_NOISE, ST_OPEN5, ST_SEARCH, ST_RETRY_SELECT, ST_UPDATE, ST_OVERLAY };

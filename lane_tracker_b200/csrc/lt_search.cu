@@ -895,3 +895,167 @@ int lt_launch_lane_rows(lt_handle* h, const int* d_x, const int* d_counts, int n
     LT_LAUNCH_CHECK();
     return 0;
 }
+
+// ---------------------------------------------------------------------------
+// text overlays (cv2.putText at lane_tracker.py:653-659, 668-672) from glyph sprites
+// ---------------------------------------------------------------------------
+
+struct TextLine { int x0, y0, len; unsigned char ch[56]; };
+
+__device__ void put_str(TextLine& l, const char* s) { while (*s && l.len < 55) l.ch[l.len++] = (unsigned char)*s++; }
+__device__ void put_int(TextLine& l, long long v) {                    // "{}".format(int)
+    char buf[24]; int n = 0;
+    unsigned long long u = v < 0 ? (unsigned long long)(-(v + 1)) + 1ull : (unsigned long long)v;
+    while (u > 0xFFFFFFFFull) { buf[n++] = (char)('0' + (int)(u % 10ull)); u /= 10ull; }   // rare: 64-bit digits
+    unsigned int w = (unsigned int)u;                                                      // common: 32-bit digits
+    do { buf[n++] = (char)('0' + (int)(w % 10u)); w /= 10u; } while (w);
+    if (v < 0 && l.len < 55) l.ch[l.len++] = '-';
+    while (n && l.len < 55) l.ch[l.len++] = (unsigned char)buf[--n];
+}
+__device__ void put_fixed2(TextLine& l, double x) {                    // "{:.2f}".format(float): exact half-even
+    if (!(x == x)) { put_str(l, "nan"); return; }
+    if (signbit(x)) put_str(l, "-");
+    double v = fabs(x);
+    if (!(v < 1e15)) { put_str(l, "inf"); return; }
+    double t = mul64(v, 100.0), e = fma(v, 100.0, -t);                 // t + e == v * 100 exactly
+    double r = floor(t), frac = add64(sub64(t, r), e);
+    if (frac > 0.5 || (frac == 0.5 && fmod(r, 2.0) != 0.0)) r += 1.0;
+    if (frac < 0.0) {                                                    // product rounded up across an integer
+        double fr2 = add64(1.0, frac);
+        r -= 1.0;
+        if (fr2 > 0.5 || (fr2 == 0.5 && fmod(r, 2.0) != 0.0)) r += 1.0;
+    }
+    long long cents = (long long)r;
+    put_int(l, cents / 100);
+    put_str(l, ".");
+    char d2[3] = {(char)('0' + (int)((cents / 10) % 10)), (char)('0' + (int)(cents % 10)), 0};
+    put_str(l, d2);
+}
+
+// Sequential reference form: glyph after glyph (string order matters where neighbouring glyphs overlap).
+__global__ void __launch_bounds__(128)
+k_text_seq(uint8_t* out, LtDims d, const LtDevState* __restrict__ state, const int* __restrict__ draw, int print_frame_count,
+           const uint8_t* __restrict__ tables, const int* __restrict__ char_start, const short* __restrict__ dy,
+           const short* __restrict__ dx, const unsigned short* __restrict__ lut, const int* __restrict__ advance,
+           int nchars, int first_char);
+
+__device__ int format_lines(TextLine* lines, const lt_state& st, int drew, int print_frame_count) {
+    for (int i = 0; i < 3; ++i) { lines[i].len = 0; lines[i].x0 = 20; lines[i].y0 = 35 + 35 * i; }
+    int n = 0;
+    if (drew) {                                                         // draw_lane, lane_tracker.py:653-659
+        put_str(lines[0], "Curve Radius: "); put_int(lines[0], st.average_curve_radius); put_str(lines[0], " m");
+        put_str(lines[1], "Eccentricity: "); put_fixed2(lines[1], st.eccentricity); put_str(lines[1], " m");
+        n = 2;
+    } else {                                                            // print_failure, lane_tracker.py:668-672
+        put_str(lines[0], "Lane Line Detection Failed");
+        n = 1;
+    }
+    if (print_frame_count) { put_str(lines[n], "Frame: "); put_int(lines[n], (long long)st.counter - 1); ++n; }
+    return n;
+}
+
+__global__ void __launch_bounds__(128)
+k_text_seq(uint8_t* out, LtDims d, const LtDevState* __restrict__ state, const int* __restrict__ draw, int print_frame_count,
+           const uint8_t* __restrict__ tables, const int* __restrict__ char_start, const short* __restrict__ dy,
+           const short* __restrict__ dx, const unsigned short* __restrict__ lut, const int* __restrict__ advance,
+           int nchars, int first_char) {
+    const int s = blockIdx.x;
+    __shared__ TextLine lines[3];
+    __shared__ int nlines;
+    if (threadIdx.x == 0) nlines = format_lines(lines, state[s].s, draw[s], print_frame_count);
+    __syncthreads();
+    uint8_t* img = out + (size_t)s * d.img_w * d.img_h * 3;
+    for (int li = 0; li < nlines; ++li) {
+        int x = lines[li].x0;
+        const int y0 = lines[li].y0;
+        for (int ci = 0; ci < lines[li].len; ++ci) {
+            int c = (int)lines[li].ch[ci] - first_char;
+            if (c < 0 || c >= nchars) c = '?' - first_char;
+            const int a = char_start[c], b = char_start[c + 1];
+            for (int p = a + threadIdx.x; p < b; p += blockDim.x) {
+                const int yy = y0 + dy[p], xx = x + dx[p];
+                if ((unsigned)yy < (unsigned)d.img_h && (unsigned)xx < (unsigned)d.img_w) {
+                    uint8_t* px = img + ((size_t)yy * d.img_w + xx) * 3;
+                    const uint8_t* t = tables + (size_t)lut[p] * 256;
+                    px[0] = t[px[0]]; px[1] = t[px[1]]; px[2] = t[px[2]];
+                }
+            }
+            x += advance[c];
+            __syncthreads();
+        }
+    }
+}
+
+// Parallel form: one CTA per (stream, line); every (glyph, pixel) of the line is an independent work item, except the
+// pixels a glyph shares with its predecessor (flagged pairs only): those are applied in a second phase, on top of
+// the predecessor's result.  Preconditions (checked on the host when the sprites are installed): the three lines
+// occupy disjoint rows and a glyph can only overlap its immediate neighbour.
+__global__ void __launch_bounds__(1024)
+k_text(uint8_t* out, LtDims d, const LtDevState* __restrict__ state, const int* __restrict__ draw, int print_frame_count,
+       const uint8_t* __restrict__ tables, const int* __restrict__ char_start, const short* __restrict__ dy,
+       const short* __restrict__ dx, const unsigned short* __restrict__ lut, const int* __restrict__ advance,
+       const unsigned char* __restrict__ pair_overlap, const unsigned long long* __restrict__ bitmaps, int nchars,
+       int first_char) {
+    const int s = blockIdx.x, li = blockIdx.y;
+    __shared__ TextLine lines[3];
+    __shared__ int nlines;
+    __shared__ int cx[56], cc[56], cstart[57], cflag[56];
+    __shared__ int s_start[130], s_adv[129];                       // glyph index tables (<= 128 glyphs), off the
+    const int ng = min(nchars, 128);                               // serial path of thread 0
+    for (int i = threadIdx.x; i <= ng; i += blockDim.x) s_start[i] = char_start[i];
+    for (int i = threadIdx.x; i < ng; i += blockDim.x) s_adv[i] = advance[i];
+    if (threadIdx.x == 0) nlines = format_lines(lines, state[s].s, draw[s], print_frame_count);
+    __syncthreads();
+    if (li >= nlines) return;
+    if (threadIdx.x == 0) {
+        int x = lines[li].x0, tot = 0;
+        for (int ci = 0; ci < lines[li].len; ++ci) {
+            int c = (int)lines[li].ch[ci] - first_char;
+            if (c < 0 || c >= ng) c = '?' - first_char;
+            cc[ci] = c; cx[ci] = x; cstart[ci] = tot;
+            tot += s_start[c + 1] - s_start[c];
+            x += s_adv[c];
+        }
+        cstart[lines[li].len] = tot;
+    }
+    __syncthreads();
+    for (int ci = threadIdx.x; ci < lines[li].len; ci += blockDim.x)
+        cflag[ci] = ci > 0 ? (int)pair_overlap[cc[ci - 1] * nchars + cc[ci]] : 0;
+    __syncthreads();
+    uint8_t* img = out + (size_t)s * d.img_w * d.img_h * 3;
+    const int nch = lines[li].len, y0 = lines[li].y0, total = cstart[nch];
+    for (int phase = 0; phase < 2; ++phase) {
+        for (int w = threadIdx.x; w < total; w += blockDim.x) {
+            int ci = 0;
+            while (cstart[ci + 1] <= w) ++ci;                              // <= 56 glyphs: linear search
+            const int c = cc[ci], p = s_start[c] + (w - cstart[ci]);
+            const int yy = y0 + dy[p], xx = cx[ci] + dx[p];
+            bool shared_px = false;
+            if (cflag[ci]) {                                                // is this pixel also in the previous glyph?
+                const int pc = cc[ci - 1], ry = dy[p] + 32, rx = xx - cx[ci - 1] + 8;      // 64x64 glyph bitmaps
+                if ((unsigned)ry < 64u && (unsigned)rx < 64u) shared_px = (bitmaps[pc * 64 + ry] >> rx) & 1ull;
+            }
+            if ((int)shared_px != phase) continue;
+            if ((unsigned)yy < (unsigned)d.img_h && (unsigned)xx < (unsigned)d.img_w) {
+                uint8_t* px = img + ((size_t)yy * d.img_w + xx) * 3;
+                const uint8_t* t = tables + (size_t)lut[p] * 256;
+                px[0] = t[px[0]]; px[1] = t[px[1]]; px[2] = t[px[2]];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+int lt_launch_text(lt_handle* h, uint8_t* d_out, int n, cudaStream_t st) {
+    if (!h->txt_tables || !d_out) return 0;
+    if (h->txt_parallel_lines && h->txt_pair_overlap && h->txt_bitmaps)
+        k_text<<<dim3(n, 3), 1024, 0, st>>>(d_out, h->d, h->state, h->draw_flags, h->cfg.print_frame_count, h->txt_tables,
+                                           h->txt_char_start, h->txt_dy, h->txt_dx, h->txt_lut, h->txt_advance,
+                                           h->txt_pair_overlap, h->txt_bitmaps, h->txt_nchars, h->txt_first);
+    else
+        k_text_seq<<<n, 128, 0, st>>>(d_out, h->d, h->state, h->draw_flags, h->cfg.print_frame_count, h->txt_tables,
+                                      h->txt_char_start, h->txt_dy, h->txt_dx, h->txt_lut, h->txt_advance, h->txt_nchars,
+                                      h->txt_first);
+    LT_LAUNCH_CHECK();
+    return 0;
+}

@@ -95,6 +95,11 @@ class BatchedLaneTracker:
         S = self.n_streams
         self._results_dev = torch.zeros(S * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
         self._results_host = torch.zeros(S * RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        from .text import TextSprites
+        self.text_enabled = False
+        self.text_rows = (0, 0)
+        if TextSprites.available():
+            self.set_text(True)
         geo = np.zeros(9, dtype=np.int32)
         check(self.lib.lt_debug_read(self._h, 10, 0, geo.ctypes.data_as(C.c_void_p), geo.nbytes))
         self.geometry = dict(roi_rows=(int(geo[0]), int(geo[1])), overlay_rows=(int(geo[2]), int(geo[3])),
@@ -133,6 +138,22 @@ class BatchedLaneTracker:
                 raise TypeError("unknown validity option %r" % k)
             setattr(v, k, float(val))
         check(self.lib.lt_set_validity(self._h, C.byref(v)))
+
+    def set_text(self, enable=True):
+        """Install (or remove) the glyph sprites of the reference's putText overlays (lane_tracker.py:653-659, 668-672)."""
+        from .text import TextSprites
+        if not enable:
+            check(self.lib.lt_set_text_sprites(self._h, None, 0, None, 0, None, None, None, 0, None, 0))
+            self.text_enabled = False
+            self.text_rows = (0, 0)
+            return
+        sp = TextSprites.load()
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(self.lib.lt_set_text_sprites(self._h, vp(sp.tables), int(sp.tables.shape[0]), vp(sp.char_start),
+                                           int(len(sp.advance)), vp(sp.dy), vp(sp.dx), vp(sp.lut), int(len(sp.dy)),
+                                           vp(sp.advance), sp.first_char))
+        self.text_enabled = True
+        self.text_rows = (max(0, 35 + int(sp.dy.min())), min(self.img_size[1], 105 + int(sp.dy.max()) + 1))
 
     def set_remap_mode(self, mode="exact"):
         """'exact': two-stage undistort + warp, bit-exact with OpenCV (default).  'fused': single resample from the
@@ -404,6 +425,7 @@ class HostPipeline:
         self.rows_in = (max(0, min(g['source_rows'][0], g['overlay_rows'][0]) - 2),
                         min(h_img, max(g['source_rows'][1], g['overlay_rows'][1]) + 2))
         self.rows_out = g['overlay_rows']
+        self.rows_text = tracker.text_rows if tracker.text_enabled else (0, 0)   # putText rows: read and rewritten
         self.params = params if params is not None else make_params()
         dev = tracker.device
         w, h = tracker.img_size
@@ -435,6 +457,9 @@ class HostPipeline:
             if self.inplace:
                 a, b = self.rows_in
                 self.t.copy_rows(sl["d_in"], host_frames, a, b, True)
+                ta, tb = self.rows_text
+                if tb > ta and not (ta >= a and tb <= b):
+                    self.t.copy_rows(sl["d_in"], host_frames, ta, min(tb, a) if ta < a else ta, True)
                 sl["frames"] = host_frames
             else:
                 sl["d_in"][:n].copy_(host_frames, non_blocking=True)
@@ -451,6 +476,9 @@ class HostPipeline:
                 a, b = self.rows_out
                 if b > a:
                     self.t.copy_rows(host_frames, sl["d_in"][:n], a, b, False)
+                ta, tb = self.rows_text
+                if tb > ta and not (ta >= a and tb <= b):
+                    self.t.copy_rows(host_frames, sl["d_in"][:n], ta, min(tb, a) if ta < a else ta, False)
             elif self.overlay:
                 sl["h_out"][:n].copy_(sl["d_out"][:n], non_blocking=True)
             sl["h_res"].copy_(sl["d_res"], non_blocking=True)
@@ -494,8 +522,8 @@ class LaneTracker:
     """Drop-in for the reference ``LaneTracker`` (same constructor, lane_tracker.py:101).
 
     NumPy arrays in, NumPy arrays out; every computation runs on the GPU.  Differences from the
-    reference, all documented in DESIGN.md: the putText overlays are not rendered, the caller's
-    ``img`` is never modified, and the debug views (``visualize_search``, ``split_view``) raise
+    reference, all documented in DESIGN.md: the caller's ``img`` is never modified (the reference
+    draws its text into it), and the debug views (``visualize_search``, ``split_view``) raise
     ``NotImplementedError``.
     """
 
@@ -705,9 +733,16 @@ class LaneTracker:
             print("x1_diff == {:.2f}, x2_diff == {:.2f}, x3_diff == {:.2f}, valid == {}".format(*diffs[0], valid[0]))
 
     def draw_lane(self, img):
-        """lane_tracker.py:629-662 (without putText): uses left_avg_x / right_avg_x."""
+        """lane_tracker.py:629-662: uses left_avg_x / right_avg_x, average_curve_radius, eccentricity."""
         w, h = self._bt.img_size
         bh = self._bt.warped_size[1]
+        if self._bt.text_enabled and self.average_curve_radius is not None and self.eccentricity is not None:
+            from .text import TextSprites, overlay_strings     # text goes onto the frame before the blend (:653-659)
+            img = np.array(img, copy=True)
+            sp = TextSprites.load()
+            for text, org in overlay_strings(True, self.average_curve_radius, self.eccentricity, self.counter,
+                                             self.print_frame_count):
+                sp.render(img, text, org)
         frames = self._upload(img, (h, w, 3)).unsqueeze(0)
         xs = np.zeros((1, 2, bh), dtype=np.int32)
         cnt = np.array([[len(self.left_avg_x), len(self.right_avg_x)]], dtype=np.int32)
@@ -718,5 +753,11 @@ class LaneTracker:
         return out[0].cpu().numpy()
 
     def print_failure(self, img):
-        """lane_tracker.py:664-673 without the putText overlay: the frame is returned unchanged."""
-        return np.array(img, copy=True)
+        """lane_tracker.py:664-673: the failure message (and frame number) on a copy of the frame."""
+        from .text import TextSprites, overlay_strings
+        out = np.array(img, copy=True)
+        if self._bt.text_enabled:
+            sp = TextSprites.load()
+            for text, org in overlay_strings(False, None, None, self.counter, self.print_frame_count):
+                sp.render(out, text, org)
+        return out

@@ -8,9 +8,11 @@ from ``oracle.cvops`` (NumPy restatements, default) or, with ``backend='cv2'``,
 from the same cv2 calls the reference makes (used for the timed CPU baseline,
 where the NumPy restatements would be an unfairly slow stand-in).
 
-Not restated: ``cv2.putText`` overlays (lane_tracker.py:653-659, 668-672) and
-the debug views (675-793).  Parity checks on output frames therefore exclude
-the text box (rows 0..110, cols 0..620).
+``cv2.putText`` overlays (lane_tracker.py:653-659, 668-672): drawn with cv2 itself under
+``backend='cv2'`` and with the glyph sprites of ``lane_tracker_b200/data`` (generated from, and checked
+bit-for-bit against, cv2.putText by tools/make_text_sprites.py) under ``backend='numpy'``;
+``render_text=False`` skips them.  Unlike the reference the caller's frame is not modified.
+Not restated: the debug views (675-793).
 """
 from __future__ import annotations
 
@@ -66,7 +68,7 @@ class OracleLaneTracker:
 
     def __init__(self, img_size, warped_size, cam_matrix, dist_coeffs, warp_matrices,
                  mpp_conversion, n_fail=8, n_reset=4, n_average=2, print_frame_count=False,
-                 backend="numpy"):
+                 backend="numpy", render_text=True):
         self.img_size = tuple(img_size)
         self.warped_size = tuple(warped_size)
         self.cam_matrix = np.asarray(cam_matrix, dtype=np.float64)
@@ -77,6 +79,8 @@ class OracleLaneTracker:
         self.n_fail, self.n_reset, self.n_average = n_fail, n_reset, n_average
         self.print_frame_count = print_frame_count
         self.backend = backend
+        self.render_text = render_text
+        self._sprites = None
         self.validity = dict(VALIDITY)    # per-instance copy: tests may install the other documented windows
         if backend == "cv2":
             import cv2  # noqa: F401  (third-party kernel library of the reference)
@@ -354,13 +358,32 @@ class OracleLaneTracker:
         mid = int(self.warped_size[0] / 2)
         self.eccentricity = (((mid - self.left_avg_x[-1]) - (self.right_avg_x[-1] - mid)) / 2) * self.mpph
 
+    def _put_text(self, img, drew_lane):
+        """The putText calls of draw_lane (:653-659) / print_failure (:668-672), on a copy of the frame."""
+        if not self.render_text:
+            return img
+        from lane_tracker_b200.text import TextSprites, overlay_strings
+        img = img.copy()
+        for text, org in overlay_strings(drew_lane, self.average_curve_radius, self.eccentricity, self.counter,
+                                         self.print_frame_count):
+            if self.backend == "cv2":
+                cv2 = self._cv2
+                cv2.putText(img, text, org, cv2.FONT_HERSHEY_SIMPLEX, fontScale=1, color=(255, 255, 255),
+                            thickness=2, lineType=cv2.LINE_AA)
+            else:
+                if self._sprites is None:
+                    self._sprites = TextSprites.load()
+                self._sprites.render(img, text, org)
+        return img
+
     def draw_lane(self, img):
-        """lane_tracker.py:629-662 without the putText overlays."""
+        """lane_tracker.py:629-662."""
         Wd, Hh = self.warped_size
         lo, hi = cvops.lane_polygon_rows(self.left_avg_x, self.left_avg_y, self.right_avg_x,
                                          self.right_avg_y, Wd, Hh)
         self.trace["lane_rows"] = (lo, hi)
         canvas = cvops.lane_canvas(lo, hi, Wd, Hh)
+        img = self._put_text(img, True)
         if self.backend == "cv2":
             cv2 = self._cv2
             unwarped = cv2.warpPerspective(canvas, self.Minv, (img.shape[1], img.shape[0]))
@@ -369,8 +392,8 @@ class OracleLaneTracker:
         return cvops.add_weighted_03(img, unwarped)
 
     def print_failure(self, img):
-        """lane_tracker.py:664-673 without the putText overlay."""
-        return img
+        """lane_tracker.py:664-673."""
+        return self._put_text(img, False)
 
     # -------------------------------------------------------------- process
     def find_lane_points(self, img, **kw):

@@ -31,7 +31,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import _liveref  # noqa: E402
 from lane_tracker_b200 import synth  # noqa: E402
 
-TEXT_BOX = (111, 620)  # rows, cols blanked before hashing output frames (putText is not restated)
+TEXT_BOX = (111, 620)  # rows, cols blanked for the legacy 'out' digests; 'out_full' digests cover the whole frame
 
 
 def sha(a):
@@ -119,6 +119,7 @@ def main():
         ref = _liveref.make_tracker()
         out = _liveref.quiet(ref.process, frame.copy())
         rec["process_out"] = out_digest(out)
+        rec["process_out_full"] = sha(out)
         rec["process_state"] = state_record(ref)
         gold["images"][name] = rec
         print(name, rec["mask_counts"], rec["process_state"]["valid"])
@@ -131,7 +132,7 @@ def main():
         kind = "outage" if 14 <= t < 26 else "synth"
         frame = outage if kind == "outage" else vid.frame(t)
         out = _liveref.quiet(ref.process, frame.copy())
-        rec = dict(t=t, kind=kind, frame=sha(frame), out=out_digest(out), state=state_record(ref))
+        rec = dict(t=t, kind=kind, frame=sha(frame), out=out_digest(out), out_full=sha(out), state=state_record(ref))
         seq.append(rec)
         print(t, kind, rec["state"]["valid"], rec["state"]["last_detection"], rec["state"]["radius"])
     gold["scenario"] = dict(seed=0, frames=seq, outage_frame="test2.jpg", outage=[14, 26])

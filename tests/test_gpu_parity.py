@@ -238,7 +238,7 @@ def test_check_validity_and_poly_points(bt):
 
 def test_draw_lane_overlay(bt, torch_mod, frames_np):
     rng = np.random.default_rng(9)
-    o = OracleLaneTracker(**CAL)
+    o = OracleLaneTracker(**CAL, render_text=False)      # lt_draw_lane is the polygon + un-warp + blend stage only
     for t in range(6):
         a = rng.normal(0, 3e-4) * (4 if t % 2 else 1); b = rng.normal(0, 0.4); c = rng.uniform(150, 600)
         lf = np.array([a, b - 2 * a * 1099, a * 1099 ** 2 - b * 1099 + c])
@@ -296,6 +296,7 @@ def test_process_scenario_matches_reference_golden(torch_mod):
         st, lx, rx = lt._bt.get_state(0)
         _check_result_against_golden(lt.last_result, w, st, lx, rx)
         assert fx.out_digest(out) == rec["out"], rec["t"]
+        assert fx.sha(out) == rec["out_full"], rec["t"]      # whole frame, putText overlays included
         if w["pix"] is not None:
             assert fx.pix_digest(lt.left_y, lt.left_x, lt.right_y, lt.right_x) == w["pix"], rec["t"]
     r = lt.get_success_ratio()
@@ -318,6 +319,7 @@ def test_process_bundled_frames_match_reference_golden(torch_mod):
         assert fx.sha(frames[i]) == g["frame"]
         assert int(res[i]["attempts"]) == 2 and not res[i]["valid_lane_lines"]
         assert fx.out_digest(out[i]) == g["process_out"], n
+        assert fx.sha(out[i]) == g["process_out_full"], n
         assert fx.sha(bt11.debug_read("mask", i)) == g["mask_neighborhood"], n
         for attempt, key in ((0, "sws_bilateral"), (1, "sws_neighborhood")):
             w = g[key]
@@ -695,3 +697,19 @@ def test_abi_error_paths_partial_batches_and_lifetime(torch_mod):
     torch_mod.cuda.synchronize()
     assert abs(torch_mod.cuda.mem_get_info()[0] - free1) < 16 << 20
     assert free0 > 0
+
+
+def test_dropin_stage_methods_with_text(torch_mod, frames_np):
+    """draw_lane / print_failure of the drop-in class include the reference's text overlays."""
+    from lane_tracker_b200 import LaneTracker
+    lt = LaneTracker(**CAL, print_frame_count=True)
+    o = OracleLaneTracker(**CAL, print_frame_count=True, backend="cv2")
+    vid = synth.RoadVideo(3)
+    for t in range(2):
+        a, b = lt.process(vid.frame(t)), o.process(vid.frame(t))
+        assert _mism(a, b) == 0
+    frame = frames_np[0]
+    assert _mism(lt.draw_lane(frame), o.draw_lane(frame.copy())) == 0
+    assert _mism(lt.print_failure(frame), o.print_failure(frame.copy())) == 0
+    ly, lx, ry, rx = lt.get_poly_points(lt.left_avg_coeffs, lt.right_avg_coeffs, 1.0)
+    assert np.array_equal(lx, o.left_avg_x) and np.array_equal(ry, o.right_avg_y)

@@ -74,6 +74,7 @@ def test_bundled_frames_process(name):
     t = OracleLaneTracker(**CAL)
     out = t.process(fx.load_frame(name))
     assert fx.out_digest(out) == want["process_out"]
+    assert fx.sha(out) == want["process_out_full"]          # including the putText overlays
     _state_matches(t, want["process_state"])
 
 
@@ -89,6 +90,7 @@ def test_scenario_sequence():
         assert fx.sha(frame) == rec["frame"], "synthetic generator is not deterministic"
         out = t.process(frame.copy())
         assert fx.out_digest(out) == rec["out"], rec["t"]
+        assert fx.sha(out) == rec["out_full"], rec["t"]
         _state_matches(t, rec["state"])
     r = t.get_success_ratio()
     assert [float(r[0]), int(r[1]), int(r[2])] == sc["success_ratio"]
@@ -103,4 +105,5 @@ def test_scenario_prefix_numpy_backend():
     for rec in sc["frames"][:4]:
         out = t.process(vid.frame(rec["t"]))
         assert fx.out_digest(out) == rec["out"], rec["t"]
+        assert fx.sha(out) == rec["out_full"], rec["t"]      # text drawn from the glyph sprites
         _state_matches(t, rec["state"])
