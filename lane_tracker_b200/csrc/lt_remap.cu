@@ -240,6 +240,14 @@ k_warp_planes(const uchar4* __restrict__ und_all, const int2* __restrict__ desc,
             int2 q = __ldg(&desc[(size_t)y * d.bv_w + px]);
             const uint32_t* base = und + q.x;
             const uint32_t f = (uint32_t)q.y;
+            if (!(f >> 10)) {                          // no tap inside the frame: the pixel is black, Lab b of black = 128
+                b2 |= 128u << (16 * half);
+                if (bv_rgb) {
+                    uint8_t* p = bv_rgb + (((size_t)s * d.bv_h + y) * d.bv_w + px) * 3;
+                    p[0] = 0; p[1] = 0; p[2] = 0;
+                }
+                continue;
+            }
             uint32_t t00 = (f & (1u << 10)) ? __ldg(base) : 0u;               // BORDER_CONSTANT 0
             uint32_t t01 = (f & (1u << 11)) ? __ldg(base + 1) : 0u;
             uint32_t t10 = (f & (1u << 12)) ? __ldg(base + d.img_w) : 0u;
@@ -429,9 +437,15 @@ k_overlay(const uint8_t* frames, uint8_t* out, const int2* __restrict__ map,
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             Tap4 t = make_taps(__ldg(&map[(size_t)y * d.img_w + q * 4 + k]));
-            int v = lane_tap(rows, d, t.sy, t.sx) * t.w00 + lane_tap(rows, d, t.sy, t.sx + 1) * t.w01 +
-                    lane_tap(rows, d, t.sy + 1, t.sx) * t.w10 + lane_tap(rows, d, t.sy + 1, t.sx + 1) * t.w11;
-            v = (v + 512) >> 10;
+            // the two taps of a canvas row share its [lo, hi] span: two span loads instead of four
+            const int2 none = make_int2(1, 0);
+            const int2 s0 = ((unsigned)t.sy < (unsigned)d.bv_h) ? __ldg(&rows[t.sy]) : none;
+            const int2 s1 = ((unsigned)(t.sy + 1) < (unsigned)d.bv_h) ? __ldg(&rows[t.sy + 1]) : none;
+            const int xa = t.sx, xb = t.sx + 1;
+            const bool ina = (unsigned)xa < (unsigned)d.bv_w, inb = (unsigned)xb < (unsigned)d.bv_w;
+            int v = ((ina && xa >= s0.x && xa <= s0.y) ? t.w00 : 0) + ((inb && xb >= s0.x && xb <= s0.y) ? t.w01 : 0) +
+                    ((ina && xa >= s1.x && xa <= s1.y) ? t.w10 : 0) + ((inb && xb >= s1.x && xb <= s1.y) ? t.w11 : 0);
+            v = (v * 255 + 512) >> 10;
             if (v) {
                 // cv2.addWeighted(img,1,lane,0.3,0): float32 a + b*0.3f, round half to even, saturate
                 float f = __fadd_rn((float)gch[k], __fmul_rn((float)v, 0.3f));
