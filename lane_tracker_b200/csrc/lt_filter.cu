@@ -77,25 +77,6 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-// One staged element: packed pixel pair at plane row r, packed column gx (may lie outside the plane).
-template <bool IS_MAX>
-__device__ __forceinline__ uint32_t stage_elem(const uint32_t* __restrict__ src, const LtDims& d, int r, int gx) {
-    constexpr uint32_t PADL = IS_MAX ? 0u : 0xFFFFu;
-    constexpr uint32_t PAD2 = PADL | (PADL << 16);
-    if ((unsigned)r >= (unsigned)d.bv_h) return PAD2;
-    const uint32_t* row = src + (size_t)r * d.p2;
-    if (gx >= 0 && gx + d.p2 < d.bv_w) return __ldg(&row[gx]);        // interior: both lanes real pixels
-    uint32_t lo = PADL, hi = PADL;
-    if (gx < 0) {
-        if (gx + d.p2 >= 0) hi = __ldg(&row[gx + d.p2]) & 0xFFFFu;     // image col gx+p2 lives in the low strip
-    } else if (gx < d.p2) {
-        lo = __ldg(&row[gx]) & 0xFFFFu;                               // hi lane: col >= bv_w -> outside
-    } else {
-        if (gx < d.bv_w && gx - d.p2 < d.p2) lo = __ldg(&row[gx - d.p2]) >> 16;   // image col gx lives in the high strip
-    }
-    return lo | (hi << 16);
-}
-
 template <int K, bool IS_MAX, bool TOPHAT>
 __device__ __forceinline__ void
 morph_body(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const uint32_t* __restrict__ orig,

@@ -538,7 +538,6 @@ int lt_launch_search(lt_handle* h, int n, const LtAttemptParams& p, const LtSear
 __global__ void k_select_retry(const LtAttemptOut* __restrict__ att, int n, int n_tries, int* list, int* count,
                                int* flags) {
     // single CTA, ordered compaction so that the retry list is deterministic
-    __shared__ int cnt;
     if (threadIdx.x == 0) {
         int c = 0;
         for (int s = 0; s < n; ++s) {
@@ -546,7 +545,6 @@ __global__ void k_select_retry(const LtAttemptOut* __restrict__ att, int n, int 
             flags[s] = retry;
             if (retry) list[c++] = s;
         }
-        cnt = c;
         *count = c;
     }
 }
