@@ -3,6 +3,9 @@
 #include <stdarg.h>
 #include <string.h>
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 #include "lt_common.cuh"
 #include "lab_tables.inc"
@@ -17,6 +20,21 @@ void lt_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 void lt_count_launch(int n) { g_launches += n; }
+
+int lt_ensure_smem(const void* func, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> granted;
+    if (bytes <= 48 * 1024) return 0;
+    int dev = 0;
+    LT_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = granted[std::make_pair(dev, func)];
+    if (bytes > cur) {
+        LT_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cur = bytes;
+    }
+    return 0;
+}
 
 extern "C" const char* lt_last_error(void) { return g_err; }
 extern "C" int lt_abi_version(void) { return LT_ABI_VERSION; }

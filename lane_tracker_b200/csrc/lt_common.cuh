@@ -50,6 +50,7 @@ struct lt_handle {
     LtDims d;
     int S;                       // max streams
     lt_validity val;             // check_validity windows
+    int bands_key[3], bands_val[2];   // cached band split of the paired morphology launch (n, height, slots)
     int sm_count;
     int src0, src1;              // frame rows the undistort of the ROI reads: [src0, src1)
     // shared tables
@@ -95,6 +96,9 @@ struct lt_handle {
 extern "C" int64_t lt_launch_count(void);
 void lt_count_launch(int n = 1);
 void lt_set_error(const char* fmt, ...);
+// Raise the dynamic shared-memory limit of kernel `func` on the CURRENT device if `bytes` exceeds what this process
+// has already requested there (per device: handles may live on different GPUs of one process). Thread-safe.
+int lt_ensure_smem(const void* func, size_t bytes);
 
 #define LT_CUDA(call)                                                                 \
     do {                                                                              \

@@ -318,9 +318,9 @@ k_morph_pair(MorphJob j55, MorphJob j29, LtDims d, int tiles, int n, size_t stre
 
 // Pick the band counts of the two jobs by simulating list scheduling of the combined grid on `slots` CTA slots.
 // Per-row costs are the measured relative walk costs of the two structuring elements (profiles/, round 1).
-static void choose_bands(int n, int tiles, int H, int slots, int* b55, int* b29) {
-    static int cache_n = -1, cache_h = -1, cache_slots = -1, c55 = 1, c29 = 1;
-    if (n == cache_n && H == cache_h && slots == cache_slots) { *b55 = c55; *b29 = c29; return; }
+static void choose_bands(lt_handle* h, int n, int tiles, int H, int slots, int* b55, int* b29) {
+    if (h->bands_key[0] == n && h->bands_key[1] == H && h->bands_key[2] == slots) { *b55 = h->bands_val[0]; *b29 = h->bands_val[1]; return; }
+    int c55 = 1, c29 = 1;
     double best = 1e300;
     std::vector<double> freeat;
     for (int a = 1; a <= 24; ++a)
@@ -341,7 +341,8 @@ static void choose_bands(int n, int tiles, int H, int slots, int* b55, int* b29)
             }
             if (makespan < best - 1e-9) { best = makespan; c55 = a; c29 = b; }
         }
-    cache_n = n; cache_h = H; cache_slots = slots;
+    h->bands_key[0] = n; h->bands_key[1] = H; h->bands_key[2] = slots;
+    h->bands_val[0] = c55; h->bands_val[1] = c29;
     *b55 = c55; *b29 = c29;
 }
 
@@ -350,16 +351,13 @@ static int launch_morph_pair(lt_handle* h, MorphJob j55, MorphJob j29, int n, co
                              cudaStream_t st) {
     size_t smem = morph_smem_bytes<55>(TOPHAT) > morph_smem_bytes<29>(TOPHAT) ? morph_smem_bytes<55>(TOPHAT)
                                                                                : morph_smem_bytes<29>(TOPHAT);
-    static bool attr_done = false;
-    if (!attr_done) {
-        LT_CUDA(cudaFuncSetAttribute(k_morph_pair<IS_MAX, TOPHAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    int rc = lt_ensure_smem((const void*)k_morph_pair<IS_MAX, TOPHAT>, smem);
+    if (rc) return rc;
     const LtDims& d = h->d;
     const int tiles = lt_div_up(d.p2, MORPH_TW);
     const int slots = MORPH_CTAS_PER_SM * (h->sm_count > 0 ? h->sm_count : 148);
     int b55, b29;
-    choose_bands(n, tiles, d.bv_h, slots, &b55, &b29);
+    choose_bands(h, n, tiles, d.bv_h, slots, &b55, &b29);
     j55.band_rows = lt_div_up(d.bv_h, b55); j55.bands = lt_div_up(d.bv_h, j55.band_rows);
     j29.band_rows = lt_div_up(d.bv_h, b29); j29.bands = lt_div_up(d.bv_h, j29.band_rows);
     const int grid = n * tiles * (j55.bands + j29.bands);
@@ -837,11 +835,8 @@ static int launch_cross(lt_handle* h, const uint32_t* plane, uint32_t* bits, int
         int pitch = d.p2 + 2 * k + 2;
         while (((pitch >> 1) & 1) == 0 || (pitch & 1)) ++pitch;       // pitch = 2 * odd: rows land in distinct banks
         size_t smem = (size_t)CROSSH_ROWS * pitch * sizeof(unsigned short);
-        static size_t cur = 0;
-        if (smem > cur && smem > 48 * 1024) {
-            LT_CUDA(cudaFuncSetAttribute(k_cross_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            cur = smem;
-        }
+        int rc = lt_ensure_smem((const void*)k_cross_h, smem);
+        if (rc) return rc;
         dim3 gh(lt_div_up(d.bv_h, CROSSH_ROWS), n);
         k_cross_h<<<gh, CROSSH_WARPS * 32, smem, st>>>(plane, bits, d, k, C, accumulate, pitch, h->stream_plane,
                                                          h->stream_mask, list, count);
@@ -849,11 +844,8 @@ static int launch_cross(lt_handle* h, const uint32_t* plane, uint32_t* bits, int
     } else {
         int wpad = (d.bv_w + 32) & ~31;
         size_t smem = (size_t)ROWK_WARPS * 2 * wpad * sizeof(uint32_t);
-        static size_t cur = 0;
-        if (smem > cur && smem > 48 * 1024) {
-            LT_CUDA(cudaFuncSetAttribute(k_cross_h_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            cur = smem;
-        }
+        int rc = lt_ensure_smem((const void*)k_cross_h_wide, smem);
+        if (rc) return rc;
         dim3 gh(lt_div_up(d.bv_h, ROWK_WARPS), n);
         k_cross_h_wide<<<gh, ROWK_WARPS * 32, smem, st>>>(plane, bits, d, k, C, accumulate, h->stream_plane,
                                                             h->stream_mask, list, count);
@@ -874,11 +866,7 @@ static int launch_box(lt_handle* h, const uint32_t* plane, uint32_t* hs, uint32_
     const LtDims& d = h->d;
     int wpad = (d.bv_w + 32) & ~31;
     size_t smem = (size_t)ROWK_WARPS * 2 * wpad * sizeof(uint32_t);
-    static size_t cur = 0;
-    if (smem > cur && smem > 48 * 1024) {
-        LT_CUDA(cudaFuncSetAttribute(k_box_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cur = smem;
-    }
+    { int rc = lt_ensure_smem((const void*)k_box_h, smem); if (rc) return rc; }
     int half = block / 2;
     const int zs = list ? (n < 8 ? n : 8) : n;      // retry-list launches: few slots, each CTA loops over the list
     dim3 gh(lt_div_up(d.bv_h, ROWK_WARPS), zs);

@@ -520,11 +520,7 @@ static size_t search_smem(const LtDims& d) { return (size_t)(10 * d.bv_h + d.bv_
 int lt_launch_search(lt_handle* h, int n, const LtAttemptParams& p, const LtSearchArgs& a, const int* list,
                      const int* count, cudaStream_t st) {
     size_t smem = search_smem(h->d);
-    static size_t cur = 0;
-    if (smem > cur) {
-        LT_CUDA(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cur = smem;
-    }
+    { int rc = lt_ensure_smem((const void*)k_search, smem); if (rc) return rc; }
     if (p.window_width < 1 || p.window_height < 1) { lt_set_error("window size must be positive"); return -1; }
     k_search<<<n, SEARCH_THREADS, smem, st>>>(h->d, p, a, h->state, h->cfg.n_reset, h->val, h->stream_mask, list, count);
     LT_LAUNCH_CHECK();

@@ -713,3 +713,22 @@ def test_dropin_stage_methods_with_text(torch_mod, frames_np):
     assert _mism(lt.print_failure(frame), o.print_failure(frame.copy())) == 0
     ly, lx, ry, rx = lt.get_poly_points(lt.left_avg_coeffs, lt.right_avg_coeffs, 1.0)
     assert np.array_equal(lx, o.left_avg_x) and np.array_equal(ry, o.right_avg_y)
+
+
+def test_two_devices_in_one_process(torch_mod):
+    """Handles on different GPUs of one process (per-device kernel attributes, no shared state)."""
+    if torch_mod.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from lane_tracker_b200 import BatchedLaneTracker
+    vid = synth.RoadVideo(50)
+    frames = np.stack([vid.frame(t) for t in range(2)])
+    outs = []
+    for dev in (1, 0):
+        with torch_mod.cuda.device(dev):
+            b = BatchedLaneTracker(2, **CAL, device=dev)
+            d = torch_mod.as_tensor(frames).to("cuda:%d" % dev)
+            out = torch_mod.empty_like(d)
+            res = b.process(d, out)
+            outs.append((out.cpu().numpy(), res.copy()))
+            b.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1].tobytes() == outs[1][1].tobytes()
