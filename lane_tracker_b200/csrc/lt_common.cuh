@@ -23,7 +23,15 @@ struct LtDims {
     int mwords;    // mask words per row = 2*p2/32
     int roi0, roi1;   // undistorted rows materialised: [roi0, roi1)
     int ov0, ov1;     // frame rows whose overlay taps can hit the bird's-eye view: [ov0, ov1)
+    int pp;           // row pitch of the PADDED pair planes (morphology inputs) = p2 + 2*LT_HALO_X
 };
+
+// Padded pair planes (planeR/planeB/tmpR/tmpB): every row carries LT_HALO_X extra entries on either side that hold
+// the seam-stitched neighbour columns (the two strips of a pair plane are adjacent in the image) or the pad value
+// of the morphological pass that reads the plane, and every stream carries LT_HALO_Y pad rows above and below.
+// The plane pointers in lt_handle address (stream 0, row 0, column 0); negative offsets reach the halo.
+constexpr int LT_HALO_X = 32;     // multiple of 4 (16-byte staging) >= 28
+constexpr int LT_HALO_Y = 36;     // >= 27 + MORPH_RB - 1
 
 // Per-stream tracking state on the device (lane_tracker.py:139-176).
 struct LtDevState {
@@ -64,9 +72,10 @@ struct lt_handle {
     unsigned short* lab_cbrt;    // [3072]
     // per-stream buffers
     uchar4* und_roi;             // [S][roi rows][img_w]
-    uint32_t* planeR; uint32_t* planeB;     // [S][bv_h][p2]
-    uint32_t* tmpR;   uint32_t* tmpB;       // eroded planes / box row sums
-    uint32_t* topR;   uint32_t* topB;       // top-hat planes
+    uint32_t* planeR; uint32_t* planeB;     // padded [S][bv_h + 2*LT_HALO_Y][pp]; lanes beyond the image / halo: 0xFFFF
+    uint32_t* tmpR;   uint32_t* tmpB;       // padded eroded planes; lanes beyond the image / halo: 0
+    uint32_t* pad_alloc[4];                 // the allocations behind the four padded planes
+    uint32_t* topR;   uint32_t* topB;       // [S][bv_h][p2] top-hat planes / box row sums
     uint32_t* merged; uint32_t* mask;       // [S][bv_h][mwords]
     uint32_t* pixels;            // [S][2][pix_cap]
     int pix_cap;
@@ -89,7 +98,8 @@ struct lt_handle {
     unsigned char* txt_pair_overlap;   // [nchars][nchars]: glyph b drawn right after glyph a shares pixels with it
     cudaEvent_t* prof_ev; int* prof_stage; int prof_cap, prof_n, prof_active, prof_calls, prof_max_calls;
     uint8_t* scratch_bv;         // lazily allocated [S][bv_h][bv_w][3] for stage calls
-    size_t stream_plane;         // entries per stream in a pair plane
+    size_t stream_plane;         // entries per stream in a plain pair plane
+    size_t stream_pad;           // entries per stream in a padded pair plane
     size_t stream_mask;          // words per stream in a bit mask
 };
 
@@ -137,7 +147,7 @@ int lt_launch_filter(lt_handle* h, int n, const LtAttemptParams& p, const int* l
                      cudaStream_t st);
 int lt_launch_mask_to_u8(lt_handle* h, const uint32_t* bits, uint8_t* d_mask, int n, cudaStream_t st);
 int lt_launch_u8_to_mask(lt_handle* h, const uint8_t* d_mask, uint32_t* bits, int n, cudaStream_t st);
-int lt_launch_plane_to_u8(lt_handle* h, const uint32_t* plane, uint8_t* d_dst, int n, cudaStream_t st);
+int lt_launch_plane_to_u8(lt_handle* h, const uint32_t* plane, int pitch, uint8_t* d_dst, int n, cudaStream_t st);
 
 struct LtSearchArgs {
     const uint32_t* mask;        // [n][bv_h][mwords]

@@ -74,120 +74,96 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+// Morphology inputs live in PADDED planes (LtPlane with halo): 32 extra columns on either side of a row hold the
+// seam-stitched neighbours (the two image strips are adjacent in the image) or the operation's pad value, and 36
+// extra rows above and below hold the pad value.  Staging a row block is therefore a plain 16-byte cp.async copy:
+// no bounds checks, no lane fix-up, no registers held across the walk.
+template <int K> struct MorphHa { static constexpr int value = (Ellipse<K>::R + 3) & ~3; };    // staged halo columns per side
+
 template <int K, bool IS_MAX, bool TOPHAT>
 __device__ __forceinline__ void
-morph_body(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const uint32_t* __restrict__ orig,
-           const LtDims& d, int band_rows, int tile, int band) {
-    // Shared-memory tables hold ROW PAIRS: element (pair m, column c) is a uint2 {row 2m, row 2m+1}.  Every table
-    // access is one LDS.64/STS.64 serving two source rows, and the vertical pipeline advances two rows per step
-    // with a single three-input VIMNMX3 per accumulator:
+morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict__ dst, int dst_pitch, bool dst_padded,
+           const uint32_t* __restrict__ orig, int orig_pitch, const LtDims& d, int band_rows, int tile, int band) {
+    // Shared-memory window tables hold ROW PAIRS: element (pair m, column c) is a uint2 {row 2m, row 2m+1}.  Every
+    // table access is one LDS.64/STS.64 serving two source rows, and the vertical pipeline advances two rows per
+    // step with a single three-input VIMNMX3 per accumulator:
     //     A[j] <- op3(A[j+2], H_a[hw(j+1)], H_b[hw(j)])        (a, b = the two rows of the pair)
     using E = Ellipse<K>;
     constexpr int R = E::R;
-    constexpr int TW = MORPH_TW, RB = MORPH_RB, RP = RB / 2;
-    constexpr int TE = TW + 2 * R;          // staged columns per row
+    constexpr int TW = MORPH_TW, RB = MORPH_RB, RP = RB / 2, HA = MorphHa<K>::value;
+    constexpr int TE = TW + 2 * HA;         // staged columns per row; column i <-> packed column x0 - HA + i
     constexpr int TEA = TE + 32;            // + slack that always holds PAD
     constexpr bool HAS32 = (2 * R + 1) >= 32;
-    constexpr int NTAB = HAS32 ? 5 : 4;
+    constexpr int NTAB = HAS32 ? 4 : 3;     // T4, T8, T16 (, T32)
     constexpr uint32_t PADL = IS_MAX ? 0u : 0xFFFFu;
     constexpr uint32_t PAD2 = PADL | (PADL << 16);
+    constexpr uint32_t PAD_NEXT = 0u;       // lane pad of the pass that reads a padded dst (dilation after erosion)
+    static_assert(HA >= R && HA <= LT_HALO_X && R + RB - 1 <= LT_HALO_Y && HA % 4 == 0 && TE % 4 == 0, "staging must be 16-byte granular");
 
     extern __shared__ uint32_t smem[];
-    uint2* T0 = reinterpret_cast<uint2*>(smem);
-    uint2* T4 = T0 + RP * TEA;
+    uint2* T4 = reinterpret_cast<uint2*>(smem);
     uint2* T8 = T4 + RP * TEA;
     uint2* T16 = T8 + RP * TEA;
-    uint2* T32 = T16 + RP * TEA;      // only touched when HAS32
-    uint2* S = T0 + NTAB * RP * TEA;  // [RP][TE]   raw words of the next row block, filled by cp.async
-    uint2* OG = S + RP * TE;          // [2][RP][TW] original-plane rows for the top-hat epilogue (double buffered)
+    uint2* T32 = T16 + RP * TEA;                        // only touched when HAS32
+    uint32_t* T0 = smem + 2 * NTAB * RP * TEA;          // [2 buffers][RB rows][TE] raw source rows (row-major)
+    uint32_t* OG = T0 + 2 * RB * TE;                    // [2 buffers][RB rows][TW] original rows (top-hat epilogue)
 
     const int tid = threadIdx.x;
     const int x0 = tile * TW;
     const int yb0 = band * band_rows;
     const int yb1 = min(yb0 + band_rows, d.bv_h);
 
-    for (int i = tid; i < NTAB * RB * TEA; i += TW) smem[i] = PAD2;
+    for (int i = tid; i < 2 * NTAB * RP * TEA; i += TW) smem[i] = PAD2;      // table slack must read as PAD
 
     const int r_begin = yb0 - R;
     const int r_end = yb1 + R;      // exclusive
     const int nblk = (r_end - r_begin + RB - 1) / RB;
-    const int xint = d.bv_w - d.p2; // packed columns < xint carry two real pixels
 
-    // How to fetch packed column gx of a plane row: columns outside [0, p2) borrow the neighbouring strip's
-    // lane (the two strips are adjacent in the image) or the pad value.
-    struct ColDesc { int off; uint32_t sel; };
-    auto describe = [&](int i) -> ColDesc {
-        const int gx = x0 + i - R;
-        ColDesc c;
-        c.off = gx;
-        c.sel = 0x3210u;                                                    // both lanes from the loaded entry
-        if (gx < 0) { c.off = gx + d.p2; c.sel = 0x1054u; }                 // hi <- entry.lo, lo <- pad
-        else if (gx >= d.p2) { c.off = gx - d.p2; c.sel = (gx < d.bv_w) ? 0x5432u : 0x5454u; }   // lo <- entry.hi
-        else if (gx >= xint) c.sel = 0x5410u;                               // lo real, hi beyond the image
-        c.off = max(0, min(c.off, d.p2 - 1));
-        return c;
-    };
-    // Staging is asynchronous (cp.async straight into shared memory, no registers held across the walk); the
-    // raw words get their lane selection / padding (one PRMT) when the block is published into T0.
-    auto finish = [&](uint32_t raw, int r, const ColDesc& c) -> uint32_t {
-        return ((unsigned)r < (unsigned)d.bv_h) ? __byte_perm(raw, PAD2, c.sel) : PAD2;
-    };
-    // Work split of a row block: every thread owns table column `tid` of all RP row pairs; the 2R halo columns
-    // of the RP pairs (NX pair-elements) go to the first NX threads.
-    constexpr int NX = 2 * R * RP;
-    constexpr int NXT = (NX + TW - 1) / TW;         // halo pair-elements per thread (1 or 2)
-    const ColDesc cmain = describe(tid);
-    bool xok[NXT];
-    int xpair[NXT], xidx[NXT], xsidx[NXT];
-    ColDesc cx[NXT];
-#pragma unroll
-    for (int q = 0; q < NXT; ++q) {
-        const int e = tid + q * TW;
-        xok[q] = e < NX;
-        xpair[q] = xok[q] ? e / (2 * R) : 0;
-        const int xcol = TW + (xok[q] ? e - xpair[q] * 2 * R : 0);
-        xidx[q] = xpair[q] * TEA + xcol;
-        xsidx[q] = xpair[q] * TE + xcol;
-        cx[q] = describe(xcol);
-    }
     const int gx = x0 + tid;                       // this thread's packed column
     const bool col_ok = gx < d.p2;
     const uint32_t lane_mask = (gx + d.p2 < d.bv_w) ? 0xFFFFFFFFu : 0x0000FFFFu;
 
+    // stage rows [rbase, rbase + RB) x columns [x0 - HA, x0 + TW + HA) (and the original rows of the outputs the
+    // block completes) with 16-byte cp.async; halo columns / pad rows of the padded planes make every address valid
     auto stage_async = [&](int rbase, int buf) {
-        uint32_t* Sw = reinterpret_cast<uint32_t*>(S);
-#pragma unroll
-        for (int rr = 0; rr < RB; ++rr) {
-            const int r = rbase + rr;
-            if ((unsigned)r < (unsigned)d.bv_h)
-                cp_async4(&Sw[2 * ((rr >> 1) * TE + tid) + (rr & 1)], &src[(size_t)r * d.p2 + cmain.off]);
+        constexpr int CH = TE / 4;                                      // 16-byte chunks per row
+        uint32_t* Tb = T0 + buf * RB * TE;
+        for (int c = tid; c < RB * CH; c += TW) {
+            const int rr = c / CH, cc = c - rr * CH;
+            cp_async16(Tb + rr * TE + 4 * cc, src + (ptrdiff_t)(rbase + rr) * src_pitch + (x0 - HA + 4 * cc));
         }
-#pragma unroll
-        for (int q = 0; q < NXT; ++q) {
-            if (xok[q]) {
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const int r = rbase + 2 * xpair[q] + t;
-                    if ((unsigned)r < (unsigned)d.bv_h)
-                        cp_async4(&Sw[2 * xsidx[q] + t], &src[(size_t)r * d.p2 + cx[q].off]);
-                }
-            }
-        }
-        if (TOPHAT && col_ok) {
-            uint32_t* Ow = reinterpret_cast<uint32_t*>(OG + buf * RP * TW);
-#pragma unroll
-            for (int rr = 0; rr < RB; ++rr) {
-                const int y = rbase - R + rr;       // output rows completed while this block is walked
-                if ((unsigned)y < (unsigned)d.bv_h)
-                    cp_async4(&Ow[2 * ((rr >> 1) * TW + tid) + (rr & 1)], &orig[(size_t)y * d.p2 + gx]);
+        if (TOPHAT) {
+            constexpr int CO = TW / 4;
+            uint32_t* Ob = OG + buf * RB * TW;
+            for (int c = tid; c < RB * CO; c += TW) {
+                const int rr = c / CO, cc = c - rr * CO;
+                const int y = rbase - R + rr;                           // output rows completed while this block is walked
+                if (x0 + 4 * cc < d.p2 && (unsigned)y < (unsigned)d.bv_h)
+                    cp_async16(Ob + rr * TW + 4 * cc, orig + (ptrdiff_t)y * orig_pitch + (x0 + 4 * cc));
             }
         }
         cp_async_commit();
     };
     stage_async(r_begin, 0);
+
+    // table columns beyond the thread's own: the 2*HA halo columns of the RP row pairs, spread over the threads
+    // (recomputed per block instead of held in registers across the walk)
+    constexpr int NX = 2 * HA * RP;
+    constexpr int NXT = (NX + TW - 1) / TW;
+    auto halo_elem = [&](int q, int& pr, int& col) -> bool {
+        const int e = tid + q * TW;
+        pr = e / (2 * HA);
+        const int k = e - pr * 2 * HA;
+        col = k < HA ? k : TW + k;                                       // left halo 0..HA-1, right halo TW+HA..TE-1
+        return e < NX;
+    };
 
     uint32_t A[K];
 #pragma unroll
@@ -198,26 +174,19 @@ morph_body(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const u
 
     for (int blk = 0; blk < nblk; ++blk) {
         const int rb0 = r_begin + blk * RB;
-        // the staged block has landed: give the raw words their lanes / padding and publish them as T0
+        const uint32_t* Tc = T0 + (blk & 1) * RB * TE;                   // this block's source rows
         cp_async_wait_all();
-        __syncthreads();
-#pragma unroll
-        for (int m = 0; m < RP; ++m) {
-            const uint2 raw = S[m * TE + tid];
-            T0[m * TEA + tid] = make_uint2(finish(raw.x, rb0 + 2 * m, cmain), finish(raw.y, rb0 + 2 * m + 1, cmain));
-        }
-#pragma unroll
-        for (int q = 0; q < NXT; ++q)
-            if (xok[q]) {
-                const uint2 raw = S[xsidx[q]];
-                T0[xidx[q]] = make_uint2(finish(raw.x, rb0 + 2 * xpair[q], cx[q]), finish(raw.y, rb0 + 2 * xpair[q] + 1, cx[q]));
-            }
-        __syncthreads();
-        if (blk + 1 < nblk) stage_async(rb0 + RB, (blk + 1) & 1);     // S is free again: fetch the next block
-        // window tables: T4 -> (T8, T16) -> T32
-        auto build4 = [&](int idx) {
-            const uint2* t = T0 + idx;
-            T4[idx] = o2(o3(t[0], t[1], t[2]), t[3]);
+        __syncthreads();                                                 // rows landed; previous walk finished
+        if (blk + 1 < nblk) stage_async(rb0 + RB, (blk + 1) & 1);
+        // window tables: T4 (from the raw rows) -> T8, T16, T32
+        auto build4 = [&](int pr, int col, int idx) {
+            const uint32_t* ra = Tc + (2 * pr) * TE + col;
+            const uint32_t* rb = ra + TE;
+            uint32_t a0 = ra[0], b0 = rb[0];
+            uint32_t a1 = col + 1 < TE ? ra[1] : PAD2, b1 = col + 1 < TE ? rb[1] : PAD2;
+            uint32_t a2 = col + 2 < TE ? ra[2] : PAD2, b2 = col + 2 < TE ? rb[2] : PAD2;
+            uint32_t a3 = col + 3 < TE ? ra[3] : PAD2, b3 = col + 3 < TE ? rb[3] : PAD2;
+            T4[idx] = make_uint2(op2<IS_MAX>(op3<IS_MAX>(a0, a1, a2), a3), op2<IS_MAX>(op3<IS_MAX>(b0, b1, b2), b3));
         };
         auto build81632 = [&](int idx) {
             const uint2* t = T4 + idx;
@@ -225,17 +194,17 @@ morph_body(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const u
             uint2 v16 = o3(v8, t[8], t[12]);
             T8[idx] = v8;
             T16[idx] = v16;
-            if (HAS32) T32[idx] = o3(v16, o2(t[16], t[20]), o2(t[24], t[28]));   // no extra barrier for T32
+            if (HAS32) T32[idx] = o3(v16, o2(t[16], t[20]), o2(t[24], t[28]));
         };
 #pragma unroll
-        for (int m = 0; m < RP; ++m) build4(m * TEA + tid);
+        for (int m = 0; m < RP; ++m) build4(m, tid + HA, m * TEA + tid + HA);
 #pragma unroll
-        for (int q = 0; q < NXT; ++q) if (xok[q]) build4(xidx[q]);
+        for (int q = 0; q < NXT; ++q) { int pr, col; if (halo_elem(q, pr, col)) build4(pr, col, pr * TEA + col); }
         __syncthreads();
 #pragma unroll
-        for (int m = 0; m < RP; ++m) build81632(m * TEA + tid);
+        for (int m = 0; m < RP; ++m) build81632(m * TEA + tid + HA);
 #pragma unroll
-        for (int q = 0; q < NXT; ++q) if (xok[q]) build81632(xidx[q]);
+        for (int q = 0; q < NXT; ++q) { int pr, col; if (halo_elem(q, pr, col)) build81632(pr * TEA + col); }
         __syncthreads();
         // walk the RP row pairs of this block
 #pragma unroll 1
@@ -245,16 +214,19 @@ morph_body(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const u
             const int ya = r - R;                   // output rows completed by this pair: ya and ya+1
             const bool emit_a = col_ok && ya >= yb0 && ya < yb1;
             const bool emit_b = col_ok && ya + 1 >= yb0 && ya + 1 < yb1;
-            uint2 og = make_uint2(0u, 0u);
-            if (TOPHAT) og = OG[(blk & 1) * RP * TW + m * TW + tid];
-            const int base = m * TEA + tid + R;     // this thread's column in the tables
+            uint32_t oga = 0, ogb = 0;
+            if (TOPHAT) {
+                const uint32_t* Ob = OG + (blk & 1) * RB * TW + (2 * m) * TW + tid;
+                oga = Ob[0]; ogb = Ob[TW];
+            }
+            const int base = m * TEA + tid + HA;    // this thread's column in the tables
             uint32_t Ha[E::ND], Hb[E::ND];
 #pragma unroll
             for (int u = 0; u < E::ND; ++u) {
                 const int w = E::uniq(u);
                 const int len = 2 * w + 1;
                 uint2 h;
-                if (w == 0) h = T0[base];
+                if (w == 0) h = make_uint2(Tc[(2 * m) * TE + tid + HA], Tc[(2 * m + 1) * TE + tid + HA]);
                 else if (len >= 32) h = o2(T32[base - w], T32[base + w - 31]);
                 else if (len >= 16) h = o2(T16[base - w], T16[base + w - 15]);
                 else h = o2(T8[base - w], T8[base + w - 7]);
@@ -267,14 +239,17 @@ morph_body(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const u
                 A[j] = op3<IS_MAX>(A[j + 2], Ha[ell_uidx<K>(E::hw(j + 1))], Hb[ell_uidx<K>(E::hw(j))]);
             A[K - 2] = op2<IS_MAX>(Ha[ell_uidx<K>(E::hw(K - 1))], Hb[ell_uidx<K>(E::hw(K - 2))]);
             A[K - 1] = Hb[ell_uidx<K>(E::hw(K - 1))];
-            if (emit_a) {
-                uint32_t v = TOPHAT ? og.x - out_a : out_a;      // open <= src per lane: no borrow between lanes
-                dst[(size_t)ya * d.p2 + gx] = v & lane_mask;
-            }
-            if (emit_b) {
-                uint32_t v = TOPHAT ? og.y - A[0] : A[0];
-                dst[(size_t)(ya + 1) * d.p2 + gx] = v & lane_mask;
-            }
+            auto emit = [&](int y, uint32_t v) {
+                v &= lane_mask;                                          // hi lane beyond the image: 0 (the pad of the
+                uint32_t* row = dst + (ptrdiff_t)y * dst_pitch;          // dilation that consumes an eroded plane)
+                row[gx] = v;
+                if (dst_padded) {                                        // seam-stitched halo copies for the next pass
+                    if (gx >= d.p2 - LT_HALO_X) row[gx - d.p2] = (v << 16) | PAD_NEXT;
+                    if (gx < LT_HALO_X) row[gx + d.p2] = (gx + d.p2 < d.bv_w) ? (v >> 16) | (PAD_NEXT << 16) : PAD_NEXT | (PAD_NEXT << 16);
+                }
+            };
+            if (emit_a) emit(ya, TOPHAT ? oga - out_a : out_a);          // open <= src per lane: no borrow between lanes
+            if (emit_b) emit(ya + 1, TOPHAT ? ogb - A[0] : A[0]);
         }
     }
 }
@@ -282,22 +257,22 @@ morph_body(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const u
 // One launch erodes (or dilates) BOTH planes: the 55x55 work items of the Lab-b plane come first, the lighter
 // 29x29 items of the R plane fill the slots they leave free, so the grid packs the SMs without a second wave.
 struct MorphJob {
-    const uint32_t* src; uint32_t* dst; const uint32_t* orig;
+    const uint32_t* src; uint32_t* dst; const uint32_t* orig;     // src, orig: padded planes (pitch d.pp)
     int bands, band_rows;
 };
 
 template <int K>
 constexpr size_t morph_smem_bytes(bool tophat) {
     constexpr int R = Ellipse<K>::R;
-    constexpr int TEA = MORPH_TW + 2 * R + 32;
-    constexpr int NTAB = (2 * R + 1 >= 32) ? 5 : 4;
-    return ((size_t)NTAB * MORPH_RB * TEA + (size_t)MORPH_RB * (MORPH_TW + 2 * R) +
+    constexpr int TE = MORPH_TW + 2 * MorphHa<K>::value;
+    constexpr int NTAB = (2 * R + 1 >= 32) ? 4 : 3;
+    return ((size_t)NTAB * MORPH_RB * (TE + 32) + (size_t)2 * MORPH_RB * TE +
             (tophat ? 2 * MORPH_RB * MORPH_TW : 0)) * sizeof(uint32_t);
 }
 
 template <bool IS_MAX, bool TOPHAT>
 __global__ void __launch_bounds__(MORPH_TW, MORPH_CTAS_PER_SM)
-k_morph_pair(MorphJob j55, MorphJob j29, LtDims d, int tiles, int n, size_t stream_stride,
+k_morph_pair(MorphJob j55, MorphJob j29, LtDims d, int tiles, int n, size_t src_stride, size_t dst_stride,
              const int* __restrict__ list, const int* __restrict__ count) {
     int item = blockIdx.x;
     const int n55 = n * tiles * j55.bands;
@@ -309,11 +284,13 @@ k_morph_pair(MorphJob j55, MorphJob j29, LtDims d, int tiles, int n, size_t stre
     const int tile = tb % tiles, band = tb / tiles;
     if (count != nullptr && slot >= *count) return;
     const int s = list ? list[slot] : slot;
-    const uint32_t* src = j.src + (size_t)s * stream_stride;
-    uint32_t* dst = j.dst + (size_t)s * stream_stride;
-    const uint32_t* orig = TOPHAT ? j.orig + (size_t)s * stream_stride : nullptr;
-    if (big) morph_body<55, IS_MAX, TOPHAT>(src, dst, orig, d, j.band_rows, tile, band);
-    else morph_body<29, IS_MAX, TOPHAT>(src, dst, orig, d, j.band_rows, tile, band);
+    // erosion: padded plane -> padded plane; dilation + top-hat: padded plane -> plain top-hat plane
+    const uint32_t* src = j.src + (size_t)s * src_stride;
+    uint32_t* dst = j.dst + (size_t)s * dst_stride;
+    const uint32_t* orig = TOPHAT ? j.orig + (size_t)s * src_stride : nullptr;
+    const int dst_pitch = TOPHAT ? d.p2 : d.pp;
+    if (big) morph_body<55, IS_MAX, TOPHAT>(src, d.pp, dst, dst_pitch, !TOPHAT, orig, d.pp, d, j.band_rows, tile, band);
+    else morph_body<29, IS_MAX, TOPHAT>(src, d.pp, dst, dst_pitch, !TOPHAT, orig, d.pp, d, j.band_rows, tile, band);
 }
 
 // Pick the band counts of the two jobs by simulating list scheduling of the combined grid on `slots` CTA slots.
@@ -361,7 +338,8 @@ static int launch_morph_pair(lt_handle* h, MorphJob j55, MorphJob j29, int n, co
     j55.band_rows = lt_div_up(d.bv_h, b55); j55.bands = lt_div_up(d.bv_h, j55.band_rows);
     j29.band_rows = lt_div_up(d.bv_h, b29); j29.bands = lt_div_up(d.bv_h, j29.band_rows);
     const int grid = n * tiles * (j55.bands + j29.bands);
-    k_morph_pair<IS_MAX, TOPHAT><<<grid, MORPH_TW, smem, st>>>(j55, j29, d, tiles, n, h->stream_plane, list, count);
+    k_morph_pair<IS_MAX, TOPHAT><<<grid, MORPH_TW, smem, st>>>(j55, j29, d, tiles, n, h->stream_pad,
+                                                               TOPHAT ? h->stream_plane : h->stream_pad, list, count);
     LT_LAUNCH_CHECK();
     return 0;
 }
@@ -413,7 +391,7 @@ __device__ __forceinline__ uint32_t unpack_pair(uint32_t v16) {            // (h
 
 __global__ void __launch_bounds__(CROSSH_WARPS * 32)
 k_cross_h(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_all, LtDims d, int k, int C,
-          int accumulate, int pitch, size_t plane_stride, size_t bits_stride, const int* __restrict__ list,
+          int accumulate, int pitch, int ppitch, size_t plane_stride, size_t bits_stride, const int* __restrict__ list,
           const int* __restrict__ count) {
     int slot = blockIdx.y;
     if (count != nullptr && slot >= *count) return;
@@ -447,7 +425,7 @@ k_cross_h(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_al
 #pragma unroll
             for (int j = 0; j < RPW; ++j) {
                 const int y = y0 + wq + j * CROSSH_WARPS;
-                v[j] = (y < d.bv_h) ? __ldg(reinterpret_cast<const uint4*>(src + (size_t)y * d.p2 + g0)) : make_uint4(0, 0, 0, 0);
+                v[j] = (y < d.bv_h) ? __ldg(reinterpret_cast<const uint4*>(src + (size_t)y * ppitch + g0)) : make_uint4(0, 0, 0, 0);
             }
 #pragma unroll
             for (int j = 0; j < RPW; ++j) {
@@ -466,7 +444,7 @@ k_cross_h(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_al
 #pragma unroll
             for (int j = 0; j < RPW; ++j) {
                 const int y = y0 + wq + j * CROSSH_WARPS;
-                v[j] = (y < d.bv_h) ? fetch(src + (size_t)y * d.p2, i - k) : 0u;
+                v[j] = (y < d.bv_h) ? fetch(src + (size_t)y * ppitch, i - k) : 0u;
             }
 #pragma unroll
             for (int j = 0; j < RPW; ++j) tile[(wq + j * CROSSH_WARPS) * pitch + i] = (unsigned short)v[j];
@@ -520,7 +498,7 @@ k_cross_h(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_al
 // generic fallback of the horizontal half for k > 127 (packed lanes would overflow 15 bits): prefix sums
 __global__ void __launch_bounds__(ROWK_WARPS * 32)
 k_cross_h_wide(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_all, LtDims d, int k, int C,
-               int accumulate, size_t plane_stride, size_t bits_stride, const int* __restrict__ list,
+               int accumulate, int ppitch, size_t plane_stride, size_t bits_stride, const int* __restrict__ list,
                const int* __restrict__ count) {
     int slot = blockIdx.y;
     if (count != nullptr && slot >= *count) return;
@@ -532,7 +510,7 @@ k_cross_h_wide(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bi
     int wpad = (d.bv_w + 32) & ~31;
     uint32_t* lin = smem + (size_t)warp * 2 * wpad;
     uint32_t* E = lin + wpad;
-    warp_row_prefix(plane_all + (size_t)s * plane_stride + (size_t)y * d.p2, d, lin, E, lane);
+    warp_row_prefix(plane_all + (size_t)s * plane_stride + (size_t)y * ppitch, d, lin, E, lane);
     uint32_t* brow = bits_all + (size_t)s * bits_stride + (size_t)y * d.mwords;
     const int Ck = C * k;
     for (int wd = 0; wd < d.mwords; ++wd) {
@@ -557,7 +535,7 @@ constexpr int CV_CHUNK = 8;
 template <bool PACKED>
 __global__ void __launch_bounds__(32)
 k_cross_v(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_all, LtDims d, int k, int C,
-          int band_rows, size_t plane_stride, size_t bits_stride, const int* __restrict__ list,
+          int band_rows, int ppitch, size_t plane_stride, size_t bits_stride, const int* __restrict__ list,
           const int* __restrict__ count) {
     int slot = blockIdx.z;
     if (count != nullptr && slot >= *count) return;
@@ -568,7 +546,7 @@ k_cross_v(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_al
     const uint32_t* P = plane_all + (size_t)s * plane_stride + x;
     uint32_t* bits = bits_all + (size_t)s * bits_stride;
     const bool hi_ok = x + d.p2 < d.bv_w;
-    auto ld = [&](int r) -> uint32_t { return ((unsigned)r < (unsigned)d.bv_h) ? __ldg(&P[(size_t)r * d.p2]) : 0u; };
+    auto ld = [&](int r) -> uint32_t { return ((unsigned)r < (unsigned)d.bv_h) ? __ldg(&P[(size_t)r * ppitch]) : 0u; };
     uint32_t U = 0, D = 0;
     for (int i0 = 1; i0 <= k; i0 += CV_CHUNK) {  // initial window sums, CV_CHUNK rows per side in flight
         uint32_t a[CV_CHUNK], b[CV_CHUNK];
@@ -622,7 +600,7 @@ k_cross_v(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_al
 
 __global__ void __launch_bounds__(ROWK_WARPS * 32)
 k_box_h(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ hs_all, LtDims d, int half,
-        size_t plane_stride, const int* __restrict__ list, const int* __restrict__ count, int nslots) {
+        int ppitch, size_t plane_stride, size_t hs_stride, const int* __restrict__ list, const int* __restrict__ count, int nslots) {
     extern __shared__ uint32_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int y = blockIdx.x * ROWK_WARPS + warp;
@@ -633,8 +611,8 @@ k_box_h(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ hs_all, L
     const int nsl = count ? *count : nslots;          // attempt-2 launches loop over the (usually empty) retry list
     for (int slot = blockIdx.y; slot < nsl; slot += gridDim.y) {
         const int s = list ? list[slot] : slot;
-        warp_row_prefix(plane_all + (size_t)s * plane_stride + (size_t)y * d.p2, d, lin, E, lane);
-        uint32_t* hrow = hs_all + (size_t)s * plane_stride + (size_t)y * d.p2;
+        warp_row_prefix(plane_all + (size_t)s * plane_stride + (size_t)y * ppitch, d, lin, E, lane);
+        uint32_t* hrow = hs_all + (size_t)s * hs_stride + (size_t)y * d.p2;
         const int W = d.bv_w;
         const uint32_t first = lin[0], last = lin[W - 1];
         auto rowsum = [&](int c) -> uint32_t {
@@ -652,7 +630,8 @@ k_box_h(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ hs_all, L
 
 __global__ void __launch_bounds__(32)
 k_box_v(const uint32_t* __restrict__ plane_all, const uint32_t* __restrict__ hs_all, uint32_t* __restrict__ bits_all,
-        LtDims d, int half, int c, int accumulate, int band_rows, size_t plane_stride, size_t bits_stride,
+        LtDims d, int half, int c, int accumulate, int band_rows, int ppitch, size_t plane_stride, size_t hs_stride,
+        size_t bits_stride,
         const int* __restrict__ list, const int* __restrict__ count, int nslots) {
     const int nsl = count ? *count : nslots;
     for (int slot = blockIdx.z; slot < nsl; slot += gridDim.z) {
@@ -661,7 +640,7 @@ k_box_v(const uint32_t* __restrict__ plane_all, const uint32_t* __restrict__ hs_
     int x = blockIdx.x * 32 + lane;
     int yb0 = blockIdx.y * band_rows, yb1 = min(yb0 + band_rows, d.bv_h);
     const uint32_t* P = plane_all + (size_t)s * plane_stride + x;
-    const uint32_t* Hs = hs_all + (size_t)s * plane_stride + x;
+    const uint32_t* Hs = hs_all + (size_t)s * hs_stride + x;
     uint32_t* bits = bits_all + (size_t)s * bits_stride;
     const bool hi_ok = x + d.p2 < d.bv_w;
     auto ldh = [&](int r) -> uint32_t { r = max(0, min(d.bv_h - 1, r)); return __ldg(&Hs[(size_t)r * d.p2]); };
@@ -669,7 +648,7 @@ k_box_v(const uint32_t* __restrict__ plane_all, const uint32_t* __restrict__ hs_
     for (int dy = -half; dy <= half; ++dy) { uint32_t v = ldh(yb0 + dy); Sl += v & 0xFFFFu; Sh += v >> 16; }
     const uint32_t n = (uint32_t)(2 * half + 1) * (uint32_t)(2 * half + 1);
     for (int y = yb0; y < yb1; ++y) {
-        uint32_t p = __ldg(&P[(size_t)y * d.p2]);
+        uint32_t p = __ldg(&P[(size_t)y * ppitch]);
         int ml = (int)((2u * Sl + n) / (2u * n)), mh = (int)((2u * Sh + n) / (2u * n));
         bool pl = ((int)(p & 0xFFFFu) - ml) > c;
         bool ph = hi_ok && (((int)(p >> 16) - mh) > c);
@@ -690,13 +669,13 @@ k_box_v(const uint32_t* __restrict__ plane_all, const uint32_t* __restrict__ hs_
 // mask_noise (lane_tracker.py:221-231): merged &= ~inRange(b, thresh, 255) | cross(b, k_noise, C_noise)
 __global__ void __launch_bounds__(32)
 k_noise_combine(const uint32_t* __restrict__ planeB_all, const uint32_t* __restrict__ noise_bits_all,
-                uint32_t* __restrict__ merged_all, LtDims d, int thresh, size_t plane_stride, size_t bits_stride,
+                uint32_t* __restrict__ merged_all, LtDims d, int thresh, int ppitch, size_t plane_stride, size_t bits_stride,
                 const int* __restrict__ list, const int* __restrict__ count) {
     int slot = blockIdx.z;
     if (count != nullptr && slot >= *count) return;
     int s = list ? list[slot] : slot;
     int lane = threadIdx.x, x = blockIdx.x * 32 + lane, y = blockIdx.y;
-    uint32_t p = __ldg(&planeB_all[(size_t)s * plane_stride + (size_t)y * d.p2 + x]);
+    uint32_t p = __ldg(&planeB_all[(size_t)s * plane_stride + (size_t)y * ppitch + x]);
     uint32_t il = __ballot_sync(0xFFFFFFFFu, (int)(p & 0xFFFFu) >= thresh);
     uint32_t ih = __ballot_sync(0xFFFFFFFFu, (int)(p >> 16) >= thresh);
     if (lane == 0) {
@@ -798,10 +777,11 @@ __global__ void k_u8_to_mask(const uint8_t* __restrict__ in, uint32_t* __restric
     if (lane == 0) bits[(size_t)s * bits_stride + (size_t)y * d.mwords + wd] = b;
 }
 
-__global__ void k_plane_to_u8(const uint32_t* __restrict__ plane, uint8_t* __restrict__ out, LtDims d, size_t plane_stride) {
+__global__ void k_plane_to_u8(const uint32_t* __restrict__ plane, uint8_t* __restrict__ out, LtDims d, int ppitch,
+                              size_t plane_stride) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, s = blockIdx.z;
     if (x >= d.bv_w) return;
-    uint32_t v = __ldg(&plane[(size_t)s * plane_stride + (size_t)y * d.p2 + (x >= d.p2 ? x - d.p2 : x)]);
+    uint32_t v = __ldg(&plane[(size_t)s * plane_stride + (size_t)y * ppitch + (x >= d.p2 ? x - d.p2 : x)]);
     out[((size_t)s * d.bv_h + y) * d.bv_w + x] = (uint8_t)((x >= d.p2 ? (v >> 16) : v) & 255u);
 }
 
@@ -817,9 +797,9 @@ int lt_launch_u8_to_mask(lt_handle* h, const uint8_t* d_mask, uint32_t* bits, in
     LT_LAUNCH_CHECK();
     return 0;
 }
-int lt_launch_plane_to_u8(lt_handle* h, const uint32_t* plane, uint8_t* d_dst, int n, cudaStream_t st) {
+int lt_launch_plane_to_u8(lt_handle* h, const uint32_t* plane, int pitch, uint8_t* d_dst, int n, cudaStream_t st) {
     dim3 g(lt_div_up(h->d.bv_w, 256), h->d.bv_h, n);
-    k_plane_to_u8<<<g, 256, 0, st>>>(plane, d_dst, h->d, h->stream_plane);
+    k_plane_to_u8<<<g, 256, 0, st>>>(plane, d_dst, h->d, pitch, pitch == h->d.p2 ? h->stream_plane : h->stream_pad);
     LT_LAUNCH_CHECK();
     return 0;
 }
@@ -828,9 +808,11 @@ int lt_launch_plane_to_u8(lt_handle* h, const uint32_t* plane, uint8_t* d_dst, i
 // the whole filter for one attempt
 // ---------------------------------------------------------------------------
 
-static int launch_cross(lt_handle* h, const uint32_t* plane, uint32_t* bits, int k, int C, int accumulate, int n,
+static int launch_cross(lt_handle* h, const uint32_t* plane, bool padded, uint32_t* bits, int k, int C, int accumulate, int n,
                         const int* list, const int* count, cudaStream_t st) {
     const LtDims& d = h->d;
+    const int ppitch = padded ? d.pp : d.p2;
+    const size_t pstride = padded ? h->stream_pad : h->stream_plane;
     if (k <= 127 && C >= 0 && k * 255 + C * k + 1 < 32768) {   // packed u16 lanes must stay below 2^15
         int pitch = d.p2 + 2 * k + 2;
         while (((pitch >> 1) & 1) == 0 || (pitch & 1)) ++pitch;       // pitch = 2 * odd: rows land in distinct banks
@@ -838,7 +820,7 @@ static int launch_cross(lt_handle* h, const uint32_t* plane, uint32_t* bits, int
         int rc = lt_ensure_smem((const void*)k_cross_h, smem);
         if (rc) return rc;
         dim3 gh(lt_div_up(d.bv_h, CROSSH_ROWS), n);
-        k_cross_h<<<gh, CROSSH_WARPS * 32, smem, st>>>(plane, bits, d, k, C, accumulate, pitch, h->stream_plane,
+        k_cross_h<<<gh, CROSSH_WARPS * 32, smem, st>>>(plane, bits, d, k, C, accumulate, pitch, ppitch, pstride,
                                                          h->stream_mask, list, count);
         LT_LAUNCH_CHECK();
     } else {
@@ -847,16 +829,16 @@ static int launch_cross(lt_handle* h, const uint32_t* plane, uint32_t* bits, int
         int rc = lt_ensure_smem((const void*)k_cross_h_wide, smem);
         if (rc) return rc;
         dim3 gh(lt_div_up(d.bv_h, ROWK_WARPS), n);
-        k_cross_h_wide<<<gh, ROWK_WARPS * 32, smem, st>>>(plane, bits, d, k, C, accumulate, h->stream_plane,
+        k_cross_h_wide<<<gh, ROWK_WARPS * 32, smem, st>>>(plane, bits, d, k, C, accumulate, ppitch, pstride,
                                                             h->stream_mask, list, count);
         LT_LAUNCH_CHECK();
     }
     int band_rows = 128;
     dim3 gv(d.p2 / 32, lt_div_up(d.bv_h, band_rows), n);
     if (k <= 127 && C >= 0 && k * 255 + C * k + 1 < 32768)
-        k_cross_v<true><<<gv, 32, 0, st>>>(plane, bits, d, k, C, band_rows, h->stream_plane, h->stream_mask, list, count);
+        k_cross_v<true><<<gv, 32, 0, st>>>(plane, bits, d, k, C, band_rows, ppitch, pstride, h->stream_mask, list, count);
     else
-        k_cross_v<false><<<gv, 32, 0, st>>>(plane, bits, d, k, C, band_rows, h->stream_plane, h->stream_mask, list, count);
+        k_cross_v<false><<<gv, 32, 0, st>>>(plane, bits, d, k, C, band_rows, ppitch, pstride, h->stream_mask, list, count);
     LT_LAUNCH_CHECK();
     return 0;
 }
@@ -870,11 +852,11 @@ static int launch_box(lt_handle* h, const uint32_t* plane, uint32_t* hs, uint32_
     int half = block / 2;
     const int zs = list ? (n < 8 ? n : 8) : n;      // retry-list launches: few slots, each CTA loops over the list
     dim3 gh(lt_div_up(d.bv_h, ROWK_WARPS), zs);
-    k_box_h<<<gh, ROWK_WARPS * 32, smem, st>>>(plane, hs, d, half, h->stream_plane, list, count, n);
+    k_box_h<<<gh, ROWK_WARPS * 32, smem, st>>>(plane, hs, d, half, d.pp, h->stream_pad, h->stream_plane, list, count, n);
     LT_LAUNCH_CHECK();
     int band_rows = 64;
     dim3 gv(d.p2 / 32, lt_div_up(d.bv_h, band_rows), zs);
-    k_box_v<<<gv, 32, 0, st>>>(plane, hs, bits, d, half, c, accumulate, band_rows, h->stream_plane, h->stream_mask,
+    k_box_v<<<gv, 32, 0, st>>>(plane, hs, bits, d, half, c, accumulate, band_rows, d.pp, h->stream_pad, h->stream_plane, h->stream_mask,
                                list, count, n);
     LT_LAUNCH_CHECK();
     return 0;
@@ -891,19 +873,19 @@ int lt_launch_filter(lt_handle* h, int n, const LtAttemptParams& p, const int* l
         MorphJob t55 = {h->tmpB, h->topB, h->planeB, 0, 0}, t29 = {h->tmpR, h->topR, h->planeR, 0, 0};
         if ((rc = launch_morph_pair<true, true>(h, t55, t29, n, list, count, st))) return rc;
         lt_prof_mark(h, ST_TOPHAT55, st);           // both dilations + top-hat epilogues in one launch
-        if ((rc = launch_cross(h, h->topR, h->merged, p.ksize_r, p.C_r, 0, n, list, count, st))) return rc;
+        if ((rc = launch_cross(h, h->topR, false, h->merged, p.ksize_r, p.C_r, 0, n, list, count, st))) return rc;
         lt_prof_mark(h, ST_CROSS_R, st);
-        if ((rc = launch_cross(h, h->topB, h->merged, p.ksize_b, p.C_b, 1, n, list, count, st))) return rc;
+        if ((rc = launch_cross(h, h->topB, false, h->merged, p.ksize_b, p.C_b, 1, n, list, count, st))) return rc;
         lt_prof_mark(h, ST_CROSS_B, st);
     } else {
-        if ((rc = launch_box(h, h->planeR, h->tmpR, h->merged, p.ksize_r, p.C_r, 0, n, list, count, st))) return rc;
-        if ((rc = launch_box(h, h->planeB, h->tmpB, h->merged, p.ksize_b, p.C_b, 1, n, list, count, st))) return rc;
+        if ((rc = launch_box(h, h->planeR, h->topR, h->merged, p.ksize_r, p.C_r, 0, n, list, count, st))) return rc;
+        if ((rc = launch_box(h, h->planeB, h->topB, h->merged, p.ksize_b, p.C_b, 1, n, list, count, st))) return rc;
         lt_prof_mark(h, ST_BOX, st);
     }
     if (p.mask_noise) {
-        if ((rc = launch_cross(h, h->planeB, h->mask, p.ksize_noise, p.C_noise, 0, n, list, count, st))) return rc;
+        if ((rc = launch_cross(h, h->planeB, true, h->mask, p.ksize_noise, p.C_noise, 0, n, list, count, st))) return rc;
         dim3 g(d.p2 / 32, d.bv_h, n);
-        k_noise_combine<<<g, 32, 0, st>>>(h->planeB, h->mask, h->merged, d, p.noise_thresh, h->stream_plane,
+        k_noise_combine<<<g, 32, 0, st>>>(h->planeB, h->mask, h->merged, d, p.noise_thresh, d.pp, h->stream_pad,
                                           h->stream_mask, list, count);
         LT_LAUNCH_CHECK();
         lt_prof_mark(h, ST_NOISE, st);

@@ -224,10 +224,30 @@ __device__ __forceinline__ uint32_t blend_rgbx(uint32_t t00, uint32_t t01, uint3
     return R | (G << 8) | (B << 16);
 }
 
+// Store one packed column of the two morphology input planes (padded layout, lt_common.cuh): lanes beyond the image
+// carry the erosion pad 0xFFFF, and the columns next to the seam are mirrored into the halo of the other strip
+// (column -j holds pixel p2 - j in its hi lane, column p2 + j holds pixel p2 + j in its lo lane).
+__device__ __forceinline__ void store_padded(uint32_t* __restrict__ planeR, uint32_t* __restrict__ planeB, uint32_t r2,
+                                             uint32_t b2, int x, int y, int s, size_t stream_pad, const LtDims& d) {
+    const bool hi_real = x + d.p2 < d.bv_w;
+    if (!hi_real) { r2 |= 0xFFFF0000u; b2 |= 0xFFFF0000u; }
+    const size_t row = (size_t)s * stream_pad + (ptrdiff_t)y * d.pp;
+    planeR[row + x] = r2;
+    planeB[row + x] = b2;
+    if (x >= d.p2 - LT_HALO_X) {
+        planeR[row + x - d.p2] = (r2 << 16) | 0xFFFFu;
+        planeB[row + x - d.p2] = (b2 << 16) | 0xFFFFu;
+    }
+    if (x < LT_HALO_X) {
+        planeR[row + x + d.p2] = (r2 >> 16) | 0xFFFF0000u;      // hi lane of a halo column lies beyond the image
+        planeB[row + x + d.p2] = (b2 >> 16) | 0xFFFF0000u;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_warp_planes(const uchar4* __restrict__ und_all, const int2* __restrict__ desc, uint32_t* __restrict__ planeR,
               uint32_t* __restrict__ planeB, uint8_t* __restrict__ bv_rgb,
-              const unsigned short* __restrict__ g, const unsigned short* __restrict__ cb, LtDims d) {
+              const unsigned short* __restrict__ g, const unsigned short* __restrict__ cb, LtDims d, size_t stream_pad) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y, s = blockIdx.z;
     if (x >= d.p2) return;
@@ -261,16 +281,14 @@ k_warp_planes(const uchar4* __restrict__ und_all, const int2* __restrict__ desc,
             }
         }
     }
-    size_t o = ((size_t)s * d.bv_h + y) * d.p2 + x;
-    planeR[o] = r2;
-    planeB[o] = b2;
+    store_padded(planeR, planeB, r2, b2, x, y, s, stream_pad, d);
 }
 
 int lt_launch_warp(lt_handle* h, uint8_t* d_bv_rgb, int n, cudaStream_t st) {
     const LtDims& d = h->d;
     dim3 g(lt_div_up(d.p2, 256), d.bv_h, n);
     k_warp_planes<<<g, 256, 0, st>>>(h->und_roi, h->bv_desc, h->planeR, h->planeB, d_bv_rgb, h->lab_gamma,
-                                     h->lab_cbrt, d);
+                                     h->lab_cbrt, d, h->stream_pad);
     LT_LAUNCH_CHECK();
     return 0;
 }
@@ -337,7 +355,7 @@ int lt_launch_build_fused_desc(lt_handle* h, cudaStream_t st) {
 __global__ void __launch_bounds__(256)
 k_warp_planes_fused(const uint8_t* __restrict__ frames, const int2* __restrict__ desc, uint32_t* __restrict__ planeR,
                     uint32_t* __restrict__ planeB, uint8_t* __restrict__ bv_rgb,
-                    const unsigned short* __restrict__ g, const unsigned short* __restrict__ cb, LtDims d) {
+                    const unsigned short* __restrict__ g, const unsigned short* __restrict__ cb, LtDims d, size_t stream_pad) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y, s = blockIdx.z;
     if (x >= d.p2) return;
@@ -363,16 +381,14 @@ k_warp_planes_fused(const uint8_t* __restrict__ frames, const int2* __restrict__
             }
         }
     }
-    size_t o = ((size_t)s * d.bv_h + y) * d.p2 + x;
-    planeR[o] = r2;
-    planeB[o] = b2;
+    store_padded(planeR, planeB, r2, b2, x, y, s, stream_pad, d);
 }
 
 int lt_launch_warp_fused(lt_handle* h, const uint8_t* d_frames, uint8_t* d_bv_rgb, int n, cudaStream_t st) {
     const LtDims& d = h->d;
     dim3 g(lt_div_up(d.p2, 256), d.bv_h, n);
     k_warp_planes_fused<<<g, 256, 0, st>>>(d_frames, h->fused_desc, h->planeR, h->planeB, d_bv_rgb, h->lab_gamma,
-                                           h->lab_cbrt, d);
+                                           h->lab_cbrt, d, h->stream_pad);
     LT_LAUNCH_CHECK();
     return 0;
 }
@@ -380,7 +396,7 @@ int lt_launch_warp_fused(lt_handle* h, const uint8_t* d_frames, uint8_t* d_bv_rg
 // planes from a caller-supplied bird's-eye RGB image (filter_lane_points API, lane_tracker.py:207-208)
 __global__ void __launch_bounds__(256)
 k_planes_from_bv(const uint8_t* __restrict__ bv_rgb, uint32_t* __restrict__ planeR, uint32_t* __restrict__ planeB,
-                 const unsigned short* __restrict__ g, const unsigned short* __restrict__ cb, LtDims d) {
+                 const unsigned short* __restrict__ g, const unsigned short* __restrict__ cb, LtDims d, size_t stream_pad) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y, s = blockIdx.z;
     if (x >= d.p2) return;
@@ -395,15 +411,13 @@ k_planes_from_bv(const uint8_t* __restrict__ bv_rgb, uint32_t* __restrict__ plan
             b2 |= (uint32_t)lab_b(o, g, cb) << (16 * half);
         }
     }
-    size_t o = ((size_t)s * d.bv_h + y) * d.p2 + x;
-    planeR[o] = r2;
-    planeB[o] = b2;
+    store_padded(planeR, planeB, r2, b2, x, y, s, stream_pad, d);
 }
 
 int lt_launch_planes_from_bv(lt_handle* h, const uint8_t* d_bv_rgb, int n, cudaStream_t st) {
     const LtDims& d = h->d;
     dim3 g(lt_div_up(d.p2, 256), d.bv_h, n);
-    k_planes_from_bv<<<g, 256, 0, st>>>(d_bv_rgb, h->planeR, h->planeB, h->lab_gamma, h->lab_cbrt, d);
+    k_planes_from_bv<<<g, 256, 0, st>>>(d_bv_rgb, h->planeR, h->planeB, h->lab_gamma, h->lab_cbrt, d, h->stream_pad);
     LT_LAUNCH_CHECK();
     return 0;
 }
