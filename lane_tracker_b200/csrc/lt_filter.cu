@@ -91,10 +91,13 @@ template <int K, bool IS_MAX, bool TOPHAT>
 __device__ __forceinline__ void
 morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict__ dst, int dst_pitch, bool dst_padded,
            const uint32_t* __restrict__ orig, int orig_pitch, const LtDims& d, int band_rows, int tile, int band) {
-    // Shared-memory window tables hold ROW PAIRS: element (pair m, column c) is a uint2 {row 2m, row 2m+1}.  Every
-    // table access is one LDS.64/STS.64 serving two source rows, and the vertical pipeline advances two rows per
-    // step with a single three-input VIMNMX3 per accumulator:
-    //     A[j] <- op3(A[j+2], H_a[hw(j+1)], H_b[hw(j)])        (a, b = the two rows of the pair)
+    // The kernel is bound by shared-memory bandwidth, so the window tables are BYTE packed: element (pair m, column c)
+    // is one 32-bit word {a.lo, b.lo, a.hi, b.hi} (a, b = rows 2m, 2m+1; lo, hi = the two strips of the pair plane).
+    // One LDS.32 serves two source rows x two pixels.  The arithmetic stays on 16-bit lanes (VIMNMX.U16x2) by
+    // working at "scale 256": a lane holds value << 8 | junk, and min/max of such lanes orders by the value byte, so
+    // row b's lanes are the table word as loaded and row a's are the word shifted left by 8; the junk byte is dropped
+    // when a result is emitted.  The vertical pipeline advances two rows per step with one VIMNMX3 per accumulator:
+    //     A[j] <- op3(A[j+2], H_a[hw(j+1)], H_b[hw(j)])
     using E = Ellipse<K>;
     constexpr int R = E::R;
     constexpr int TW = MORPH_TW, RB = MORPH_RB, RP = RB / 2, HA = MorphHa<K>::value;
@@ -108,11 +111,11 @@ morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict
     static_assert(HA >= R && HA <= LT_HALO_X && R + RB - 1 <= LT_HALO_Y && HA % 4 == 0 && TE % 4 == 0, "staging must be 16-byte granular");
 
     extern __shared__ uint32_t smem[];
-    uint2* T4 = reinterpret_cast<uint2*>(smem);
-    uint2* T8 = T4 + RP * TEA;
-    uint2* T16 = T8 + RP * TEA;
-    uint2* T32 = T16 + RP * TEA;                        // only touched when HAS32
-    uint32_t* T0 = smem + 2 * NTAB * RP * TEA;          // [2 buffers][RB rows][TE] raw source rows (row-major)
+    uint32_t* T4 = smem;
+    uint32_t* T8 = T4 + RP * TEA;
+    uint32_t* T16 = T8 + RP * TEA;
+    uint32_t* T32 = T16 + RP * TEA;                     // only touched when HAS32
+    uint32_t* T0 = smem + NTAB * RP * TEA;              // [2 buffers][RB rows][TE] raw source rows (row-major)
     uint32_t* OG = T0 + 2 * RB * TE;                    // [2 buffers][RB rows][TW] original rows (top-hat epilogue)
 
     const int tid = threadIdx.x;
@@ -120,7 +123,7 @@ morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict
     const int yb0 = band * band_rows;
     const int yb1 = min(yb0 + band_rows, d.bv_h);
 
-    for (int i = tid; i < 2 * NTAB * RP * TEA; i += TW) smem[i] = PAD2;      // table slack must read as PAD
+    for (int i = tid; i < NTAB * RP * TEA; i += TW) smem[i] = PAD2;      // table slack must read as PAD
 
     const int r_begin = yb0 - R;
     const int r_end = yb1 + R;      // exclusive
@@ -169,6 +172,9 @@ morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict
 #pragma unroll
     for (int j = 0; j < K; ++j) A[j] = PAD2;
 
+    // a table word seen as the scale-256 lanes of row a (.x) and row b (.y)
+    auto lanes = [](uint32_t t) { return make_uint2(t << 8, t); };
+    auto pack = [](uint2 v) { return __byte_perm(v.x, v.y, 0x7351); };          // value bytes back to {a.lo, b.lo, a.hi, b.hi}
     auto o2 = [](uint2 a, uint2 b) { return make_uint2(op2<IS_MAX>(a.x, b.x), op2<IS_MAX>(a.y, b.y)); };
     auto o3 = [](uint2 a, uint2 b, uint2 c) { return make_uint2(op3<IS_MAX>(a.x, b.x, c.x), op3<IS_MAX>(a.y, b.y, c.y)); };
 
@@ -186,15 +192,16 @@ morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict
             uint32_t a1 = col + 1 < TE ? ra[1] : PAD2, b1 = col + 1 < TE ? rb[1] : PAD2;
             uint32_t a2 = col + 2 < TE ? ra[2] : PAD2, b2 = col + 2 < TE ? rb[2] : PAD2;
             uint32_t a3 = col + 3 < TE ? ra[3] : PAD2, b3 = col + 3 < TE ? rb[3] : PAD2;
-            T4[idx] = make_uint2(op2<IS_MAX>(op3<IS_MAX>(a0, a1, a2), a3), op2<IS_MAX>(op3<IS_MAX>(b0, b1, b2), b3));
+            // raw lanes are plain values (or the 16-bit pad): their low bytes are the table bytes
+            T4[idx] = __byte_perm(op2<IS_MAX>(op3<IS_MAX>(a0, a1, a2), a3), op2<IS_MAX>(op3<IS_MAX>(b0, b1, b2), b3), 0x6240);
         };
         auto build81632 = [&](int idx) {
-            const uint2* t = T4 + idx;
-            uint2 v8 = o2(t[0], t[4]);
-            uint2 v16 = o3(v8, t[8], t[12]);
-            T8[idx] = v8;
-            T16[idx] = v16;
-            if (HAS32) T32[idx] = o3(v16, o2(t[16], t[20]), o2(t[24], t[28]));
+            const uint32_t* t = T4 + idx;
+            uint2 v8 = o2(lanes(t[0]), lanes(t[4]));
+            uint2 v16 = o3(v8, lanes(t[8]), lanes(t[12]));
+            T8[idx] = pack(v8);
+            T16[idx] = pack(v16);
+            if (HAS32) T32[idx] = pack(o3(v16, o2(lanes(t[16]), lanes(t[20])), o2(lanes(t[24]), lanes(t[28]))));
         };
 #pragma unroll
         for (int m = 0; m < RP; ++m) build4(m, tid + HA, m * TEA + tid + HA);
@@ -226,10 +233,10 @@ morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict
                 const int w = E::uniq(u);
                 const int len = 2 * w + 1;
                 uint2 h;
-                if (w == 0) h = make_uint2(Tc[(2 * m) * TE + tid + HA], Tc[(2 * m + 1) * TE + tid + HA]);
-                else if (len >= 32) h = o2(T32[base - w], T32[base + w - 31]);
-                else if (len >= 16) h = o2(T16[base - w], T16[base + w - 15]);
-                else h = o2(T8[base - w], T8[base + w - 7]);
+                if (w == 0) h = make_uint2(Tc[(2 * m) * TE + tid + HA] << 8, Tc[(2 * m + 1) * TE + tid + HA] << 8);
+                else if (len >= 32) h = o2(lanes(T32[base - w]), lanes(T32[base + w - 31]));
+                else if (len >= 16) h = o2(lanes(T16[base - w]), lanes(T16[base + w - 15]));
+                else h = o2(lanes(T8[base - w]), lanes(T8[base + w - 7]));
                 Ha[u] = h.x;
                 Hb[u] = h.y;
             }
@@ -239,7 +246,9 @@ morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict
                 A[j] = op3<IS_MAX>(A[j + 2], Ha[ell_uidx<K>(E::hw(j + 1))], Hb[ell_uidx<K>(E::hw(j))]);
             A[K - 2] = op2<IS_MAX>(Ha[ell_uidx<K>(E::hw(K - 1))], Hb[ell_uidx<K>(E::hw(K - 2))]);
             A[K - 1] = Hb[ell_uidx<K>(E::hw(K - 1))];
-            auto emit = [&](int y, uint32_t v) {
+            auto emit = [&](int y, uint32_t v256) {
+                uint32_t v = __byte_perm(v256, 0, 0x4341);               // scale 256 -> plain values
+                if (TOPHAT) v = (y == ya ? oga : ogb) - v;               // open <= src per lane: no borrow between lanes
                 v &= lane_mask;                                          // hi lane beyond the image: 0 (the pad of the
                 uint32_t* row = dst + (ptrdiff_t)y * dst_pitch;          // dilation that consumes an eroded plane)
                 row[gx] = v;
@@ -248,8 +257,8 @@ morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict
                     if (gx < LT_HALO_X) row[gx + d.p2] = (gx + d.p2 < d.bv_w) ? (v >> 16) | (PAD_NEXT << 16) : PAD_NEXT | (PAD_NEXT << 16);
                 }
             };
-            if (emit_a) emit(ya, TOPHAT ? oga - out_a : out_a);          // open <= src per lane: no borrow between lanes
-            if (emit_b) emit(ya + 1, TOPHAT ? ogb - A[0] : A[0]);
+            if (emit_a) emit(ya, out_a);
+            if (emit_b) emit(ya + 1, A[0]);
         }
     }
 }
@@ -266,7 +275,7 @@ constexpr size_t morph_smem_bytes(bool tophat) {
     constexpr int R = Ellipse<K>::R;
     constexpr int TE = MORPH_TW + 2 * MorphHa<K>::value;
     constexpr int NTAB = (2 * R + 1 >= 32) ? 4 : 3;
-    return ((size_t)NTAB * MORPH_RB * (TE + 32) + (size_t)2 * MORPH_RB * TE +
+    return ((size_t)NTAB * (MORPH_RB / 2) * (TE + 32) + (size_t)2 * MORPH_RB * TE +
             (tophat ? 2 * MORPH_RB * MORPH_TW : 0)) * sizeof(uint32_t);
 }
 
