@@ -107,7 +107,6 @@ morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict
     constexpr int NTAB = HAS32 ? 4 : 3;     // T4, T8, T16 (, T32)
     constexpr uint32_t PADL = IS_MAX ? 0u : 0xFFFFu;
     constexpr uint32_t PAD2 = PADL | (PADL << 16);
-    constexpr uint32_t PAD_NEXT = 0u;       // lane pad of the pass that reads a padded dst (dilation after erosion)
     static_assert(HA >= R && HA <= LT_HALO_X && R + RB - 1 <= LT_HALO_Y && HA % 4 == 0 && TE % 4 == 0, "staging must be 16-byte granular");
 
     extern __shared__ uint32_t smem[];
@@ -122,51 +121,58 @@ morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict
     const int x0 = tile * TW;
     const int yb0 = band * band_rows;
     const int yb1 = min(yb0 + band_rows, d.bv_h);
-
-    for (int i = tid; i < NTAB * RP * TEA; i += TW) smem[i] = PAD2;      // table slack must read as PAD
-
     const int r_begin = yb0 - R;
     const int r_end = yb1 + R;      // exclusive
     const int nblk = (r_end - r_begin + RB - 1) / RB;
 
-    const int gx = x0 + tid;                       // this thread's packed column
-    const bool col_ok = gx < d.p2;
-    const uint32_t lane_mask = (gx + d.p2 < d.bv_w) ? 0xFFFFFFFFu : 0x0000FFFFu;
+    // Table entries whose window runs past the staged columns are built from whatever follows in shared memory and
+    // are never read by the walk (its windows end at column tid + HA + w <= TE - 1), so nothing needs initialising.
 
-    // stage rows [rbase, rbase + RB) x columns [x0 - HA, x0 + TW + HA) (and the original rows of the outputs the
-    // block completes) with 16-byte cp.async; halo columns / pad rows of the padded planes make every address valid
-    auto stage_async = [&](int rbase, int buf) {
-        constexpr int CH = TE / 4;                                      // 16-byte chunks per row
-        uint32_t* Tb = T0 + buf * RB * TE;
-        for (int c = tid; c < RB * CH; c += TW) {
-            const int rr = c / CH, cc = c - rr * CH;
-            cp_async16(Tb + rr * TE + 4 * cc, src + (ptrdiff_t)(rbase + rr) * src_pitch + (x0 - HA + 4 * cc));
+    // ---- staging: rows [rbase, rbase + RB) x columns [x0 - HA, x0 + TW + HA) as 16-byte cp.async, three groups of
+    // 64 threads each taking every third row; the halo columns / pad rows of the padded planes make every address valid
+    constexpr int CH = TE / 4;                                          // 16-byte chunks per staged row
+    static_assert(CH <= 64 && TW == 192 && RB == 8, "staging thread mapping");
+    const int sg = tid >> 6, sc = tid & 63;
+    const bool s_on = sc < CH;
+    const uint32_t* sp = src + (ptrdiff_t)(r_begin + sg) * src_pitch + (x0 - HA + 4 * sc);    // advances RB rows per block
+    uint32_t* const sdst = T0 + sg * TE + 4 * sc;
+    // original rows for the top-hat epilogue: 48 chunks per row, thread -> (row tid / 48 and + 4, chunk tid % 48)
+    const int orow = tid / 48, oc = tid - orow * 48;
+    const bool o_on = TOPHAT && x0 + 4 * oc < d.p2;
+    const uint32_t* op = TOPHAT ? orig + (ptrdiff_t)(r_begin - R + orow) * orig_pitch + (x0 + 4 * oc) : nullptr;
+    uint32_t* const odst = OG + orow * TW + 4 * oc;
+    int oy = r_begin - R + orow;                                        // image row of this thread's first original row
+    auto stage_async = [&](int buf) {
+        if (s_on) {
+            uint32_t* t = sdst + buf * RB * TE;
+            cp_async16(t, sp);
+            cp_async16(t + 3 * TE, sp + 3 * (ptrdiff_t)src_pitch);
+            if (sg < 2) cp_async16(t + 6 * TE, sp + 6 * (ptrdiff_t)src_pitch);
         }
+        sp += (ptrdiff_t)RB * src_pitch;
         if (TOPHAT) {
-            constexpr int CO = TW / 4;
-            uint32_t* Ob = OG + buf * RB * TW;
-            for (int c = tid; c < RB * CO; c += TW) {
-                const int rr = c / CO, cc = c - rr * CO;
-                const int y = rbase - R + rr;                           // output rows completed while this block is walked
-                if (x0 + 4 * cc < d.p2 && (unsigned)y < (unsigned)d.bv_h)
-                    cp_async16(Ob + rr * TW + 4 * cc, orig + (ptrdiff_t)y * orig_pitch + (x0 + 4 * cc));
-            }
+            uint32_t* t = odst + buf * RB * TW;
+            if (o_on && (unsigned)oy < (unsigned)d.bv_h) cp_async16(t, op);
+            if (o_on && (unsigned)(oy + 4) < (unsigned)d.bv_h) cp_async16(t + 4 * TW, op + 4 * (ptrdiff_t)orig_pitch);
+            op += (ptrdiff_t)RB * orig_pitch;
+            oy += RB;
         }
         cp_async_commit();
     };
-    stage_async(r_begin, 0);
+    stage_async(0);
 
-    // table columns beyond the thread's own: the 2*HA halo columns of the RP row pairs, spread over the threads
-    // (recomputed per block instead of held in registers across the walk)
-    constexpr int NX = 2 * HA * RP;
-    constexpr int NXT = (NX + TW - 1) / TW;
-    auto halo_elem = [&](int q, int& pr, int& col) -> bool {
-        const int e = tid + q * TW;
-        pr = e / (2 * HA);
-        const int k = e - pr * 2 * HA;
-        col = k < HA ? k : TW + k;                                       // left halo 0..HA-1, right halo TW+HA..TE-1
-        return e < NX;
-    };
+    // ---- output addressing: one running pointer per thread; threads next to the seam also own one halo column
+    const int gx = x0 + tid;                       // this thread's packed column
+    const bool col_ok = gx < d.p2;
+    const uint32_t lane_mask = (gx + d.p2 < d.bv_w) ? 0xFFFFFFFFu : 0x0000FFFFu;
+    // halo copy for the pass that reads a padded dst (pad 0): column gx - p2 = {0, v.lo}, column gx + p2 = {v.hi, 0}
+    int hoff = 0;
+    uint32_t hsel = 0;
+    if (dst_padded && col_ok) {
+        if (gx >= d.p2 - LT_HALO_X) { hoff = -d.p2; hsel = 0x1044u; }
+        else if (gx < LT_HALO_X) { hoff = d.p2; hsel = 0x4432u; }
+    }
+    uint32_t* dp = dst + (ptrdiff_t)(yb0 - 2 * R) * dst_pitch + gx;     // row of the first (unemitted) walk output
 
     uint32_t A[K];
 #pragma unroll
@@ -178,22 +184,30 @@ morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict
     auto o2 = [](uint2 a, uint2 b) { return make_uint2(op2<IS_MAX>(a.x, b.x), op2<IS_MAX>(a.y, b.y)); };
     auto o3 = [](uint2 a, uint2 b, uint2 c) { return make_uint2(op3<IS_MAX>(a.x, b.x, c.x), op3<IS_MAX>(a.y, b.y, c.y)); };
 
+    // table columns beyond the thread's own: the 2*HA halo columns of the RP row pairs, spread over the threads
+    constexpr int NX = 2 * HA * RP;
+    constexpr int NXT = (NX + TW - 1) / TW;
+    auto halo_elem = [&](int q, int& pr, int& col) -> bool {
+        const int e = tid + q * TW;
+        pr = e / (2 * HA);
+        const int k = e - pr * 2 * HA;
+        col = k < HA ? k : TW + k;                                       // left halo 0..HA-1, right halo TW+HA..TE-1
+        return e < NX;
+    };
+
     for (int blk = 0; blk < nblk; ++blk) {
         const int rb0 = r_begin + blk * RB;
         const uint32_t* Tc = T0 + (blk & 1) * RB * TE;                   // this block's source rows
         cp_async_wait_all();
         __syncthreads();                                                 // rows landed; previous walk finished
-        if (blk + 1 < nblk) stage_async(rb0 + RB, (blk + 1) & 1);
+        if (blk + 1 < nblk) stage_async((blk + 1) & 1);
         // window tables: T4 (from the raw rows) -> T8, T16, T32
         auto build4 = [&](int pr, int col, int idx) {
             const uint32_t* ra = Tc + (2 * pr) * TE + col;
             const uint32_t* rb = ra + TE;
-            uint32_t a0 = ra[0], b0 = rb[0];
-            uint32_t a1 = col + 1 < TE ? ra[1] : PAD2, b1 = col + 1 < TE ? rb[1] : PAD2;
-            uint32_t a2 = col + 2 < TE ? ra[2] : PAD2, b2 = col + 2 < TE ? rb[2] : PAD2;
-            uint32_t a3 = col + 3 < TE ? ra[3] : PAD2, b3 = col + 3 < TE ? rb[3] : PAD2;
             // raw lanes are plain values (or the 16-bit pad): their low bytes are the table bytes
-            T4[idx] = __byte_perm(op2<IS_MAX>(op3<IS_MAX>(a0, a1, a2), a3), op2<IS_MAX>(op3<IS_MAX>(b0, b1, b2), b3), 0x6240);
+            T4[idx] = __byte_perm(op2<IS_MAX>(op3<IS_MAX>(ra[0], ra[1], ra[2]), ra[3]),
+                                  op2<IS_MAX>(op3<IS_MAX>(rb[0], rb[1], rb[2]), rb[3]), 0x6240);
         };
         auto build81632 = [&](int idx) {
             const uint32_t* t = T4 + idx;
@@ -214,26 +228,19 @@ morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict
         for (int q = 0; q < NXT; ++q) { int pr, col; if (halo_elem(q, pr, col)) build81632(pr * TEA + col); }
         __syncthreads();
         // walk the RP row pairs of this block
+        const int npair = min(RP, (r_end - rb0 + 1) >> 1);
+        const uint32_t* Ob = OG + (blk & 1) * RB * TW + tid;
+        const uint32_t* Tw = Tc + tid + HA;
+        int base = tid + HA;                        // this thread's column in the tables of pair m
 #pragma unroll 1
-        for (int m = 0; m < RP; ++m) {
-            const int r = rb0 + 2 * m;              // source rows r (a) and r+1 (b)
-            if (r >= r_end) break;
-            const int ya = r - R;                   // output rows completed by this pair: ya and ya+1
-            const bool emit_a = col_ok && ya >= yb0 && ya < yb1;
-            const bool emit_b = col_ok && ya + 1 >= yb0 && ya + 1 < yb1;
-            uint32_t oga = 0, ogb = 0;
-            if (TOPHAT) {
-                const uint32_t* Ob = OG + (blk & 1) * RB * TW + (2 * m) * TW + tid;
-                oga = Ob[0]; ogb = Ob[TW];
-            }
-            const int base = m * TEA + tid + HA;    // this thread's column in the tables
+        for (int m = 0; m < npair; ++m, base += TEA, Tw += 2 * TE, Ob += 2 * TW, dp += 2 * (ptrdiff_t)dst_pitch) {
             uint32_t Ha[E::ND], Hb[E::ND];
 #pragma unroll
             for (int u = 0; u < E::ND; ++u) {
                 const int w = E::uniq(u);
                 const int len = 2 * w + 1;
                 uint2 h;
-                if (w == 0) h = make_uint2(Tc[(2 * m) * TE + tid + HA] << 8, Tc[(2 * m + 1) * TE + tid + HA] << 8);
+                if (w == 0) h = make_uint2(Tw[0] << 8, Tw[TE] << 8);
                 else if (len >= 32) h = o2(lanes(T32[base - w]), lanes(T32[base + w - 31]));
                 else if (len >= 16) h = o2(lanes(T16[base - w]), lanes(T16[base + w - 15]));
                 else h = o2(lanes(T8[base - w]), lanes(T8[base + w - 7]));
@@ -246,20 +253,23 @@ morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict
                 A[j] = op3<IS_MAX>(A[j + 2], Ha[ell_uidx<K>(E::hw(j + 1))], Hb[ell_uidx<K>(E::hw(j))]);
             A[K - 2] = op2<IS_MAX>(Ha[ell_uidx<K>(E::hw(K - 1))], Hb[ell_uidx<K>(E::hw(K - 2))]);
             A[K - 1] = Hb[ell_uidx<K>(E::hw(K - 1))];
-            auto emit = [&](int y, uint32_t v256) {
-                uint32_t v = __byte_perm(v256, 0, 0x4341);               // scale 256 -> plain values
-                if (TOPHAT) v = (y == ya ? oga : ogb) - v;               // open <= src per lane: no borrow between lanes
-                v &= lane_mask;                                          // hi lane beyond the image: 0 (the pad of the
-                uint32_t* row = dst + (ptrdiff_t)y * dst_pitch;          // dilation that consumes an eroded plane)
-                row[gx] = v;
-                if (dst_padded) {                                        // seam-stitched halo copies for the next pass
-                    if (gx >= d.p2 - LT_HALO_X) row[gx - d.p2] = (v << 16) | PAD_NEXT;
-                    if (gx < LT_HALO_X) row[gx + d.p2] = (gx + d.p2 < d.bv_w) ? (v >> 16) | (PAD_NEXT << 16) : PAD_NEXT | (PAD_NEXT << 16);
-                }
-            };
-            if (emit_a) emit(ya, out_a);
-            if (emit_b) emit(ya + 1, A[0]);
+            // the pair completes output rows ya = rb0 + 2m - R (dp points at it) and ya + 1
+            const int ya = rb0 + 2 * m - R;
+            if (ya + 1 < yb0 || ya >= yb1 || !col_ok) continue;
+            uint32_t va = __byte_perm(out_a, 0, 0x4341), vb = __byte_perm(A[0], 0, 0x4341);   // scale 256 -> plain values
+            if (TOPHAT) { va = Ob[0] - va; vb = Ob[TW] - vb; }          // open <= src per lane: no borrow between lanes
+            va &= lane_mask;                                             // hi lane beyond the image: 0 (the pad of the
+            vb &= lane_mask;                                             // dilation that consumes an eroded plane)
+            uint32_t* const pb = dp + dst_pitch;
+            const bool ea = ya >= yb0, eb = ya + 1 < yb1;
+            if (ea) dp[0] = va;
+            if (eb) pb[0] = vb;
+            if (dst_padded && hsel) {                                    // seam-stitched halo copies for the next pass
+                if (ea) dp[hoff] = __byte_perm(va, 0, hsel);
+                if (eb) pb[hoff] = __byte_perm(vb, 0, hsel);
+            }
         }
+        dp += 2 * (ptrdiff_t)(RP - npair) * dst_pitch;                   // (only the last block is short)
     }
 }
 
@@ -276,7 +286,7 @@ constexpr size_t morph_smem_bytes(bool tophat) {
     constexpr int TE = MORPH_TW + 2 * MorphHa<K>::value;
     constexpr int NTAB = (2 * R + 1 >= 32) ? 4 : 3;
     return ((size_t)NTAB * (MORPH_RB / 2) * (TE + 32) + (size_t)2 * MORPH_RB * TE +
-            (tophat ? 2 * MORPH_RB * MORPH_TW : 0)) * sizeof(uint32_t);
+            (tophat ? 2 * MORPH_RB * MORPH_TW : 0) + 4) * sizeof(uint32_t);
 }
 
 template <bool IS_MAX, bool TOPHAT>
