@@ -119,7 +119,7 @@ extern "C" int lt_destroy(lt_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->cfg.device);
     void* ptrs[] = {h->und_map, h->bv_map, h->ov_map, h->bv_desc, h->fused_desc, h->lab_gamma, h->lab_cbrt, h->und_roi, h->pad_alloc[0], h->pad_alloc[1],
-                    h->pad_alloc[2], h->pad_alloc[3], h->topR, h->topB, h->merged, h->mask, h->pixels, h->pix_counts, h->lane_rows,
+                    h->pad_alloc[2], h->pad_alloc[3], h->pad_alloc[4], h->pad_alloc[5], h->merged, h->mask, h->pixels, h->pix_counts, h->lane_rows,
                     h->avg_x, h->state, h->att, h->retry_list, h->retry_count, h->draw_flags, h->scratch_bv,
                     h->cap_pixels, h->cap_counts, h->cap_cents, h->cap_ncents,
                     h->txt_tables, h->txt_char_start, h->txt_dy, h->txt_dx, h->txt_lut, h->txt_advance, h->txt_pair_overlap,
@@ -154,7 +154,6 @@ extern "C" int lt_create(const lt_config* cfg, lt_handle** out) {
     d.img_w = cfg->img_w; d.img_h = cfg->img_h; d.bv_w = cfg->bv_w; d.bv_h = cfg->bv_h;
     d.p2 = 32 * ((cfg->bv_w + 63) / 64);
     d.mwords = 2 * d.p2 / 32;
-    h->stream_plane = (size_t)d.bv_h * d.p2;
     d.pp = d.p2 + 2 * LT_HALO_X;
     h->stream_pad = (size_t)(d.bv_h + 2 * LT_HALO_Y) * d.pp;
     h->stream_mask = (size_t)d.bv_h * d.mwords;
@@ -212,16 +211,16 @@ extern "C" int lt_create(const lt_config* cfg, lt_handle** out) {
     {
         // padded planes: + one row of slack (the last tile of a row block stages a few entries past the row end)
         const size_t n = S * h->stream_pad + d.pp, origin = (size_t)LT_HALO_Y * d.pp + LT_HALO_X;
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 6; ++i) {
             A(pad_alloc[i], n);
             if (!rc) cudaMemsetAsync(h->pad_alloc[i], i < 2 ? 0xFF : 0x00, n * sizeof(uint32_t), st);   // pad of erode / dilate
         }
         if (!rc) {
             h->planeR = h->pad_alloc[0] + origin; h->planeB = h->pad_alloc[1] + origin;
             h->tmpR = h->pad_alloc[2] + origin;   h->tmpB = h->pad_alloc[3] + origin;
+            h->topR = h->pad_alloc[4] + origin;   h->topB = h->pad_alloc[5] + origin;
         }
     }
-    A(topR, S * h->stream_plane); A(topB, S * h->stream_plane);
     A(merged, S * h->stream_mask); A(mask, S * h->stream_mask);
     A(pixels, S * 2 * (size_t)h->pix_cap); A(pix_counts, S * 2);
     A(lane_rows, S * (size_t)d.bv_h); A(avg_x, S * 2 * (size_t)d.bv_h);
@@ -716,9 +715,7 @@ extern "C" int64_t lt_debug_read(lt_handle* h, int32_t what, int32_t id, void* d
             lt_handle one = *h;     // view of this stream as slot 0
             if (what <= 6) {
                 const uint32_t* pl = what == 3 ? h->planeR : what == 4 ? h->planeB : what == 5 ? h->topR : h->topB;
-                const bool padded = what <= 4;
-                rc = lt_launch_plane_to_u8(&one, pl + (size_t)id * (padded ? h->stream_pad : h->stream_plane),
-                                           padded ? d.pp : d.p2, tmp, 1, 0);
+                rc = lt_launch_plane_to_u8(&one, pl + (size_t)id * h->stream_pad, d.pp, tmp, 1, 0);
             } else {
                 const uint32_t* bits = what == 7 ? h->mask : h->merged;
                 rc = lt_launch_mask_to_u8(&one, bits + (size_t)id * h->stream_mask, tmp, 1, 0);

@@ -26,12 +26,12 @@ struct LtDims {
     int pp;           // row pitch of the PADDED pair planes (morphology inputs) = p2 + 2*LT_HALO_X
 };
 
-// Padded pair planes (planeR/planeB/tmpR/tmpB): every row carries LT_HALO_X extra entries on either side that hold
+// Padded pair planes (all six of them): every row carries LT_HALO_X extra entries on either side that hold
 // the seam-stitched neighbour columns (the two strips of a pair plane are adjacent in the image) or the pad value
 // of the morphological pass that reads the plane, and every stream carries LT_HALO_Y pad rows above and below.
 // The plane pointers in lt_handle address (stream 0, row 0, column 0); negative offsets reach the halo.
 constexpr int LT_HALO_X = 32;     // multiple of 4 (16-byte staging) >= 28
-constexpr int LT_HALO_Y = 36;     // >= 27 + MORPH_RB - 1
+constexpr int LT_HALO_Y = 48;     // >= 27 + MORPH_RB - 1; the row-padded fast path of k_cross_v needs k + 8
 
 // Per-stream tracking state on the device (lane_tracker.py:139-176).
 struct LtDevState {
@@ -74,8 +74,8 @@ struct lt_handle {
     uchar4* und_roi;             // [S][roi rows][img_w]
     uint32_t* planeR; uint32_t* planeB;     // padded [S][bv_h + 2*LT_HALO_Y][pp]; lanes beyond the image / halo: 0xFFFF
     uint32_t* tmpR;   uint32_t* tmpB;       // padded eroded planes; lanes beyond the image / halo: 0
-    uint32_t* pad_alloc[4];                 // the allocations behind the four padded planes
-    uint32_t* topR;   uint32_t* topB;       // [S][bv_h][p2] top-hat planes / box row sums
+    uint32_t* topR;   uint32_t* topB;       // padded top-hat planes / box row sums; halo and pad rows: 0
+    uint32_t* pad_alloc[6];                 // the allocations behind the six padded planes
     uint32_t* merged; uint32_t* mask;       // [S][bv_h][mwords]
     uint32_t* pixels;            // [S][2][pix_cap]
     int pix_cap;
@@ -98,7 +98,6 @@ struct lt_handle {
     unsigned char* txt_pair_overlap;   // [nchars][nchars]: glyph b drawn right after glyph a shares pixels with it
     cudaEvent_t* prof_ev; int* prof_stage; int prof_cap, prof_n, prof_active, prof_calls, prof_max_calls;
     uint8_t* scratch_bv;         // lazily allocated [S][bv_h][bv_w][3] for stage calls
-    size_t stream_plane;         // entries per stream in a plain pair plane
     size_t stream_pad;           // entries per stream in a padded pair plane
     size_t stream_mask;          // words per stream in a bit mask
 };

@@ -10,6 +10,8 @@
 // the row from two table reads each, and folds them into a K-deep register pipeline
 // A[j] = op(A[j+1], Hop_{hw[j]}) whose head is a finished output row.  All min/max are
 // single VIMNMX(3).U16x2 instructions.
+#include <cstdlib>
+#include <cstdio>
 #include <algorithm>
 #include <functional>
 #include <vector>
@@ -303,11 +305,11 @@ k_morph_pair(MorphJob j55, MorphJob j29, LtDims d, int tiles, int n, size_t src_
     const int tile = tb % tiles, band = tb / tiles;
     if (count != nullptr && slot >= *count) return;
     const int s = list ? list[slot] : slot;
-    // erosion: padded plane -> padded plane; dilation + top-hat: padded plane -> plain top-hat plane
+    // all planes are padded; only the eroded planes (read by the dilation) need their column halos written
     const uint32_t* src = j.src + (size_t)s * src_stride;
     uint32_t* dst = j.dst + (size_t)s * dst_stride;
     const uint32_t* orig = TOPHAT ? j.orig + (size_t)s * src_stride : nullptr;
-    const int dst_pitch = TOPHAT ? d.p2 : d.pp;
+    const int dst_pitch = d.pp;
     if (big) morph_body<55, IS_MAX, TOPHAT>(src, d.pp, dst, dst_pitch, !TOPHAT, orig, d.pp, d, j.band_rows, tile, band);
     else morph_body<29, IS_MAX, TOPHAT>(src, d.pp, dst, dst_pitch, !TOPHAT, orig, d.pp, d, j.band_rows, tile, band);
 }
@@ -318,6 +320,15 @@ static void choose_bands(lt_handle* h, int n, int tiles, int H, int slots, int* 
     if (h->bands_key[0] == n && h->bands_key[1] == H && h->bands_key[2] == slots) { *b55 = h->bands_val[0]; *b29 = h->bands_val[1]; return; }
     int c55 = 1, c29 = 1;
     double best = 1e300;
+    if (const char* ov = getenv("LT_MORPH_BANDS")) {      // tuning knob: "b55,b29"
+        if (sscanf(ov, "%d,%d", &c55, &c29) == 2 && c55 >= 1 && c29 >= 1) {
+            h->bands_key[0] = n; h->bands_key[1] = H; h->bands_key[2] = slots;
+            h->bands_val[0] = c55; h->bands_val[1] = c29;
+            *b55 = c55; *b29 = c29;
+            return;
+        }
+        c55 = c29 = 1;
+    }
     std::vector<double> freeat;
     for (int a = 1; a <= 24; ++a)
         for (int b = 1; b <= 24; ++b) {
@@ -358,7 +369,7 @@ static int launch_morph_pair(lt_handle* h, MorphJob j55, MorphJob j29, int n, co
     j29.band_rows = lt_div_up(d.bv_h, b29); j29.bands = lt_div_up(d.bv_h, j29.band_rows);
     const int grid = n * tiles * (j55.bands + j29.bands);
     k_morph_pair<IS_MAX, TOPHAT><<<grid, MORPH_TW, smem, st>>>(j55, j29, d, tiles, n, h->stream_pad,
-                                                               TOPHAT ? h->stream_plane : h->stream_pad, list, count);
+                                                               h->stream_pad, list, count);
     LT_LAUNCH_CHECK();
     return 0;
 }
@@ -549,24 +560,36 @@ k_cross_h_wide(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bi
 // Vertical half: one thread per packed column walks a band of rows with running sums U, D (packed u16x2);
 // the plane rows each step needs are fetched CV_CHUNK steps ahead so that the loads stay in flight.
 // PACKED: k*255 + C*k + 1 < 2^15, the compare is done on both lanes at once with a guard bit.
+// ROWPAD: k + CV_CHUNK <= LT_HALO_Y, every row the walk touches exists in the padded plane (pad rows are zero, which
+//         is the filter's border), so loads carry no bounds logic.
+// The pass bits of a row are gathered with one ballot per strip; lane (y mod 32) keeps the words of row y and every
+// 32 rows all lanes flush theirs with one RED.OR each (instead of a divergent single-lane store per row).
 constexpr int CV_CHUNK = 8;
+constexpr int CV_BAND = 128;        // rows per CTA (multiple of 32)
 
-template <bool PACKED>
+template <bool PACKED, bool ROWPAD>
 __global__ void __launch_bounds__(32)
 k_cross_v(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_all, LtDims d, int k, int C,
-          int band_rows, int ppitch, size_t plane_stride, size_t bits_stride, const int* __restrict__ list,
+          int ppitch, size_t plane_stride, size_t bits_stride, const int* __restrict__ list,
           const int* __restrict__ count) {
     int slot = blockIdx.z;
     if (count != nullptr && slot >= *count) return;
     int s = list ? list[slot] : slot;
-    int lane = threadIdx.x;
-    int x = blockIdx.x * 32 + lane;              // packed column; p2 is a multiple of 32
-    int yb0 = blockIdx.y * band_rows, yb1 = min(yb0 + band_rows, d.bv_h);
-    const uint32_t* P = plane_all + (size_t)s * plane_stride + x;
+    const int lane = threadIdx.x;
+    const int x = blockIdx.x * 32 + lane;              // packed column; p2 is a multiple of 32
+    const int yb0 = blockIdx.y * CV_BAND, yb1 = min(yb0 + CV_BAND, d.bv_h);
+    const char* P = reinterpret_cast<const char*>(plane_all + (size_t)s * plane_stride + x);
+    const ptrdiff_t pitchB = (ptrdiff_t)ppitch * 4;
     uint32_t* bits = bits_all + (size_t)s * bits_stride;
     const bool hi_ok = x + d.p2 < d.bv_w;
-    auto ld = [&](int r) -> uint32_t { return ((unsigned)r < (unsigned)d.bv_h) ? __ldg(&P[(size_t)r * ppitch]) : 0u; };
-    uint32_t U = 0, D = 0;
+    auto ld = [&](int r) -> uint32_t {
+        if (ROWPAD) return __ldg(reinterpret_cast<const uint32_t*>(P + r * pitchB));
+        return ((unsigned)r < (unsigned)d.bv_h) ? __ldg(reinterpret_cast<const uint32_t*>(P + r * pitchB)) : 0u;
+    };
+    const int Ck = C * k;
+    const uint32_t kk = (uint32_t)k, bias = (uint32_t)(Ck + 1) * 0x00010001u;
+    // running sums carry the compare bias: pass <=> k*p >= U + C*k + 1 (and the same for D), per lane
+    uint32_t U = PACKED ? bias : 0u, D = U;
     for (int i0 = 1; i0 <= k; i0 += CV_CHUNK) {  // initial window sums, CV_CHUNK rows per side in flight
         uint32_t a[CV_CHUNK], b[CV_CHUNK];
 #pragma unroll
@@ -578,36 +601,41 @@ k_cross_v(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_al
 #pragma unroll
         for (int j = 0; j < CV_CHUNK; ++j) { U += a[j]; D += b[j]; }
     }
-    const int Ck = C * k;
-    const uint32_t kk = (uint32_t)k, bias = (uint32_t)(Ck + 1) * 0x00010001u;
     uint32_t p = ld(yb0);
+    uint32_t keep_l = 0, keep_h = 0;
     for (int yc = yb0; yc < yb1; yc += CV_CHUNK) {
         uint32_t pc[CV_CHUNK], pu[CV_CHUNK], pd[CV_CHUNK];
 #pragma unroll
         for (int j = 0; j < CV_CHUNK; ++j) { pc[j] = ld(yc + j + 1); pu[j] = ld(yc + j - k); pd[j] = ld(yc + j + k + 1); }
 #pragma unroll
         for (int j = 0; j < CV_CHUNK; ++j) {
-            const int y = yc + j;
             bool pl, ph;
             if (PACKED) {
-                uint32_t T = (p * kk) | 0x80008000u;
-                uint32_t ok = (T - (U + bias)) & (T - (D + bias));
-                pl = (ok >> 15) & 1u;
-                ph = hi_ok && (ok >> 31);
+                // lanes hold values < 2^15: bit 15 of ((A | 0x8000) - B) is set iff A >= B, per lane
+                uint32_t T = p * kk + 0x80008000u;
+                uint32_t ok = (T - U) & (T - D);
+                pl = (ok & 0x8000u) != 0;
+                ph = hi_ok && ((int)ok < 0);
             } else {
                 int tl = k * (int)(p & 0xFFFFu) - Ck, th = k * (int)(p >> 16) - Ck;
                 pl = ((int)(U & 0xFFFFu) < tl) && ((int)(D & 0xFFFFu) < tl);
                 ph = hi_ok && ((int)(U >> 16) < th) && ((int)(D >> 16) < th);
             }
             uint32_t bl = __ballot_sync(0xFFFFFFFFu, pl), bh = __ballot_sync(0xFFFFFFFFu, ph);
-            if (lane == 0 && y < yb1) {
-                uint32_t* brow = bits + (size_t)y * d.mwords;     // fire-and-forget RED.OR: no load to wait for
-                if (bl) atomicOr(&brow[blockIdx.x], bl);
-                if (bh) atomicOr(&brow[blockIdx.x + (d.p2 >> 5)], bh);
-            }
+            if (lane == ((yc + j) & 31)) { keep_l = bl; keep_h = bh; }
             U = U + p - pu[j];                    // lanes stay in [0, 65535]: add first, then subtract
             D = D + pd[j] - pc[j];
             p = pc[j];
+        }
+        const int ynext = yc + CV_CHUNK;
+        if ((ynext & 31) == 0 || ynext >= yb1) {        // lane r holds row (ynext - 1 rounded down to 32) + r
+            const int y = ((ynext - 1) & ~31) + lane;
+            if (y < yb1) {
+                uint32_t* brow = bits + (size_t)y * d.mwords;     // fire-and-forget RED.OR: no load to wait for
+                if (keep_l) atomicOr(&brow[blockIdx.x], keep_l);
+                if (keep_h) atomicOr(&brow[blockIdx.x + (d.p2 >> 5)], keep_h);
+            }
+            keep_l = keep_h = 0;
         }
     }
 }
@@ -631,7 +659,7 @@ k_box_h(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ hs_all, L
     for (int slot = blockIdx.y; slot < nsl; slot += gridDim.y) {
         const int s = list ? list[slot] : slot;
         warp_row_prefix(plane_all + (size_t)s * plane_stride + (size_t)y * ppitch, d, lin, E, lane);
-        uint32_t* hrow = hs_all + (size_t)s * hs_stride + (size_t)y * d.p2;
+        uint32_t* hrow = hs_all + (size_t)s * hs_stride + (size_t)y * ppitch;
         const int W = d.bv_w;
         const uint32_t first = lin[0], last = lin[W - 1];
         auto rowsum = [&](int c) -> uint32_t {
@@ -662,7 +690,7 @@ k_box_v(const uint32_t* __restrict__ plane_all, const uint32_t* __restrict__ hs_
     const uint32_t* Hs = hs_all + (size_t)s * hs_stride + x;
     uint32_t* bits = bits_all + (size_t)s * bits_stride;
     const bool hi_ok = x + d.p2 < d.bv_w;
-    auto ldh = [&](int r) -> uint32_t { r = max(0, min(d.bv_h - 1, r)); return __ldg(&Hs[(size_t)r * d.p2]); };
+    auto ldh = [&](int r) -> uint32_t { r = max(0, min(d.bv_h - 1, r)); return __ldg(&Hs[(size_t)r * ppitch]); };
     uint32_t Sl = 0, Sh = 0;
     for (int dy = -half; dy <= half; ++dy) { uint32_t v = ldh(yb0 + dy); Sl += v & 0xFFFFu; Sh += v >> 16; }
     const uint32_t n = (uint32_t)(2 * half + 1) * (uint32_t)(2 * half + 1);
@@ -818,7 +846,7 @@ int lt_launch_u8_to_mask(lt_handle* h, const uint8_t* d_mask, uint32_t* bits, in
 }
 int lt_launch_plane_to_u8(lt_handle* h, const uint32_t* plane, int pitch, uint8_t* d_dst, int n, cudaStream_t st) {
     dim3 g(lt_div_up(h->d.bv_w, 256), h->d.bv_h, n);
-    k_plane_to_u8<<<g, 256, 0, st>>>(plane, d_dst, h->d, pitch, pitch == h->d.p2 ? h->stream_plane : h->stream_pad);
+    k_plane_to_u8<<<g, 256, 0, st>>>(plane, d_dst, h->d, pitch, h->stream_pad);
     LT_LAUNCH_CHECK();
     return 0;
 }
@@ -827,11 +855,11 @@ int lt_launch_plane_to_u8(lt_handle* h, const uint32_t* plane, int pitch, uint8_
 // the whole filter for one attempt
 // ---------------------------------------------------------------------------
 
-static int launch_cross(lt_handle* h, const uint32_t* plane, bool padded, uint32_t* bits, int k, int C, int accumulate, int n,
+static int launch_cross(lt_handle* h, const uint32_t* plane, uint32_t* bits, int k, int C, int accumulate, int n,
                         const int* list, const int* count, cudaStream_t st) {
     const LtDims& d = h->d;
-    const int ppitch = padded ? d.pp : d.p2;
-    const size_t pstride = padded ? h->stream_pad : h->stream_plane;
+    const int ppitch = d.pp;
+    const size_t pstride = h->stream_pad;
     if (k <= 127 && C >= 0 && k * 255 + C * k + 1 < 32768) {   // packed u16 lanes must stay below 2^15
         int pitch = d.p2 + 2 * k + 2;
         while (((pitch >> 1) & 1) == 0 || (pitch & 1)) ++pitch;       // pitch = 2 * odd: rows land in distinct banks
@@ -852,12 +880,15 @@ static int launch_cross(lt_handle* h, const uint32_t* plane, bool padded, uint32
                                                             h->stream_mask, list, count);
         LT_LAUNCH_CHECK();
     }
-    int band_rows = 128;
-    dim3 gv(d.p2 / 32, lt_div_up(d.bv_h, band_rows), n);
-    if (k <= 127 && C >= 0 && k * 255 + C * k + 1 < 32768)
-        k_cross_v<true><<<gv, 32, 0, st>>>(plane, bits, d, k, C, band_rows, ppitch, pstride, h->stream_mask, list, count);
-    else
-        k_cross_v<false><<<gv, 32, 0, st>>>(plane, bits, d, k, C, band_rows, ppitch, pstride, h->stream_mask, list, count);
+    dim3 gv(d.p2 / 32, lt_div_up(d.bv_h, CV_BAND), n);
+    const bool packed = k <= 127 && C >= 0 && k * 255 + C * k + 1 < 32768;
+    const bool rowpad = k + CV_CHUNK <= LT_HALO_Y;
+#define LT_CROSS_V(PK, RP) k_cross_v<PK, RP><<<gv, 32, 0, st>>>(plane, bits, d, k, C, ppitch, pstride, h->stream_mask, list, count)
+    if (packed && rowpad) LT_CROSS_V(true, true);
+    else if (packed) LT_CROSS_V(true, false);
+    else if (rowpad) LT_CROSS_V(false, true);
+    else LT_CROSS_V(false, false);
+#undef LT_CROSS_V
     LT_LAUNCH_CHECK();
     return 0;
 }
@@ -871,11 +902,11 @@ static int launch_box(lt_handle* h, const uint32_t* plane, uint32_t* hs, uint32_
     int half = block / 2;
     const int zs = list ? (n < 8 ? n : 8) : n;      // retry-list launches: few slots, each CTA loops over the list
     dim3 gh(lt_div_up(d.bv_h, ROWK_WARPS), zs);
-    k_box_h<<<gh, ROWK_WARPS * 32, smem, st>>>(plane, hs, d, half, d.pp, h->stream_pad, h->stream_plane, list, count, n);
+    k_box_h<<<gh, ROWK_WARPS * 32, smem, st>>>(plane, hs, d, half, d.pp, h->stream_pad, h->stream_pad, list, count, n);
     LT_LAUNCH_CHECK();
     int band_rows = 64;
     dim3 gv(d.p2 / 32, lt_div_up(d.bv_h, band_rows), zs);
-    k_box_v<<<gv, 32, 0, st>>>(plane, hs, bits, d, half, c, accumulate, band_rows, d.pp, h->stream_pad, h->stream_plane, h->stream_mask,
+    k_box_v<<<gv, 32, 0, st>>>(plane, hs, bits, d, half, c, accumulate, band_rows, d.pp, h->stream_pad, h->stream_pad, h->stream_mask,
                                list, count, n);
     LT_LAUNCH_CHECK();
     return 0;
@@ -892,9 +923,9 @@ int lt_launch_filter(lt_handle* h, int n, const LtAttemptParams& p, const int* l
         MorphJob t55 = {h->tmpB, h->topB, h->planeB, 0, 0}, t29 = {h->tmpR, h->topR, h->planeR, 0, 0};
         if ((rc = launch_morph_pair<true, true>(h, t55, t29, n, list, count, st))) return rc;
         lt_prof_mark(h, ST_TOPHAT55, st);           // both dilations + top-hat epilogues in one launch
-        if ((rc = launch_cross(h, h->topR, false, h->merged, p.ksize_r, p.C_r, 0, n, list, count, st))) return rc;
+        if ((rc = launch_cross(h, h->topR, h->merged, p.ksize_r, p.C_r, 0, n, list, count, st))) return rc;
         lt_prof_mark(h, ST_CROSS_R, st);
-        if ((rc = launch_cross(h, h->topB, false, h->merged, p.ksize_b, p.C_b, 1, n, list, count, st))) return rc;
+        if ((rc = launch_cross(h, h->topB, h->merged, p.ksize_b, p.C_b, 1, n, list, count, st))) return rc;
         lt_prof_mark(h, ST_CROSS_B, st);
     } else {
         if ((rc = launch_box(h, h->planeR, h->topR, h->merged, p.ksize_r, p.C_r, 0, n, list, count, st))) return rc;
@@ -902,7 +933,7 @@ int lt_launch_filter(lt_handle* h, int n, const LtAttemptParams& p, const int* l
         lt_prof_mark(h, ST_BOX, st);
     }
     if (p.mask_noise) {
-        if ((rc = launch_cross(h, h->planeB, true, h->mask, p.ksize_noise, p.C_noise, 0, n, list, count, st))) return rc;
+        if ((rc = launch_cross(h, h->planeB, h->mask, p.ksize_noise, p.C_noise, 0, n, list, count, st))) return rc;
         dim3 g(d.p2 / 32, d.bv_h, n);
         k_noise_combine<<<g, 32, 0, st>>>(h->planeB, h->mask, h->merged, d, p.noise_thresh, d.pp, h->stream_pad,
                                           h->stream_mask, list, count);
