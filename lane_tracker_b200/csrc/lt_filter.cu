@@ -104,7 +104,8 @@ morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict
     constexpr int R = E::R;
     constexpr int TW = MORPH_TW, RB = MORPH_RB, RP = RB / 2, HA = MorphHa<K>::value;
     constexpr int TE = TW + 2 * HA;         // staged columns per row; column i <-> packed column x0 - HA + i
-    constexpr int TEA = TE + 32;            // + slack that always holds PAD
+    constexpr int TEA = TE + 32;            // table row pitch: + slack for the window reads of the last columns
+    constexpr int TEP = TE + 4;             // raw row pitch: + slack read (never written, never used) by the last T4 columns
     constexpr bool HAS32 = (2 * R + 1) >= 32;
     constexpr int NTAB = HAS32 ? 4 : 3;     // T4, T8, T16 (, T32)
     constexpr uint32_t PADL = IS_MAX ? 0u : 0xFFFFu;
@@ -116,8 +117,8 @@ morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict
     uint32_t* T8 = T4 + RP * TEA;
     uint32_t* T16 = T8 + RP * TEA;
     uint32_t* T32 = T16 + RP * TEA;                     // only touched when HAS32
-    uint32_t* T0 = smem + NTAB * RP * TEA;              // [2 buffers][RB rows][TE] raw source rows (row-major)
-    uint32_t* OG = T0 + 2 * RB * TE;                    // [2 buffers][RB rows][TW] original rows (top-hat epilogue)
+    uint32_t* T0 = smem + NTAB * RP * TEA;              // [2 buffers][RB rows][TEP] raw source rows (row-major)
+    uint32_t* OG = T0 + 2 * RB * TEP;                    // [2 buffers][RB rows][TW] original rows (top-hat epilogue)
 
     const int tid = threadIdx.x;
     const int x0 = tile * TW;
@@ -137,7 +138,7 @@ morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict
     const int sg = tid >> 6, sc = tid & 63;
     const bool s_on = sc < CH;
     const uint32_t* sp = src + (ptrdiff_t)(r_begin + sg) * src_pitch + (x0 - HA + 4 * sc);    // advances RB rows per block
-    uint32_t* const sdst = T0 + sg * TE + 4 * sc;
+    uint32_t* const sdst = T0 + sg * TEP + 4 * sc;
     // original rows for the top-hat epilogue: 48 chunks per row, thread -> (row tid / 48 and + 4, chunk tid % 48)
     const int orow = tid / 48, oc = tid - orow * 48;
     const bool o_on = TOPHAT && x0 + 4 * oc < d.p2;
@@ -146,10 +147,10 @@ morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict
     int oy = r_begin - R + orow;                                        // image row of this thread's first original row
     auto stage_async = [&](int buf) {
         if (s_on) {
-            uint32_t* t = sdst + buf * RB * TE;
+            uint32_t* t = sdst + buf * RB * TEP;
             cp_async16(t, sp);
-            cp_async16(t + 3 * TE, sp + 3 * (ptrdiff_t)src_pitch);
-            if (sg < 2) cp_async16(t + 6 * TE, sp + 6 * (ptrdiff_t)src_pitch);
+            cp_async16(t + 3 * TEP, sp + 3 * (ptrdiff_t)src_pitch);
+            if (sg < 2) cp_async16(t + 6 * TEP, sp + 6 * (ptrdiff_t)src_pitch);
         }
         sp += (ptrdiff_t)RB * src_pitch;
         if (TOPHAT) {
@@ -199,14 +200,14 @@ morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict
 
     for (int blk = 0; blk < nblk; ++blk) {
         const int rb0 = r_begin + blk * RB;
-        const uint32_t* Tc = T0 + (blk & 1) * RB * TE;                   // this block's source rows
+        const uint32_t* Tc = T0 + (blk & 1) * RB * TEP;                  // this block's source rows
         cp_async_wait_all();
         __syncthreads();                                                 // rows landed; previous walk finished
         if (blk + 1 < nblk) stage_async((blk + 1) & 1);
         // window tables: T4 (from the raw rows) -> T8, T16, T32
         auto build4 = [&](int pr, int col, int idx) {
-            const uint32_t* ra = Tc + (2 * pr) * TE + col;
-            const uint32_t* rb = ra + TE;
+            const uint32_t* ra = Tc + (2 * pr) * TEP + col;
+            const uint32_t* rb = ra + TEP;
             // raw lanes are plain values (or the 16-bit pad): their low bytes are the table bytes
             T4[idx] = __byte_perm(op2<IS_MAX>(op3<IS_MAX>(ra[0], ra[1], ra[2]), ra[3]),
                                   op2<IS_MAX>(op3<IS_MAX>(rb[0], rb[1], rb[2]), rb[3]), 0x6240);
@@ -235,14 +236,14 @@ morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict
         const uint32_t* Tw = Tc + tid + HA;
         int base = tid + HA;                        // this thread's column in the tables of pair m
 #pragma unroll 1
-        for (int m = 0; m < npair; ++m, base += TEA, Tw += 2 * TE, Ob += 2 * TW, dp += 2 * (ptrdiff_t)dst_pitch) {
+        for (int m = 0; m < npair; ++m, base += TEA, Tw += 2 * TEP, Ob += 2 * TW, dp += 2 * (ptrdiff_t)dst_pitch) {
             uint32_t Ha[E::ND], Hb[E::ND];
 #pragma unroll
             for (int u = 0; u < E::ND; ++u) {
                 const int w = E::uniq(u);
                 const int len = 2 * w + 1;
                 uint2 h;
-                if (w == 0) h = make_uint2(Tw[0] << 8, Tw[TE] << 8);
+                if (w == 0) h = make_uint2(Tw[0] << 8, Tw[TEP] << 8);
                 else if (len >= 32) h = o2(lanes(T32[base - w]), lanes(T32[base + w - 31]));
                 else if (len >= 16) h = o2(lanes(T16[base - w]), lanes(T16[base + w - 15]));
                 else h = o2(lanes(T8[base - w]), lanes(T8[base + w - 7]));
@@ -287,8 +288,8 @@ constexpr size_t morph_smem_bytes(bool tophat) {
     constexpr int R = Ellipse<K>::R;
     constexpr int TE = MORPH_TW + 2 * MorphHa<K>::value;
     constexpr int NTAB = (2 * R + 1 >= 32) ? 4 : 3;
-    return ((size_t)NTAB * (MORPH_RB / 2) * (TE + 32) + (size_t)2 * MORPH_RB * TE +
-            (tophat ? 2 * MORPH_RB * MORPH_TW : 0) + 4) * sizeof(uint32_t);
+    return ((size_t)NTAB * (MORPH_RB / 2) * (TE + 32) + (size_t)2 * MORPH_RB * (TE + 4) +
+            (tophat ? 2 * MORPH_RB * MORPH_TW : 0)) * sizeof(uint32_t);
 }
 
 template <bool IS_MAX, bool TOPHAT>
