@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define LT_ABI_VERSION 2
+#define LT_ABI_VERSION 3
 #define LT_MAX_AVERAGE 8          /* capacity of the n_average rings */
 
 typedef struct lt_handle lt_handle;
@@ -237,6 +237,35 @@ int lt_get_poly_points(lt_handle* h, const double* d_fits, int32_t n_streams, do
  * polygon of the given polylines, un-warps and blends it.  d_x/d_counts as above. */
 int lt_draw_lane(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int32_t n_streams,
                  const int32_t* d_x, const int32_t* d_counts, void* stream);
+
+/* ---- debug views (lane_tracker.py:675-793, utils.py:57-103; not on the per-frame path) ---- */
+
+/* cv2.warpPerspective(img, M, warped_size) of the RAW frames (lane_tracker.py:1035, the middle panel of the
+ * split view): d_frames [n][img_h][img_w][3] -> d_bv_rgb [n][bv_h][bv_w][3]. */
+int lt_warp_frame(lt_handle* h, const uint8_t* d_frames, int32_t n_streams, uint8_t* d_bv_rgb, void* stream);
+
+typedef struct lt_vis {
+    int32_t mode;               /* 0: visualize_sliding_window_search (:689-729), 1: visualize_band_search (:731-771) */
+    int32_t n_left, n_right;    /* lane pixels of the search (left_y/left_x, right_y/right_x) */
+    int32_t n_rects;            /* mode 0: search windows, <= 2 * LT_MAX_LEVELS */
+    int32_t bandwidth;          /* mode 1 */
+    int32_t reserved0;
+    double  partial;            /* mode 1: `partial` of the band polylines */
+    double  band_left[3], band_right[3];   /* mode 1: last_left_coeffs / last_right_coeffs the band was built on */
+    double  left_fit[3], right_fit[3];     /* the new fit, drawn as graph points in (255, 235, 0) */
+} lt_vis;
+
+/* One search visualisation image, d_vis [bv_h][bv_w][3], from the binary image d_mask u8 [bv_h][bv_w], the lane
+ * pixel lists (device, packed y << 16 | (x + 32768) as produced by lt_sliding_window_search / lt_band_search) and,
+ * in mode 0, the search windows as HOST int32 [n_rects][5] = {row0, row1, col0, col1, side (0 left, 1 right)},
+ * half-open, i.e. window_mask (:675-687) with Python's slice rules already applied. */
+int lt_visualize_search(lt_handle* h, const lt_vis* v, const uint8_t* d_mask, const uint32_t* d_left,
+                        const uint32_t* d_right, const int32_t* h_rects, uint8_t* d_vis, void* stream);
+
+/* cv2.resize(img, dsize) as called by utils.create_split_view (utils.py:88): uint8, INTER_LINEAR, 1 or 3 channels.
+ * Pitches in bytes, so that the destination can be a panel of a larger canvas. Runs on the current device. */
+int lt_resize_linear(const uint8_t* d_src, int32_t src_w, int32_t src_h, int32_t channels, int64_t src_pitch,
+                     uint8_t* d_dst, int32_t dst_w, int32_t dst_h, int64_t dst_pitch, void* stream);
 
 /* ---- state access (tests, checkpoint/restore) ------------------------------ */
 int lt_get_state(lt_handle* h, int32_t stream_id, lt_state* h_state, int32_t* h_left_avg_x,

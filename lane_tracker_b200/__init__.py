@@ -4,9 +4,10 @@ The tracker classes need the in-tree CUDA library (liblane_tracker_b200.so) and 
 importing them without either raises.  ``lane_tracker_b200.synth`` (test/bench data) and
 ``lane_tracker_b200.utils`` (calibration loaders) are plain NumPy.
 """
-from .utils import load_camera_calib, load_warp_params  # noqa: F401
+from .utils import create_split_view, load_camera_calib, load_warp_params  # noqa: F401
 
-__all__ = ["LaneTracker", "BatchedLaneTracker", "HostPipeline", "load_camera_calib", "load_warp_params"]
+__all__ = ["LaneTracker", "BatchedLaneTracker", "HostPipeline", "load_camera_calib", "load_warp_params",
+           "create_split_view"]
 
 
 def __getattr__(name):

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "liblane_tracker_b200.so")
 
 LT_MAX_AVERAGE = 8
 LT_MAX_LEVELS = 128
-LT_ABI_VERSION = 2
+LT_ABI_VERSION = 3
 LT_NSTAGES = 16
 
 i32, f64 = C.c_int32, C.c_double
@@ -65,6 +65,13 @@ class lt_validity(C.Structure):
 
 # every symbol include/lane_tracker_b200.h declares: (restype, argtypes)
 P = C.c_void_p
+class lt_vis(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("n_left", C.c_int32), ("n_right", C.c_int32), ("n_rects", C.c_int32),
+                ("bandwidth", C.c_int32), ("reserved0", C.c_int32), ("partial", C.c_double),
+                ("band_left", C.c_double * 3), ("band_right", C.c_double * 3),
+                ("left_fit", C.c_double * 3), ("right_fit", C.c_double * 3)]
+
+
 SIGNATURES = {
     "lt_create": (C.c_int, [C.POINTER(lt_config), C.POINTER(P)]),
     "lt_destroy": (C.c_int, [P]),
@@ -93,6 +100,9 @@ SIGNATURES = {
     "lt_check_validity": (C.c_int, [P, P, i32, P, P, P]),
     "lt_get_poly_points": (C.c_int, [P, P, i32, f64, P, P, P]),
     "lt_draw_lane": (C.c_int, [P, P, P, i32, P, P, P]),
+    "lt_warp_frame": (C.c_int, [P, P, i32, P, P]),
+    "lt_visualize_search": (C.c_int, [P, C.POINTER(lt_vis), P, P, P, P, P, P]),
+    "lt_resize_linear": (C.c_int, [P, i32, i32, i32, C.c_int64, P, i32, i32, C.c_int64, P]),
     "lt_get_state": (C.c_int, [P, i32, C.POINTER(lt_state), P, P]),
     "lt_set_state": (C.c_int, [P, i32, C.POINTER(lt_state), P, P]),
     "lt_debug_read": (C.c_int64, [P, i32, i32, P, C.c_int64]),

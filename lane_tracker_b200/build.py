@@ -20,6 +20,7 @@ SOURCES = {
     "lt_remap.cu": ["-fmad=false"],
     "lt_filter.cu": [],
     "lt_search.cu": ["-fmad=false"],
+    "lt_vis.cu": ["-fmad=false"],
 }
 
 

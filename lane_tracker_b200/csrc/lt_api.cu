@@ -120,7 +120,7 @@ extern "C" int lt_destroy(lt_handle* h) {
     cudaSetDevice(h->cfg.device);
     void* ptrs[] = {h->und_map, h->bv_map, h->ov_map, h->bv_desc, h->fused_desc, h->lab_gamma, h->lab_cbrt, h->und_roi, h->pad_alloc[0], h->pad_alloc[1],
                     h->pad_alloc[2], h->pad_alloc[3], h->pad_alloc[4], h->pad_alloc[5], h->merged, h->mask, h->pixels, h->pix_counts, h->lane_rows,
-                    h->avg_x, h->state, h->att, h->retry_list, h->retry_count, h->draw_flags, h->scratch_bv,
+                    h->avg_x, h->state, h->att, h->retry_list, h->retry_count, h->draw_flags, h->scratch_bv, h->vis_scratch,
                     h->cap_pixels, h->cap_counts, h->cap_cents, h->cap_ncents,
                     h->txt_tables, h->txt_char_start, h->txt_dy, h->txt_dx, h->txt_lut, h->txt_advance, h->txt_pair_overlap,
                     h->txt_bitmaps};
@@ -650,6 +650,75 @@ extern "C" int lt_draw_lane(lt_handle* h, const uint8_t* d_frames, uint8_t* d_ou
 // ---------------------------------------------------------------------------
 // state and debug access (synchronous)
 // ---------------------------------------------------------------------------
+
+// ---------------------------------------------------------------------------
+// debug views
+// ---------------------------------------------------------------------------
+
+extern "C" int lt_warp_frame(lt_handle* h, const uint8_t* d_frames, int32_t n, uint8_t* d_bv_rgb, void* stream) {
+    if (!h || !d_frames || !d_bv_rgb) { lt_set_error("null argument"); return -1; }
+    LT_CUDA(cudaSetDevice(h->cfg.device));
+    int rc;
+    if ((rc = check_any_n(h, n))) return rc;
+    return lt_launch_warp_frame(h, d_frames, d_bv_rgb, n, (cudaStream_t)stream);
+}
+
+extern "C" int lt_visualize_search(lt_handle* h, const lt_vis* v, const uint8_t* d_mask, const uint32_t* d_left,
+                                   const uint32_t* d_right, const int32_t* h_rects, uint8_t* d_vis, void* stream) {
+    if (!h || !v || !d_mask || !d_vis) { lt_set_error("null argument"); return -1; }
+    if (v->mode != 0 && v->mode != 1) { lt_set_error("lt_vis.mode must be 0 (sliding window) or 1 (band)"); return -1; }
+    if (v->n_left < 0 || v->n_right < 0 || (v->n_left && !d_left) || (v->n_right && !d_right)) { lt_set_error("bad pixel lists"); return -1; }
+    if (v->n_rects < 0 || v->n_rects > 2 * LT_MAX_LEVELS || (v->n_rects && !h_rects)) { lt_set_error("n_rects outside [0, %d]", 2 * LT_MAX_LEVELS); return -1; }
+    if (v->mode == 1 && !(v->partial >= 0.0 && v->partial <= 1.0)) { lt_set_error("partial must lie in [0, 1]"); return -1; }
+    LT_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const LtDims& d = h->d;
+    const int W = d.bv_w, H = d.bv_h;
+    // work area: rects | fits [2][2][3] | xs [2 calls][2][H] | counts [2][2] | rows [2][H]
+    const size_t o_fits = (size_t)5 * 2 * LT_MAX_LEVELS * sizeof(int), o_xs = o_fits + 12 * sizeof(double),
+                 o_cnt = o_xs + (size_t)4 * H * sizeof(int), o_rows = o_cnt + 4 * sizeof(int),
+                 total = o_rows + (size_t)2 * H * sizeof(int2);
+    if (!h->vis_scratch) LT_CUDA(cudaMalloc((void**)&h->vis_scratch, total));
+    int* d_rects = reinterpret_cast<int*>(h->vis_scratch);
+    double* d_fits = reinterpret_cast<double*>(h->vis_scratch + o_fits);
+    int* d_xs = reinterpret_cast<int*>(h->vis_scratch + o_xs);
+    int* d_cnt = reinterpret_cast<int*>(h->vis_scratch + o_cnt);
+    int2* d_rows = reinterpret_cast<int2*>(h->vis_scratch + o_rows);
+    double fits[12];
+    for (int j = 0; j < 3; ++j) {
+        fits[j] = v->left_fit[j]; fits[3 + j] = v->right_fit[j];
+        fits[6 + j] = v->band_left[j]; fits[9 + j] = v->band_right[j];
+    }
+    LT_CUDA(cudaMemcpyAsync(d_fits, fits, sizeof(fits), cudaMemcpyHostToDevice, st));
+    const int nrect = v->mode == 0 ? v->n_rects : 0;
+    if (nrect) LT_CUDA(cudaMemcpyAsync(d_rects, h_rects, (size_t)nrect * 5 * sizeof(int), cudaMemcpyHostToDevice, st));
+    LT_CUDA(cudaStreamSynchronize(st));                       // fits / rects came from pageable host memory
+    const uint32_t RED = 255u, BLUE = 255u << 16, YELLOW = 255u | (235u << 8);
+    int rc;
+    if ((rc = lt_launch_vis_base(d_mask, d_rects, nrect, W, H, d_vis, st))) return rc;
+    // later writes win: left pixels, then right pixels (lane_tracker.py:720-721 / :745-746)
+    if ((rc = lt_launch_vis_scatter(d_left, v->n_left, W, H, RED, d_vis, st))) return rc;
+    if ((rc = lt_launch_vis_scatter(d_right, v->n_right, W, H, BLUE, d_vis, st))) return rc;
+    if (v->mode == 1) {
+        if ((rc = lt_launch_poly_points(h, d_fits + 6, 1, v->partial, d_xs + 2 * H, d_cnt + 2, st))) return rc;
+        if ((rc = lt_launch_band_rows(h, d_xs + 2 * H, d_cnt + 2, v->bandwidth, d_rows, d_rows + H, st))) return rc;
+        if ((rc = lt_launch_vis_band_blend(d_rows, d_rows + H, W, H, d_vis, st))) return rc;
+    }
+    if ((rc = lt_launch_poly_points(h, d_fits, 1, 1.0, d_xs, d_cnt, st))) return rc;
+    if ((rc = lt_launch_vis_scatter_poly(d_xs, d_cnt, W, H, YELLOW, d_vis, st))) return rc;
+    if ((rc = lt_launch_vis_scatter_poly(d_xs + H, d_cnt + 1, W, H, YELLOW, d_vis, st))) return rc;
+    return 0;
+}
+
+extern "C" int lt_resize_linear(const uint8_t* d_src, int32_t sw, int32_t sh, int32_t cn, int64_t src_pitch, uint8_t* d_dst,
+                                int32_t dw, int32_t dh, int64_t dst_pitch, void* stream) {
+    if (!d_src || !d_dst) { lt_set_error("null argument"); return -1; }
+    if (sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0 || (cn != 1 && cn != 3) || src_pitch < (int64_t)sw * cn || dst_pitch < (int64_t)dw * cn) {
+        lt_set_error("lt_resize_linear: sizes must be positive, channels 1 or 3, pitches >= row bytes");
+        return -1;
+    }
+    return lt_launch_resize_linear(d_src, sw, sh, cn, (size_t)src_pitch, d_dst, dw, dh, (size_t)dst_pitch, (cudaStream_t)stream);
+}
 
 extern "C" int lt_get_state(lt_handle* h, int32_t id, lt_state* hs, int32_t* h_lx, int32_t* h_rx) {
     if (!h || !hs || id < 0 || id >= h->S) { lt_set_error("bad argument"); return -1; }

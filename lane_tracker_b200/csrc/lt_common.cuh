@@ -98,6 +98,7 @@ struct lt_handle {
     unsigned char* txt_pair_overlap;   // [nchars][nchars]: glyph b drawn right after glyph a shares pixels with it
     cudaEvent_t* prof_ev; int* prof_stage; int prof_cap, prof_n, prof_active, prof_calls, prof_max_calls;
     uint8_t* scratch_bv;         // lazily allocated [S][bv_h][bv_w][3] for stage calls
+    unsigned char* vis_scratch;  // lazily allocated work area of lt_visualize_search
     size_t stream_pad;           // entries per stream in a padded pair plane
     size_t stream_mask;          // words per stream in a bit mask
 };
@@ -169,6 +170,16 @@ int lt_launch_poly_points(lt_handle* h, const double* d_fits, int n, double part
                           cudaStream_t st);
 int lt_launch_lane_rows(lt_handle* h, const int* d_x, const int* d_counts, int n, cudaStream_t st);
 int lt_launch_text(lt_handle* h, uint8_t* d_out, int n, cudaStream_t st);
+// debug views (lt_vis.cu, and the two helpers that live next to the code they reuse)
+int lt_launch_warp_frame(lt_handle* h, const uint8_t* d_frames, uint8_t* d_bv_rgb, int n, cudaStream_t st);
+int lt_launch_band_rows(lt_handle* h, const int* d_x, const int* d_counts, int bandwidth, int2* rows_l, int2* rows_r,
+                        cudaStream_t st);
+int lt_launch_vis_base(const uint8_t* d_mask, const int* d_rects, int nrect, int W, int H, uint8_t* d_out, cudaStream_t st);
+int lt_launch_vis_scatter(const uint32_t* d_px, int n, int W, int H, uint32_t rgb, uint8_t* d_out, cudaStream_t st);
+int lt_launch_vis_scatter_poly(const int* d_xs, const int* d_count, int W, int H, uint32_t rgb, uint8_t* d_out, cudaStream_t st);
+int lt_launch_vis_band_blend(const int2* rows_l, const int2* rows_r, int W, int H, uint8_t* d_out, cudaStream_t st);
+int lt_launch_resize_linear(const uint8_t* d_src, int sw, int sh, int cn, size_t src_pitch, uint8_t* d_dst, int dw, int dh,
+                            size_t dst_pitch, cudaStream_t st);
 
 enum LtStage { ST_BEGIN = 0, ST_UNDISTORT, ST_WARP, ST_ERODE55, ST_ERODE29, ST_TOPHAT55, ST_TOPHAT29, ST_CROSS_R,
                ST_CROSS_B, ST_BOX, ST_NOISE, ST_OPEN5, ST_SEARCH, ST_RETRY_SELECT, ST_UPDATE, ST_OVERLAY };

@@ -162,6 +162,26 @@ k_undistort_roi(const uint8_t* __restrict__ frames, uchar4* __restrict__ und, co
         make_uchar4(o & 255, (o >> 8) & 255, (o >> 16) & 255, 0);
 }
 
+// cv2.warpPerspective(img, M, warped_size) of the RAW frame (lane_tracker.py:1035, the split view's middle panel)
+__global__ void __launch_bounds__(256)
+k_warp_frame(const uint8_t* __restrict__ frames, uint8_t* __restrict__ bv_rgb, const int2* __restrict__ map, LtDims d) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, s = blockIdx.z;
+    if (x >= d.bv_w) return;
+    const uint8_t* img = frames + (size_t)s * d.img_w * d.img_h * 3;
+    Tap4 t = make_taps(__ldg(&map[(size_t)y * d.bv_w + x]));
+    uint32_t o = blend_rgb(load_rgb(img, d.img_w, d.img_h, t.sy, t.sx), load_rgb(img, d.img_w, d.img_h, t.sy, t.sx + 1),
+                           load_rgb(img, d.img_w, d.img_h, t.sy + 1, t.sx), load_rgb(img, d.img_w, d.img_h, t.sy + 1, t.sx + 1), t);
+    uint8_t* p = bv_rgb + (((size_t)s * d.bv_h + y) * d.bv_w + x) * 3;
+    p[0] = o & 255; p[1] = (o >> 8) & 255; p[2] = (o >> 16) & 255;
+}
+
+int lt_launch_warp_frame(lt_handle* h, const uint8_t* d_frames, uint8_t* d_bv_rgb, int n, cudaStream_t st) {
+    const LtDims& d = h->d;
+    k_warp_frame<<<dim3(lt_div_up(d.bv_w, 256), d.bv_h, n), 256, 0, st>>>(d_frames, d_bv_rgb, h->bv_map, d);
+    LT_LAUNCH_CHECK();
+    return 0;
+}
+
 int lt_launch_undistort(lt_handle* h, const uint8_t* d_frames, int n, cudaStream_t st) {
     const LtDims& d = h->d;
     dim3 g(lt_div_up(d.img_w, 256), d.roi1 - d.roi0, n);

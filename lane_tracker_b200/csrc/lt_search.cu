@@ -571,7 +571,7 @@ __device__ void lane_rows_from_polylines(const int* xl, int nl, const int* xr, i
             for (int dlt = -1; dlt <= 1; dlt += 2) {
                 int j = i + dlt;
                 if (j < 0 || j >= nn) continue;
-                int xa = xs[i], xb = xs[j];
+                int xa = min(max(xs[i], 0), W - 1), xb = min(max(xs[j], 0), W - 1);   // cv::clipLine, rows one apart
                 int adx = abs(xb - xa);
                 if (adx < 2) continue;
                 int xleft = min(xa, xb), half = adx / 2;
@@ -886,6 +886,32 @@ k_lane_rows(LtDims d, const int* __restrict__ xs, const int* __restrict__ counts
 
 int lt_launch_lane_rows(lt_handle* h, const int* d_x, const int* d_counts, int n, cudaStream_t st) {
     k_lane_rows<<<n, SEARCH_THREADS, 0, st>>>(h->d, d_x, d_counts, h->lane_rows, h->draw_flags);
+    LT_LAUNCH_CHECK();
+    return 0;
+}
+
+// Row spans of the two search-band polygons of visualize_band_search (lane_tracker.py:749-760): the polylines of
+// get_poly_points(last coeffs, partial) shifted by -/+ bandwidth.  Vertices may leave the canvas; cv::Line clips an edge
+// before it rasterises it, which for one-row-apart vertices equals clamping x (lane_rows_from_polylines).
+__global__ void __launch_bounds__(SEARCH_THREADS)
+k_band_rows(LtDims d, const int* __restrict__ xs, const int* __restrict__ counts, int bandwidth, int2* __restrict__ rows_l,
+            int2* __restrict__ rows_r) {
+    const int H = d.bv_h;
+    extern __shared__ unsigned char smem_raw[];
+    int* lo = reinterpret_cast<int*>(smem_raw);
+    int* hi = lo + H;
+    for (int side = 0; side < 2; ++side) {
+        const int n = counts[side];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { int x = xs[side * H + i]; lo[i] = x - bandwidth; hi[i] = x + bandwidth; }
+        __syncthreads();
+        lane_rows_from_polylines(lo, n, hi, n, d.bv_w, H, side ? rows_r : rows_l);
+        __syncthreads();
+    }
+}
+
+int lt_launch_band_rows(lt_handle* h, const int* d_x, const int* d_counts, int bandwidth, int2* rows_l, int2* rows_r,
+                        cudaStream_t st) {
+    k_band_rows<<<1, SEARCH_THREADS, (size_t)2 * h->d.bv_h * sizeof(int), st>>>(h->d, d_x, d_counts, bandwidth, rows_l, rows_r);
     LT_LAUNCH_CHECK();
     return 0;
 }

@@ -336,6 +336,55 @@ class BatchedLaneTracker:
                                     _stream_ptr(self.device)))
         return out
 
+    # -- debug views ---------------------------------------------------------
+    def warp_frame(self, frames):
+        """``cv2.warpPerspective(img, M, warped_size)`` of raw frames (lane_tracker.py:1035) -> [n, bv_h, bv_w, 3]."""
+        n = self._check_frames(frames)
+        bw, bh = self.warped_size
+        out = torch.empty((n, bh, bw, 3), dtype=torch.uint8, device=self.device)
+        check(self.lib.lt_warp_frame(self._h, _ptr(frames), n, _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def visualize_search(self, mask, mode, left, right, new_fits, rects=None, band_fits=None, bandwidth=0, partial=1.0):
+        """One search visualisation (lane_tracker.py:689-771).  mask: uint8 [bv_h, bv_w] tensor on the device;
+        left / right: (y, x) integer arrays; new_fits / band_fits: [2][3]; rects: int32 [n][5] (mode 'sws')."""
+        bw, bh = self.warped_size
+        if tuple(mask.shape) != (bh, bw) or mask.dtype != torch.uint8 or not mask.is_contiguous():
+            raise ValueError("mask must be a contiguous uint8 [%d, %d] tensor" % (bh, bw))
+        v = _lib.lt_vis()
+        v.mode = {"sws": 0, "bs": 1}[mode]
+        packed = []
+        for ys, xs in (left, right):
+            ys = np.asarray(ys, dtype=np.int64)
+            xs = np.asarray(xs, dtype=np.int64)
+            buf = ((ys << 16) | (xs + 32768)).astype(np.uint32)
+            packed.append(torch.as_tensor(buf.view(np.int32)).to(self.device) if len(buf) else None)
+        v.n_left, v.n_right = len(left[0]), len(right[0])
+        r = np.ascontiguousarray(rects if rects is not None else np.zeros((0, 5)), dtype=np.int32).reshape(-1, 5)
+        v.n_rects, v.bandwidth, v.partial = len(r), int(bandwidth), float(partial)
+        nf = np.asarray(new_fits, dtype=np.float64).reshape(2, 3)
+        bf = np.asarray(band_fits if band_fits is not None else np.zeros((2, 3)), dtype=np.float64).reshape(2, 3)
+        for j in range(3):
+            v.left_fit[j], v.right_fit[j] = nf[0, j], nf[1, j]
+            v.band_left[j], v.band_right[j] = bf[0, j], bf[1, j]
+        out = torch.empty((bh, bw, 3), dtype=torch.uint8, device=self.device)
+        check(self.lib.lt_visualize_search(self._h, C.byref(v), _ptr(mask), _ptr(packed[0]), _ptr(packed[1]),
+                                           r.ctypes.data_as(C.c_void_p), _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def resize_linear(self, src, dsize, out=None):
+        """``cv2.resize(src, dsize)`` (utils.py:88) of a uint8 [h, w] or [h, w, 3] device tensor; ``out`` may be a
+        view into a larger canvas (rows strided, pixels contiguous)."""
+        dw, dh = int(dsize[0]), int(dsize[1])
+        cn = 1 if src.dim() == 2 else int(src.shape[2])
+        if out is None:
+            out = torch.empty((dh, dw) if src.dim() == 2 else (dh, dw, cn), dtype=torch.uint8, device=src.device)
+        if src.stride(-1) != 1 or out.stride(-1) != 1 or tuple(out.shape[:2]) != (dh, dw):
+            raise ValueError("resize_linear: bad source / destination layout")
+        check(self.lib.lt_resize_linear(_ptr(src), int(src.shape[1]), int(src.shape[0]), cn, int(src.stride(0)),
+                                        _ptr(out), dw, dh, int(out.stride(0)), _stream_ptr(self.device)))
+        return out
+
     # -- state / debug -------------------------------------------------------
     def get_state(self, stream_id=0):
         st = lt_state()
@@ -523,9 +572,13 @@ class LaneTracker:
 
     NumPy arrays in, NumPy arrays out; every computation runs on the GPU.  Differences from the
     reference, all documented in DESIGN.md: the caller's ``img`` is never modified (the reference
-    draws its text into it), and the debug views (``visualize_search``, ``split_view``) raise
-    ``NotImplementedError``.
+    draws its text into it).  The debug views (``visualize_search``, ``split_view``) are rendered on the device
+    from the buffers of the last ``process`` call.
     """
+
+    # the second attempt's hard-coded search parameters (lane_tracker.py:1081-1099); the debug views of a frame
+    # that went to attempt 2 are drawn with these, as in the reference
+    _ATTEMPT2 = dict(window_width=30, window_height=40, ignore_bottom=30, bandwidth=30, partial=1.0)
 
     def __init__(self, img_size, warped_size, cam_matrix, dist_coeffs, warp_matrices, mpp_conversion,
                  n_fail=8, n_reset=4, n_average=2, print_frame_count=False, device=None):
@@ -626,9 +679,10 @@ class LaneTracker:
                 search_range=20, mu=0.1, no_success_limit=8, start_slice=0.25, ignore_sides=360,
                 ignore_bottom=30, bandwidth=25, partial=1.0, n_tries=2, visualize_search=False,
                 split_view=False, diagnostics=False):
-        """lane_tracker.py:876-1209.  Returns the annotated frame (new array)."""
-        if visualize_search or split_view:
-            raise NotImplementedError("debug views are outside the B200 hot path (SURVEY.md section 8f)")
+        """lane_tracker.py:876-1209.  Returns the annotated frame (new array); with ``visualize_search`` the tuple
+        (frame, search visualisation), with ``split_view`` the three-panel canvas (lane_tracker.py:1161-1173)."""
+        debug = bool(visualize_search | split_view)
+        band_coeffs = (self.last_left_coeffs, self.last_right_coeffs)      # what a band search of this frame uses
         p = make_params(ksize_r=ksize_r, C_r=C_r, ksize_b=ksize_b, C_b=C_b, filter_type=filter_type,
                         mask_noise=mask_noise, noise_thresh=noise_thresh, ksize_noise=ksize_noise,
                         C_noise=C_noise, window_width=window_width, window_height=window_height,
@@ -641,6 +695,7 @@ class LaneTracker:
             raise ValueError("img must be uint8 [%d, %d, 3]" % (h, w))
         self._in_host[0].numpy()[...] = a
         self._in_dev.copy_(self._in_host, non_blocking=True)
+        warped = self._bt.warp_frame(self._in_dev)[0] if debug else None   # lane_tracker.py:1035 (raw frame)
         self._bt.process_async(self._in_dev, self._out_dev, params=p)
         self._out_host.copy_(self._out_dev, non_blocking=True)
         res = self._bt.fetch_results(1)[0]
@@ -649,7 +704,82 @@ class LaneTracker:
         if diagnostics:
             print("attempts=%d mode=%s detected=%s valid=%s" % (res["attempts"], "bs" if res["search_mode"] else "sws",
                                                                 bool(res["detected_pixels"]), bool(res["valid_lane_lines"])))
-        return self._out_host[0].numpy().copy()
+        if not debug:
+            return self._out_host[0].numpy().copy()
+        # lane_tracker.py:1130-1138: the view of the LAST attempt, drawn with that attempt's parameters
+        q = dict(window_width=window_width, window_height=window_height, ignore_bottom=ignore_bottom,
+                 bandwidth=bandwidth, partial=partial)
+        if int(res["attempts"]) == 2:
+            q = self._ATTEMPT2
+        mask = torch.from_numpy(self._bt.debug_read("mask", 0)).to(self._bt.device)
+        if res["detected_pixels"]:
+            lf, rf = np.array(res["left_fit"]), np.array(res["right_fit"])
+            if res["search_mode"] == 0:
+                vis = self._vis_sws(mask, lf, rf, q["window_width"], q["window_height"], q["ignore_bottom"])
+            else:
+                vis = self._vis_bs(mask, lf, rf, q["bandwidth"], q["partial"], band_coeffs)
+        else:
+            vis = mask                                                     # 2-D, as in the reference
+        if visualize_search:
+            return self._out_host[0].numpy().copy(), vis.cpu().numpy()
+        return self._triple_split_view_dev([self._out_dev[0], warped, vis]).cpu().numpy()
+
+    # ------------------------------------------------------------ debug views
+    def window_mask(self, img, window_width, window_height, center, level, ignore_bottom):
+        """lane_tracker.py:675-687."""
+        output = np.zeros_like(img)
+        r0, r1, c0, c1 = self._window_rect(img.shape[:2], window_width, window_height, center, level, ignore_bottom)
+        output[r0:r1, c0:c1] = 1
+        return output
+
+    @staticmethod
+    def _window_rect(shape, window_width, window_height, center, level, ignore_bottom):
+        H, W = shape
+        img_height = H - ignore_bottom
+        rows = slice(int(img_height - (level + 1) * window_height), int(img_height - level * window_height)).indices(H)
+        cols = slice(max(int(center - window_width / 2), 0), min(int(center + window_width / 2), W)).indices(W)
+        return rows[0], max(rows[1], rows[0]), cols[0], max(cols[1], cols[0])
+
+    def _vis_sws(self, mask, left_fit, right_fit, window_width, window_height, ignore_bottom):
+        bw, bh = self._bt.warped_size
+        rects = []
+        for side, cents in enumerate((self.left_window_centroids, self.right_window_centroids)):
+            for level, c in enumerate(cents):
+                rects.append(self._window_rect((bh, bw), window_width, window_height, c, level, ignore_bottom) + (side,))
+        return self._bt.visualize_search(mask, "sws", (self.left_y, self.left_x), (self.right_y, self.right_x),
+                                         [left_fit, right_fit], rects=np.array(rects, dtype=np.int32).reshape(-1, 5))
+
+    def _vis_bs(self, mask, left_fit, right_fit, bandwidth, partial, band_coeffs):
+        return self._bt.visualize_search(mask, "bs", (self.left_y, self.left_x), (self.right_y, self.right_x),
+                                         [left_fit, right_fit], band_fits=band_coeffs, bandwidth=bandwidth,
+                                         partial=partial)
+
+    def visualize_sliding_window_search(self, binary_img, left_fit_coeffs, right_fit_coeffs, window_width,
+                                        window_height, ignore_bottom):
+        """lane_tracker.py:689-729 (uses left/right_window_centroids and the lane pixel sets of the last search)."""
+        return self._vis_sws(self._mask_dev(binary_img)[0], left_fit_coeffs, right_fit_coeffs, window_width,
+                             window_height, ignore_bottom).cpu().numpy()
+
+    def visualize_band_search(self, binary_img, left_fit_coeffs, right_fit_coeffs, bandwidth, partial):
+        """lane_tracker.py:731-771 (the band is drawn around last_left_coeffs / last_right_coeffs)."""
+        return self._vis_bs(self._mask_dev(binary_img)[0], left_fit_coeffs, right_fit_coeffs, bandwidth, partial,
+                            (self.last_left_coeffs, self.last_right_coeffs)).cpu().numpy()
+
+    def _triple_split_view_dev(self, images):
+        from .utils import create_split_view
+        img1_size = (int(images[0].shape[1]), int(images[0].shape[0]))
+        img2_size = (int(images[1].shape[1]), int(images[1].shape[0]))
+        positions = [(0, 0), (0, img1_size[1]), (round(0.5 * img1_size[0]), img1_size[1])]
+        scale_factor = img2_size[0] / (0.5 * img1_size[0])
+        scaled_size = (round(img2_size[0] / scale_factor), round(img2_size[1] / scale_factor))
+        target_size = (img1_size[0], img1_size[1] + scaled_size[1])
+        return create_split_view(target_size, images, positions, [img1_size, scaled_size, scaled_size],
+                                 _device=self._bt.device, _numpy=False)
+
+    def triple_split_view(self, images):
+        """lane_tracker.py:773-793."""
+        dev = [torch.as_tensor(np.ascontiguousarray(im, dtype=np.uint8)).to(self._bt.device) for im in images]
+        return self._triple_split_view_dev(dev).cpu().numpy()
 
     def find_lane_points(self, img, ksize_r=15, C_r=8, ksize_b=35, C_b=5, filter_type="bilateral",
                          mask_noise=True, noise_thresh=140, ksize_noise=65, C_noise=10, window_width=30,

@@ -374,6 +374,44 @@ def _line_pixels(x0, y0, x1, y1):
     return pts
 
 
+def _clip_line(width, height, x1, y1, x2, y2):
+    """``cv::clipLine`` (drawing.cpp): Cohen-Sutherland style clipping of a segment to the image rectangle with
+    OpenCV's truncating ``(int64)(double)`` intersections.  ``cv::Line`` clips before it rasterises, so a polygon
+    edge that leaves the canvas is drawn as the line between its *clipped* end points.  Returns None when the
+    segment is entirely outside."""
+    right, bottom = width - 1, height - 1
+
+    def code(x, y):
+        return (x < 0) + (x > right) * 2 + (y < 0) * 4 + (y > bottom) * 8
+
+    c1, c2 = code(x1, y1), code(x2, y2)
+    if (c1 & c2) == 0 and (c1 | c2) != 0:
+        if c1 & 12:
+            a = 0 if c1 < 8 else bottom
+            x1 += int(float(a - y1) * (x2 - x1) / (y2 - y1))
+            y1 = a
+            c1 = (x1 < 0) + (x1 > right) * 2
+        if c2 & 12:
+            a = 0 if c2 < 8 else bottom
+            x2 += int(float(a - y2) * (x2 - x1) / (y2 - y1))
+            y2 = a
+            c2 = (x2 < 0) + (x2 > right) * 2
+        if (c1 & c2) == 0 and (c1 | c2) != 0:
+            if c1:
+                a = 0 if c1 == 1 else right
+                y1 += int(float(a - x1) * (y2 - y1) / (x2 - x1))
+                x1 = a
+                c1 = 0
+            if c2:
+                a = 0 if c2 == 1 else right
+                y2 += int(float(a - x2) * (y2 - y1) / (x2 - x1))
+                x2 = a
+                c2 = 0
+    if (c1 | c2) != 0:
+        return None
+    return x1, y1, x2, y2
+
+
 def lane_polygon_rows(left_x, left_y, right_x, right_y, width, height):
     """Row spans ``[lo[y], hi[y]]`` covered by the reference's lane polygon.
 
@@ -405,7 +443,10 @@ def lane_polygon_rows(left_x, left_y, right_x, right_y, width, height):
     for i in range(n):
         x0, y0 = verts[i]
         x1, y1 = verts[(i + 1) % n]
-        for (x, y) in _line_pixels(x0, y0, x1, y1):
+        seg = _clip_line(width, height, x0, y0, x1, y1)
+        if seg is None:
+            continue
+        for (x, y) in _line_pixels(*seg):
             cover(y, x, x)
     # (i) rows where both polylines have a vertex
     L = {int(y): int(x) for x, y in zip(left_x, left_y)}
@@ -444,6 +485,46 @@ def lane_canvas(lo, hi, width, height):
         if hi[y] >= lo[y]:
             img[y, lo[y]:hi[y] + 1, 1] = 255
     return img
+
+
+def add_weighted(a, b, beta):
+    """``cv2.addWeighted(a, 1, b, beta, 0)`` on uint8 arrays: float32 arithmetic, round half to even, saturate
+    (lane_tracker.py:662 with beta 0.3, :717 with 0.5, :760 with 0.3)."""
+    f = a.astype(np.float32) + b.astype(np.float32) * np.float32(beta)
+    return np.clip(np.rint(f), 0, 255).astype(np.uint8)
+
+
+def resize_linear(img, dsize):
+    """``cv2.resize(img, dsize)`` (INTER_LINEAR, uint8, 1 or 3 channels; utils.py:88): OpenCV's fixed-point path.
+
+    Horizontal taps carry 11-bit weights ``rint(w * 2048)`` computed in float32 from ``(d + 0.5) * scale - 0.5``
+    (weight forced to 0 where the tap pair leaves the row); the vertical pass clamps ROW INDICES instead and
+    combines as ``(((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2``.  (An exact 2x shrink, which
+    OpenCV routes to INTER_AREA, gives the same integers.)"""
+    dw, dh = int(dsize[0]), int(dsize[1])
+    sh, sw = img.shape[:2]
+
+    def taps(dn, sn, vertical):
+        scale = sn / dn
+        d = np.arange(dn, dtype=np.float64)
+        f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+        s = np.floor(f).astype(np.int64)
+        f = (f - s.astype(np.float32)).astype(np.float32)
+        if not vertical:
+            f = np.where((s < 0) | (s >= sn - 1), np.float32(0), f).astype(np.float32)
+            s = np.clip(s, 0, sn - 1)
+        w1 = np.rint(f * np.float32(2048)).astype(np.int64)
+        w0 = np.rint((np.float32(1) - f) * np.float32(2048)).astype(np.int64)
+        return np.clip(s, 0, sn - 1), np.clip(s + 1, 0, sn - 1), w0, w1
+
+    x0, x1, a0, a1 = taps(dw, sw, False)
+    y0, y1, b0, b1 = taps(dh, sh, True)
+    src = img.astype(np.int64)
+    e = (None,) * (img.ndim - 2)
+    rows = src[:, x0] * a0[(None, slice(None)) + e] + src[:, x1] * a1[(None, slice(None)) + e]
+    out = (((b0[(slice(None), None) + e] * (rows[y0] >> 4)) >> 16) +
+           ((b1[(slice(None), None) + e] * (rows[y1] >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
 
 
 def add_weighted_03(img, lane):

@@ -395,6 +395,90 @@ class OracleLaneTracker:
         """lane_tracker.py:664-673."""
         return self._put_text(img, False)
 
+    # ---------------------------------------------------------- debug views
+    def window_rect(self, shape, window_width, window_height, center, level, ignore_bottom):
+        """Rows/columns set by ``window_mask`` (lane_tracker.py:675-687), Python slice semantics included."""
+        H, W = shape
+        img_height = H - ignore_bottom
+        r0, r1 = _pyslice(int(img_height - (level + 1) * window_height), int(img_height - level * window_height), H)
+        c0, c1 = _pyslice(max(int(center - window_width / 2), 0), min(int(center + window_width / 2), W), W)
+        return r0, r1, c0, c1
+
+    def visualize_sliding_window_search(self, binary_img, left_fit_coeffs, right_fit_coeffs, window_width,
+                                        window_height, ignore_bottom):
+        """lane_tracker.py:689-729."""
+        pts = []
+        for cents in (self.left_window_centroids, self.right_window_centroids):
+            m = np.zeros_like(binary_img)
+            for level, c in enumerate(cents):
+                r0, r1, c0, c1 = self.window_rect(binary_img.shape, window_width, window_height, c, level, ignore_bottom)
+                m[r0:r1, c0:c1] = 255
+            pts.append(m)
+        template = np.array(pts[1] + pts[0], np.uint8)          # uint8 sum: 255 + 255 wraps to 254
+        zero = np.zeros_like(template)
+        color = np.stack([binary_img] * 3, axis=-1)
+        tmpl3 = np.stack([zero, template, zero], axis=-1)
+        if self.backend == "cv2":
+            output = self._cv2.addWeighted(color, 1, tmpl3, 0.5, 0.0)
+        else:
+            output = cvops.add_weighted(color, tmpl3, 0.5)
+        output[self.left_y, self.left_x] = [255, 0, 0]
+        output[self.right_y, self.right_x] = [0, 0, 255]
+        ly, lx, ry, rx = self.get_poly_points(left_fit_coeffs, right_fit_coeffs)
+        output[ly, lx] = [255, 235, 0]
+        output[ry, rx] = [255, 235, 0]
+        return output
+
+    def visualize_band_search(self, binary_img, left_fit_coeffs, right_fit_coeffs, bandwidth, partial):
+        """lane_tracker.py:731-771."""
+        H, W = binary_img.shape
+        output = np.stack([binary_img] * 3, axis=-1)
+        window_img = np.zeros_like(output)
+        output[self.left_y, self.left_x] = [255, 0, 0]
+        output[self.right_y, self.right_x] = [0, 0, 255]
+        lby, lbx, rby, rbx = self.get_poly_points(self.last_left_coeffs, self.last_right_coeffs, partial)
+        if self.backend == "cv2":
+            cv2 = self._cv2
+            for bx, by in ((lbx, lby), (rbx, rby)):
+                w1 = np.array([np.transpose(np.vstack([bx - bandwidth, by]))])
+                w2 = np.array([np.flipud(np.transpose(np.vstack([bx + bandwidth, by])))])
+                cv2.fillPoly(window_img, np.int_([np.hstack((w1, w2))]), (0, 255, 0))
+            result = cv2.addWeighted(output, 1, window_img, 0.3, 0)
+        else:
+            for bx, by in ((lbx, lby), (rbx, rby)):
+                xl = np.int_(bx - bandwidth)
+                xr = np.int_(bx + bandwidth)
+                lo, hi = cvops.lane_polygon_rows(xl, by, xr, by, W, H)
+                window_img |= cvops.lane_canvas(lo, hi, W, H)
+            result = cvops.add_weighted(output, window_img, 0.3)
+        ly, lx, ry, rx = self.get_poly_points(left_fit_coeffs, right_fit_coeffs)
+        result[ly, lx] = [255, 235, 0]
+        result[ry, rx] = [255, 235, 0]
+        return result
+
+    def create_split_view(self, target_size, images, positions, sizes):
+        """utils.py:57-103 without captions (the tracker passes none)."""
+        x_max, y_max = target_size
+        canvas = np.zeros((y_max, x_max, 3), dtype=np.uint8)
+        for i, img in enumerate(images):
+            # the reference's condition, operator precedence included: a != (b | c) != d
+            if img.shape[0] != sizes[i][1] | img.shape[1] != sizes[i][0]:
+                img = self._cv2.resize(img, dsize=sizes[i]) if self.backend == "cv2" else cvops.resize_linear(img, sizes[i])
+            x, y = positions[i]
+            w, h = sizes[i]
+            canvas[y:min(y + h, y_max), x:min(x + w, x_max), :] = img[:min(h, y_max - y), :min(w, x_max - x)]
+        return canvas
+
+    def triple_split_view(self, images):
+        """lane_tracker.py:773-793."""
+        img1_size = (images[0].shape[1], images[0].shape[0])
+        img2_size = (images[1].shape[1], images[1].shape[0])
+        positions = [(0, 0), (0, img1_size[1]), (round(0.5 * img1_size[0]), img1_size[1])]
+        scale_factor = img2_size[0] / (0.5 * img1_size[0])
+        scaled_size = (round(img2_size[0] / scale_factor), round(img2_size[1] / scale_factor))
+        target_size = (img1_size[0], img1_size[1] + scaled_size[1])
+        return self.create_split_view(target_size, images, positions, [img1_size, scaled_size, scaled_size])
+
     # -------------------------------------------------------------- process
     def find_lane_points(self, img, **kw):
         """lane_tracker.py:795-874."""
@@ -418,10 +502,20 @@ class OracleLaneTracker:
         return mask, "bs"
 
     def process(self, img, **kw):
-        """lane_tracker.py:876-1209 (no debug views)."""
+        """lane_tracker.py:876-1209, debug views (``visualize_search`` / ``split_view``) included."""
         p = dict(PROCESS_DEFAULTS)
         p.update(kw)
         n_tries = p.pop("n_tries")
+        visualize_search = p.pop("visualize_search", False)
+        split_view = p.pop("split_view", False)
+        warped_img = None
+        if visualize_search | split_view:
+            # lane_tracker.py:1035: bird's-eye view of the RAW frame (not undistorted), before any text is drawn
+            if self.backend == "cv2":
+                warped_img = self._cv2.warpPerspective(img, self.M, self.warped_size, flags=self._cv2.INTER_LINEAR,
+                                                       borderMode=self._cv2.BORDER_CONSTANT)
+            else:
+                warped_img = cvops.warp_perspective(img, self.M, self.warped_size)
         self.counter += 1
         self.detected_pixels = False
         self.valid_lane_lines = False
@@ -443,6 +537,26 @@ class OracleLaneTracker:
             rec["valid"] = self.valid_lane_lines
             rec["bv"] = self.trace.get("bv")
             self.trace["attempts"].append(rec)
+        vis = None
+        if visualize_search | split_view:                       # lane_tracker.py:1130-1138
+            if self.detected_pixels:
+                if mode == "sws":
+                    vis = self.visualize_sliding_window_search(mask, lf, rf, p["window_width"], p["window_height"],
+                                                               p["ignore_bottom"])
+                else:
+                    vis = self.visualize_band_search(mask, lf, rf, p["bandwidth"], p["partial"])
+            else:
+                vis = mask
+            self.trace["search_visualization"] = vis
+            self.trace["warped_img"] = warped_img
+
+        def finish(out):
+            if visualize_search:
+                return out, vis
+            if split_view:
+                return self.triple_split_view([out, warped_img, vis])
+            return out
+
         if not self.valid_lane_lines:
             self.left_fit_coeffs.append(np.array([]))
             self.right_fit_coeffs.append(np.array([]))
@@ -454,8 +568,8 @@ class OracleLaneTracker:
                 self.average_curve_radii.pop(0)
             self.last_detection += 1
             if (self.left_avg_y.size != 0) & (self.last_detection <= self.n_fail):
-                return self.draw_lane(img)
-            return self.print_failure(img)
+                return finish(self.draw_lane(img))
+            return finish(self.print_failure(img))
         self.left_fit_coeffs.append(lf)
         self.right_fit_coeffs.append(rf)
         self.last_left_coeffs, self.last_right_coeffs = lf, rf
@@ -470,4 +584,4 @@ class OracleLaneTracker:
             self.get_poly_points(self.left_avg_coeffs, self.right_avg_coeffs, p["partial"])
         self.get_curve_radius()
         self.get_eccentricity()
-        return self.draw_lane(img)
+        return finish(self.draw_lane(img))

@@ -106,9 +106,37 @@ def stage_record(ref, frame):
     return rec
 
 
+def debug_views_record():
+    """Reference debug views (visualize_search / split_view, lane_tracker.py:689-793, 1130-1209) on an 8-frame
+    sequence: sliding-window frame, band-search frames, a two-frame outage (attempt 2, still pixels) and recovery."""
+    outage = load_frame(os.path.join(HERE, "frames", "test2.jpg"))
+    vid = synth.RoadVideo(1)
+    frames = [("synth", t) for t in range(5)] + [("outage", 5), ("outage", 6), ("synth", 7)]
+    rec = dict(seed=1, outage_frame="test2.jpg", frames=[[k, t] for k, t in frames], visualize_search=[], split_view=[])
+    for mode in ("visualize_search", "split_view"):
+        ref = _liveref.make_tracker()
+        for kind, t in frames:
+            f = outage if kind == "outage" else vid.frame(t)
+            r = _liveref.quiet(ref.process, f.copy(), **{mode: True})
+            if mode == "visualize_search":
+                rec[mode].append(dict(out=sha(r[0]), vis=sha(r[1]), vis_shape=list(r[1].shape)))
+            else:
+                rec[mode].append(dict(canvas=sha(r), shape=list(r.shape)))
+            print(mode, kind, t, rec[mode][-1])
+    return rec
+
+
 def main():
     warnings.simplefilter("ignore")
     import cv2
+    if "--debug-views-only" in sys.argv:            # refresh one section, keep the rest of the file
+        with open(os.path.join(HERE, "golden.json")) as f:
+            gold = json.load(f)
+        gold["debug_views"] = debug_views_record()
+        with open(os.path.join(HERE, "golden.json"), "w") as f:
+            json.dump(gold, f, indent=1)
+        print("updated golden.json: debug_views")
+        return
     gold = dict(meta=dict(cv2=cv2.__version__, numpy=np.__version__, text_box=list(TEXT_BOX),
                           generator="tests/golden/make_golden.py", reference="pierluigiferrari/lane_tracker"))
     gold["images"] = {}
@@ -138,6 +166,7 @@ def main():
     gold["scenario"] = dict(seed=0, frames=seq, outage_frame="test2.jpg", outage=[14, 26])
     ratio = ref.get_success_ratio()
     gold["scenario"]["success_ratio"] = [float(ratio[0]), int(ratio[1]), int(ratio[2])]
+    gold["debug_views"] = debug_views_record()
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(gold, f, indent=1)
     print("wrote golden.json")

@@ -35,21 +35,22 @@ def test_exports_every_declared_symbol(lib):
     for n in names:
         assert hasattr(lib, n), "library does not export %s" % n
         assert n in _lib.SIGNATURES, "binding does not cover %s" % n
-    assert lib.lt_abi_version() == 2
+    assert lib.lt_abi_version() == _lib.LT_ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header(tmp_path, lib):
     from lane_tracker_b200 import _lib
     prog = tmp_path / "sz.c"
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lane_tracker_b200.h"\n'
-                    'int main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(lt_config), sizeof(lt_params),'
+                    'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(lt_config), sizeof(lt_params),'
                     'sizeof(lt_result), sizeof(lt_state), offsetof(lt_result, left_fit), offsetof(lt_state, last_left),'
-                    'offsetof(lt_params, partial));return 0;}\n')
+                    'offsetof(lt_params, partial), sizeof(lt_vis), offsetof(lt_vis, left_fit));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(_lib.lt_config), C.sizeof(_lib.lt_params), C.sizeof(_lib.lt_result), C.sizeof(_lib.lt_state),
-            _lib.lt_result.left_fit.offset, _lib.lt_state.last_left.offset, _lib.lt_params.partial.offset]
+            _lib.lt_result.left_fit.offset, _lib.lt_state.last_left.offset, _lib.lt_params.partial.offset,
+            C.sizeof(_lib.lt_vis), _lib.lt_vis.left_fit.offset]
     assert got == want
 
 

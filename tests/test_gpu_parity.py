@@ -66,7 +66,7 @@ def _mism(a, b):
 def test_library_loaded_is_in_tree():
     from lane_tracker_b200 import _lib
     lib = _lib.load()
-    assert "lane_tracker_b200/liblane_tracker_b200.so" in _lib.LIB_PATH and lib.lt_abi_version() == 2
+    assert "lane_tracker_b200/liblane_tracker_b200.so" in _lib.LIB_PATH and lib.lt_abi_version() == _lib.LT_ABI_VERSION
 
 
 def test_coordinate_tables(bt):
@@ -732,3 +732,77 @@ def test_two_devices_in_one_process(torch_mod):
             outs.append((out.cpu().numpy(), res.copy()))
             b.close()
     assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1].tobytes() == outs[1][1].tobytes()
+
+
+def _debug_view_frames(dv):
+    vid = synth.RoadVideo(dv["seed"])
+    outage = fx.load_frame(dv["outage_frame"])
+    return [outage if kind == "outage" else vid.frame(t) for kind, t in dv["frames"]]
+
+
+@pytest.mark.parametrize("mode", ["visualize_search", "split_view"])
+def test_debug_views_match_reference_golden(torch_mod, mode):
+    """process(visualize_search=True) / process(split_view=True) (lane_tracker.py:689-793, 1130-1209,
+    utils.py:57-103) against the digests recorded from the reference: sliding-window view, band views, the
+    attempt-2 view of an outage and the recovery, and the three-panel canvas with cv2.resize's fixed-point bilinear."""
+    from lane_tracker_b200 import LaneTracker
+    dv = GOLD["debug_views"]
+    lt = LaneTracker(**CAL)
+    for i, (frame, rec) in enumerate(zip(_debug_view_frames(dv), dv[mode])):
+        before = frame.copy()
+        r = lt.process(frame, **{mode: True})
+        assert np.array_equal(frame, before)
+        if mode == "visualize_search":
+            assert fx.sha(r[0]) == rec["out"], i
+            assert list(r[1].shape) == rec["vis_shape"] and fx.sha(r[1]) == rec["vis"], i
+        else:
+            assert list(r.shape) == rec["shape"] and fx.sha(r) == rec["canvas"], i
+
+
+def test_debug_view_stage_methods_match_oracle(torch_mod, bt, frames_np):
+    """The pieces behind the debug views against the CPU restatements, on inputs the golden sequence does not
+    reach: bands that leave the canvas, windows clipped by the image border, up- and down-scaling resizes."""
+    from lane_tracker_b200 import LaneTracker
+    from lane_tracker_b200.utils import create_split_view
+    rng = np.random.default_rng(21)
+    # raw-frame bird's-eye view (lane_tracker.py:1035)
+    got = bt.warp_frame(torch_mod.from_numpy(frames_np).cuda()).cpu().numpy()
+    for i in (0, 3):
+        assert np.array_equal(got[i], cvops.warp_perspective(frames_np[i], CAL["warp_matrices"][0], (1080, 1100)))
+    # cv2.resize restatement: shrink, enlarge, identity, one channel
+    for shape, dsize in (((1100, 1080, 3), (640, 652)), ((300, 500, 3), (777, 333)), ((64, 64), (100, 100)),
+                         ((720, 1280, 3), (1280, 720)), ((301, 500, 3), (250, 150))):
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        out = bt.resize_linear(torch_mod.from_numpy(img).cuda(), dsize).cpu().numpy()
+        assert np.array_equal(out, cvops.resize_linear(img, dsize)), (shape, dsize)
+    # search views on a random mask with hand-made search results
+    lt = LaneTracker(**CAL)
+    orc = OracleLaneTracker(**CAL)
+    mask = (rng.random((1100, 1080)) < 0.05).astype(np.uint8) * 255
+    for trial in range(6):
+        n_l, n_r = int(rng.integers(1, 4000)), int(rng.integers(1, 4000))
+        px = [rng.integers(0, 1100, n_l), rng.integers(0, 1080, n_l), rng.integers(0, 1100, n_r), rng.integers(0, 1080, n_r)]
+        cents = [[int(v) for v in rng.integers(-20, 1100, int(rng.integers(0, 30)))] for _ in range(2)]
+        for o in (lt, orc):
+            o.left_y, o.left_x, o.right_y, o.right_x = px
+            o.left_window_centroids, o.right_window_centroids = cents
+            rng2 = np.random.default_rng(100 + trial)          # same coefficients for both objects
+            o.last_left_coeffs = np.array([rng2.normal(0, 2e-4), rng2.normal(0, 0.3), rng2.uniform(-20, 300)])
+            o.last_right_coeffs = np.array([rng2.normal(0, 2e-4), rng2.normal(0, 0.3), rng2.uniform(800, 1100)])
+        lf = np.array([rng.normal(0, 1e-4), rng.normal(0, 0.2), rng.uniform(200, 500)])
+        rf = lf + np.array([0.0, 0.0, 180.0])
+        ww, wh, ib = int(rng.choice([30, 60, 200])), int(rng.choice([40, 25])), int(rng.choice([30, 0]))
+        assert np.array_equal(lt.visualize_sliding_window_search(mask, lf, rf, ww, wh, ib),
+                              orc.visualize_sliding_window_search(mask, lf, rf, ww, wh, ib)), trial
+        bw, partial = int(rng.choice([25, 60, 150])), float(rng.choice([1.0, 0.5, 0.3]))
+        assert np.array_equal(lt.visualize_band_search(mask, lf, rf, bw, partial),
+                              orc.visualize_band_search(mask, lf, rf, bw, partial)), trial
+    # split view helpers, NumPy in / NumPy out
+    a, b, c = frames_np[0], rng.integers(0, 256, (1100, 1080, 3), dtype=np.uint8), rng.integers(0, 256, (1100, 1080, 3), dtype=np.uint8)
+    assert np.array_equal(lt.triple_split_view([a, b, c]), orc.triple_split_view([a, b, c]))
+    assert np.array_equal(create_split_view((900, 500), [b, a], [(10, 20), (300, 100)], [(400, 300), (640, 360)]),
+                          orc.create_split_view((900, 500), [b, a], [(10, 20), (300, 100)], [(400, 300), (640, 360)]))
+    with pytest.raises(ValueError):                            # a 2-D third panel cannot be placed: reference behaviour
+        lt.triple_split_view([a, b, mask])
+    with pytest.raises(NotImplementedError):
+        create_split_view((900, 500), [b], [(0, 0)], [(400, 300)], captions=["x"])

@@ -143,3 +143,47 @@ def test_text_sprites_reproduce_puttext():
                     lineType=cv2.LINE_AA)
         assert np.array_equal(sp.render(bg.copy(), text, org), want), text
     assert overlay_strings(True, 2784, -0.004, 5, False)[1][0] == "Eccentricity: -0.00 m"
+
+
+@pytest.mark.parametrize("shape,dsize", [((1100, 1080, 3), (640, 652)), ((1100, 1080), (640, 652)), ((720, 1280, 3), (1280, 720)),
+                                         ((300, 500, 3), (777, 333)), ((64, 64, 3), (100, 100)), ((300, 500, 3), (250, 150)),
+                                         ((1650, 1620, 3), (960, 978))])
+def test_resize_linear(shape, dsize):
+    """cv2.resize(img, dsize) of utils.create_split_view (utils.py:88): shrink, enlarge, identity, exact 2x."""
+    img = np.random.default_rng(11).integers(0, 256, shape, dtype=np.uint8)
+    assert np.array_equal(cvops.resize_linear(img, dsize), cv2.resize(img, dsize=dsize))
+
+
+@pytest.mark.parametrize("beta", [0.5, 0.3])
+def test_add_weighted_general(noise, beta):
+    other = np.random.default_rng(12).integers(0, 256, noise.shape, dtype=np.uint8)
+    assert np.array_equal(cvops.add_weighted(noise, other, beta), cv2.addWeighted(noise, 1, other, beta, 0))
+
+
+def test_fill_poly_search_bands_leaving_the_canvas():
+    """visualize_band_search polygons (lane_tracker.py:749-758): x -/+ bandwidth may leave the canvas, where
+    cv::Line clips an edge before rasterising it."""
+    W, H = 1080, 1100
+    rng = np.random.default_rng(3)
+    checked = clipped = 0
+    for t in range(200):
+        a = rng.normal(0, 3e-4) * (5 if t % 3 == 0 else 1)
+        b = rng.normal(0, 0.5) * (3 if t % 3 == 0 else 1)
+        c = rng.uniform(-50, 1130)
+        partial = 1.0 if t % 2 == 0 else 0.5
+        ploty = np.linspace(H * (1 - partial), H - 1, int(H * partial))
+        f = a * (ploty - 1099) ** 2 + b * (ploty - 1099) + c
+        x = f[(f <= W - 1) & (f >= 0)].astype(int)
+        if len(x) == 0:
+            continue
+        y = np.arange(H - len(x), H)
+        bw = int(rng.choice([25, 40, 80, 120]))
+        canvas = np.zeros((H, W, 3), np.uint8)
+        w1 = np.array([np.transpose(np.vstack([x - bw, y]))])
+        w2 = np.array([np.flipud(np.transpose(np.vstack([x + bw, y])))])
+        cv2.fillPoly(canvas, np.int_([np.hstack((w1, w2))]), (0, 255, 0))
+        lo, hi = cvops.lane_polygon_rows(x - bw, y, x + bw, y, W, H)
+        assert np.array_equal(cvops.lane_canvas(lo, hi, W, H), canvas), t
+        checked += 1
+        clipped += int((x - bw).min() < 0 or (x + bw).max() > W - 1)
+    assert checked > 150 and clipped > 30

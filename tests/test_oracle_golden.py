@@ -107,3 +107,38 @@ def test_scenario_prefix_numpy_backend():
         assert fx.out_digest(out) == rec["out"], rec["t"]
         assert fx.sha(out) == rec["out_full"], rec["t"]      # text drawn from the glyph sprites
         _state_matches(t, rec["state"])
+
+
+def _debug_view_frames(dv):
+    vid = synth.RoadVideo(dv["seed"])
+    outage = fx.load_frame(dv["outage_frame"])
+    return [outage if kind == "outage" else vid.frame(t) for kind, t in dv["frames"]]
+
+
+@pytest.mark.parametrize("mode", ["visualize_search", "split_view"])
+def test_debug_views_golden(mode):
+    """Reference debug views recorded by make_golden.py (lane_tracker.py:689-793, 1130-1209, utils.py:57-103)."""
+    warnings.simplefilter("ignore")
+    dv = GOLD["debug_views"]
+    t = OracleLaneTracker(**CAL, backend="cv2")
+    for i, (frame, rec) in enumerate(zip(_debug_view_frames(dv), dv[mode])):
+        r = t.process(frame.copy(), **{mode: True})
+        if mode == "visualize_search":
+            assert fx.sha(r[0]) == rec["out"], i
+            assert list(r[1].shape) == rec["vis_shape"] and fx.sha(r[1]) == rec["vis"], i
+        else:
+            assert list(r.shape) == rec["shape"] and fx.sha(r) == rec["canvas"], i
+
+
+def test_debug_views_golden_numpy_backend():
+    """Same, with the NumPy restatements of fillPoly / addWeighted / resize (first three frames: SWS view + band views)."""
+    warnings.simplefilter("ignore")
+    dv = GOLD["debug_views"]
+    frames = _debug_view_frames(dv)[:3]
+    t = OracleLaneTracker(**CAL)
+    for i, frame in enumerate(frames):
+        r = t.process(frame.copy(), visualize_search=True)
+        assert fx.sha(r[1]) == dv["visualize_search"][i]["vis"], i
+    t = OracleLaneTracker(**CAL)
+    for i, frame in enumerate(frames[:2]):
+        assert fx.sha(t.process(frame.copy(), split_view=True)) == dv["split_view"][i]["canvas"], i

@@ -49,3 +49,24 @@ def test_sliding_window_restatement_on_adversarial_masks():
                 assert list(ref.left_window_centroids) == list(orc.left_window_centroids), (i, nsl)
                 assert list(ref.right_window_centroids) == list(orc.right_window_centroids), (i, nsl)
     assert n_detected > 20
+
+
+@pytest.mark.parametrize("backend", ["cv2", "numpy"])
+def test_debug_views_match_live_reference(backend):
+    """visualize_search / split_view (lane_tracker.py:689-793, 1130-1209, utils.py:57-103): sliding-window frame,
+    band-search frames, a frame that fails both attempts (still pixels -> SWS view of attempt 2) and a recovery."""
+    warnings.simplefilter("ignore")
+    vid = synth.RoadVideo(5)
+    frames = [vid.frame(t) for t in range(3)] + [fx.load_frame("test4.jpg")] + [vid.frame(4)]
+    for mode in ("visualize_search", "split_view"):
+        ref = _liveref.make_tracker()
+        orc = OracleLaneTracker(**synth.shipped_calibration(), backend=backend)
+        for i, f in enumerate(frames):
+            a = _liveref.quiet(ref.process, f.copy(), **{mode: True})
+            b = orc.process(f.copy(), **{mode: True})
+            if mode == "visualize_search":
+                assert np.array_equal(a[0], b[0]), i
+                assert a[1].shape == b[1].shape and np.array_equal(a[1], b[1]), i
+            else:
+                assert a.shape == b.shape == (720 + 652, 1280, 3)
+                assert np.array_equal(a, b), i
