@@ -320,6 +320,8 @@ extern "C" int lt_process(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out,
     if ((rc = lt_launch_update_state(h, n, d_results, two ? 2 : 1, st))) return rc;
     lt_prof_mark(h, ST_UPDATE, st);
     if (d_out) {
+        // (copying the untouched rows on a side stream under the search kernels was measured: the copy saturates HBM
+        // and slows the search by what it saves -- the plain in-order copy stays)
         if ((rc = lt_launch_overlay(h, d_frames, d_out, n, h->draw_flags, st))) return rc;
         if ((rc = lt_launch_text(h, d_out, n, st))) return rc;
         lt_prof_mark(h, ST_OVERLAY, st);

@@ -61,7 +61,7 @@ template <int K> __host__ __device__ constexpr int ell_uidx(int w) {
 // the morphology kernel
 // ---------------------------------------------------------------------------
 
-constexpr int MORPH_TW = 192;       // packed columns per CTA (= threads); 3 CTAs/SM x 6 warps leaves 112 registers/thread
+constexpr int MORPH_TW = 192;       // packed columns per CTA (= threads); 3 CTAs/SM x 6 warps at 96 registers/thread
 constexpr int MORPH_CTAS_PER_SM = 3;
 constexpr int MORPH_RB = 8;         // source rows per table build
 
@@ -72,10 +72,6 @@ template <bool IS_MAX> __device__ __forceinline__ uint32_t op3(uint32_t a, uint3
     return IS_MAX ? __vimax3_u16x2(a, b, c) : __vimin3_u16x2(a, b, c);
 }
 
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
@@ -647,7 +643,8 @@ k_cross_v(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_al
 // ---------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(ROWK_WARPS * 32)
-k_box_h(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ hs_all, LtDims d, int half,
+k_box_h(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plane1, uint32_t* __restrict__ hs0,
+        uint32_t* __restrict__ hs1, LtDims d, int half0, int half1,
         int ppitch, size_t plane_stride, size_t hs_stride, const int* __restrict__ list, const int* __restrict__ count, int nslots) {
     extern __shared__ uint32_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -657,6 +654,9 @@ k_box_h(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ hs_all, L
     uint32_t* lin = smem + (size_t)warp * 2 * wpad;
     uint32_t* E = lin + wpad;
     const int nsl = count ? *count : nslots;          // attempt-2 launches loop over the (usually empty) retry list
+    const uint32_t* plane_all = blockIdx.z ? plane1 : plane0;      // both planes (R, Lab-b) in one launch
+    uint32_t* hs_all = blockIdx.z ? hs1 : hs0;
+    const int half = blockIdx.z ? half1 : half0;
     for (int slot = blockIdx.y; slot < nsl; slot += gridDim.y) {
         const int s = list ? list[slot] : slot;
         warp_row_prefix(plane_all + (size_t)s * plane_stride + (size_t)y * ppitch, d, lin, E, lane);
@@ -677,40 +677,50 @@ k_box_h(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ hs_all, L
 }
 
 __global__ void __launch_bounds__(32)
-k_box_v(const uint32_t* __restrict__ plane_all, const uint32_t* __restrict__ hs_all, uint32_t* __restrict__ bits_all,
-        LtDims d, int half, int c, int accumulate, int band_rows, int ppitch, size_t plane_stride, size_t hs_stride,
-        size_t bits_stride,
+k_box_v(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plane1, const uint32_t* __restrict__ hs0,
+        const uint32_t* __restrict__ hs1, uint32_t* __restrict__ bits_all, LtDims d, int half0, int half1, int c0, int c1,
+        int band_rows, int ppitch, size_t plane_stride, size_t hs_stride, size_t bits_stride,
         const int* __restrict__ list, const int* __restrict__ count, int nslots) {
+    // one thread per packed column; the thresholds of the R and the Lab-b plane are OR-ed in registers and the mask
+    // word is written once (lane_tracker.py:217-218 + the OR at :233)
     const int nsl = count ? *count : nslots;
     for (int slot = blockIdx.z; slot < nsl; slot += gridDim.z) {
-    const int s = list ? list[slot] : slot;
-    int lane = threadIdx.x;
-    int x = blockIdx.x * 32 + lane;
-    int yb0 = blockIdx.y * band_rows, yb1 = min(yb0 + band_rows, d.bv_h);
-    const uint32_t* P = plane_all + (size_t)s * plane_stride + x;
-    const uint32_t* Hs = hs_all + (size_t)s * hs_stride + x;
-    uint32_t* bits = bits_all + (size_t)s * bits_stride;
-    const bool hi_ok = x + d.p2 < d.bv_w;
-    auto ldh = [&](int r) -> uint32_t { r = max(0, min(d.bv_h - 1, r)); return __ldg(&Hs[(size_t)r * ppitch]); };
-    uint32_t Sl = 0, Sh = 0;
-    for (int dy = -half; dy <= half; ++dy) { uint32_t v = ldh(yb0 + dy); Sl += v & 0xFFFFu; Sh += v >> 16; }
-    const uint32_t n = (uint32_t)(2 * half + 1) * (uint32_t)(2 * half + 1);
-    for (int y = yb0; y < yb1; ++y) {
-        uint32_t p = __ldg(&P[(size_t)y * ppitch]);
-        int ml = (int)((2u * Sl + n) / (2u * n)), mh = (int)((2u * Sh + n) / (2u * n));
-        bool pl = ((int)(p & 0xFFFFu) - ml) > c;
-        bool ph = hi_ok && (((int)(p >> 16) - mh) > c);
-        uint32_t bl = __ballot_sync(0xFFFFFFFFu, pl), bh = __ballot_sync(0xFFFFFFFFu, ph);
-        if (lane == 0) {
+        const int s = list ? list[slot] : slot;
+        const int lane = threadIdx.x;
+        const int x = blockIdx.x * 32 + lane;
+        const int yb0 = blockIdx.y * band_rows, yb1 = min(yb0 + band_rows, d.bv_h);
+        uint32_t* bits = bits_all + (size_t)s * bits_stride;
+        const bool hi_ok = x + d.p2 < d.bv_w;
+        for (int y = yb0 + lane; y < yb1; y += 32) {                    // clear, then OR the two planes in
             uint32_t* brow = bits + (size_t)y * d.mwords;
-            int wl = blockIdx.x, wh = blockIdx.x + (d.p2 >> 5);
-            brow[wl] = accumulate ? (brow[wl] | bl) : bl;
-            brow[wh] = accumulate ? (brow[wh] | bh) : bh;
+            brow[blockIdx.x] = 0u; brow[blockIdx.x + (d.p2 >> 5)] = 0u;
         }
-        uint32_t a = ldh(y + half + 1), b = ldh(y - half);
-        Sl += (a & 0xFFFFu) - (b & 0xFFFFu);
-        Sh += (a >> 16) - (b >> 16);
-    }
+        __syncwarp();
+        for (int pl = 0; pl < 2; ++pl) {
+            const uint32_t* P = (pl ? plane1 : plane0) + (size_t)s * plane_stride + x;
+            const uint32_t* Hs = (pl ? hs1 : hs0) + (size_t)s * hs_stride + x;
+            const int half = pl ? half1 : half0, c = pl ? c1 : c0;
+            auto ldh = [&](int r) -> uint32_t { r = max(0, min(d.bv_h - 1, r)); return __ldg(&Hs[(size_t)r * ppitch]); };
+            uint32_t Sl = 0, Sh = 0;
+            for (int dy = -half; dy <= half; ++dy) { uint32_t v = ldh(yb0 + dy); Sl += v & 0xFFFFu; Sh += v >> 16; }
+            const uint32_t n = (uint32_t)(2 * half + 1) * (uint32_t)(2 * half + 1);
+            for (int y = yb0; y < yb1; ++y) {
+                uint32_t p = __ldg(&P[(size_t)y * ppitch]);
+                int ml = (int)((2u * Sl + n) / (2u * n)), mh = (int)((2u * Sh + n) / (2u * n));
+                bool pl_ = ((int)(p & 0xFFFFu) - ml) > c;
+                bool ph = hi_ok && (((int)(p >> 16) - mh) > c);
+                uint32_t bl = __ballot_sync(0xFFFFFFFFu, pl_), bh = __ballot_sync(0xFFFFFFFFu, ph);
+                if (lane == 0) {
+                    uint32_t* brow = bits + (size_t)y * d.mwords;
+                    brow[blockIdx.x] |= bl;
+                    brow[blockIdx.x + (d.p2 >> 5)] |= bh;
+                }
+                uint32_t a = ldh(y + half + 1), b = ldh(y - half);
+                Sl += (a & 0xFFFFu) - (b & 0xFFFFu);
+                Sh += (a >> 16) - (b >> 16);
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -894,21 +904,23 @@ static int launch_cross(lt_handle* h, const uint32_t* plane, uint32_t* bits, int
     return 0;
 }
 
-static int launch_box(lt_handle* h, const uint32_t* plane, uint32_t* hs, uint32_t* bits, int block, int c,
-                      int accumulate, int n, const int* list, const int* count, cudaStream_t st) {
+static int launch_box_pair(lt_handle* h, int block_r, int c_r, int block_b, int c_b, int n, const int* list,
+                           const int* count, cudaStream_t st) {
+    // adaptiveThreshold of the R and the Lab-b plane in two launches (row sums of both, then columns + OR);
+    // the top-hat planes, unused by this filter type, hold the row sums
     const LtDims& d = h->d;
     int wpad = (d.bv_w + 32) & ~31;
     size_t smem = (size_t)ROWK_WARPS * 2 * wpad * sizeof(uint32_t);
     { int rc = lt_ensure_smem((const void*)k_box_h, smem); if (rc) return rc; }
-    int half = block / 2;
     const int zs = list ? (n < 8 ? n : 8) : n;      // retry-list launches: few slots, each CTA loops over the list
-    dim3 gh(lt_div_up(d.bv_h, ROWK_WARPS), zs);
-    k_box_h<<<gh, ROWK_WARPS * 32, smem, st>>>(plane, hs, d, half, d.pp, h->stream_pad, h->stream_pad, list, count, n);
+    dim3 gh(lt_div_up(d.bv_h, ROWK_WARPS), zs, 2);
+    k_box_h<<<gh, ROWK_WARPS * 32, smem, st>>>(h->planeR, h->planeB, h->topR, h->topB, d, block_r / 2, block_b / 2, d.pp,
+                                               h->stream_pad, h->stream_pad, list, count, n);
     LT_LAUNCH_CHECK();
     int band_rows = 64;
     dim3 gv(d.p2 / 32, lt_div_up(d.bv_h, band_rows), zs);
-    k_box_v<<<gv, 32, 0, st>>>(plane, hs, bits, d, half, c, accumulate, band_rows, d.pp, h->stream_pad, h->stream_pad, h->stream_mask,
-                               list, count, n);
+    k_box_v<<<gv, 32, 0, st>>>(h->planeR, h->planeB, h->topR, h->topB, h->merged, d, block_r / 2, block_b / 2, c_r, c_b,
+                               band_rows, d.pp, h->stream_pad, h->stream_pad, h->stream_mask, list, count, n);
     LT_LAUNCH_CHECK();
     return 0;
 }
@@ -929,8 +941,7 @@ int lt_launch_filter(lt_handle* h, int n, const LtAttemptParams& p, const int* l
         if ((rc = launch_cross(h, h->topB, h->merged, p.ksize_b, p.C_b, 1, n, list, count, st))) return rc;
         lt_prof_mark(h, ST_CROSS_B, st);
     } else {
-        if ((rc = launch_box(h, h->planeR, h->topR, h->merged, p.ksize_r, p.C_r, 0, n, list, count, st))) return rc;
-        if ((rc = launch_box(h, h->planeB, h->topB, h->merged, p.ksize_b, p.C_b, 1, n, list, count, st))) return rc;
+        if ((rc = launch_box_pair(h, p.ksize_r, p.C_r, p.ksize_b, p.C_b, n, list, count, st))) return rc;
         lt_prof_mark(h, ST_BOX, st);
     }
     if (p.mask_noise) {

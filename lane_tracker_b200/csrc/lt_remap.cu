@@ -515,16 +515,22 @@ k_copy_rows(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t frame
         if (i0 + (size_t)u * blockDim.x < total) fd[idx[u]] = v[u];
 }
 
-int lt_launch_overlay(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int n, const int* d_draw,
-                      cudaStream_t st) {
+// The rows of the output frame that the lane overlay cannot reach are a plain copy of the input.
+static void overlay_rows(const lt_handle* h, const uint8_t* d_frames, const uint8_t* d_out, int& r0, int& r1, bool& vec_ok) {
+    const LtDims& d = h->d;
+    const size_t row_bytes = (size_t)d.img_w * 3;
+    r0 = d.ov0; r1 = d.ov1;
+    if (r0 >= r1) { r0 = 0; r1 = 0; }
+    vec_ok = (row_bytes % 16 == 0) && (((uintptr_t)d_frames | (uintptr_t)d_out) % 16 == 0);
+    if (d_out != d_frames && !vec_ok) { r0 = 0; r1 = d.img_h; }   // generic path: k_overlay copies every row itself
+}
+
+int lt_launch_copy_untouched_rows(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int n, cudaStream_t st) {
     const LtDims& d = h->d;
     const size_t row_bytes = (size_t)d.img_w * 3, frame_bytes = row_bytes * d.img_h;
-    int r0 = d.ov0, r1 = d.ov1;
-    if (r0 >= r1) { r0 = 0; r1 = 0; }
-    const bool inplace = (d_out == d_frames);
-    const bool vec_ok = (row_bytes % 16 == 0) && (((uintptr_t)d_frames | (uintptr_t)d_out) % 16 == 0);
-    if (!inplace && !vec_ok) { r0 = 0; r1 = d.img_h; }            // generic path copies every row itself
-    if (!inplace && vec_ok && (r0 > 0 || r1 < d.img_h)) {
+    int r0, r1; bool vec_ok;
+    overlay_rows(h, d_frames, d_out, r0, r1, vec_ok);
+    if (d_out != d_frames && vec_ok && (r0 > 0 || r1 < d.img_h)) {
         const size_t a_vec = (size_t)r0 * row_bytes / 16, b_off = (size_t)r1 * row_bytes / 16;
         const size_t b_vec = (size_t)(d.img_h - r1) * row_bytes / 16;
         dim3 g((unsigned)((a_vec + b_vec + 1023) / 1024), n);
@@ -532,6 +538,15 @@ int lt_launch_overlay(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int
                                         frame_bytes / 16, a_vec, b_off, b_vec);
         LT_LAUNCH_CHECK();
     }
+    return 0;
+}
+
+int lt_launch_overlay(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int n, const int* d_draw,
+                      cudaStream_t st, bool rows_already_copied) {
+    const LtDims& d = h->d;
+    int r0, r1; bool vec_ok;
+    overlay_rows(h, d_frames, d_out, r0, r1, vec_ok);
+    if (!rows_already_copied) { int rc = lt_launch_copy_untouched_rows(h, d_frames, d_out, n, st); if (rc) return rc; }
     if (r1 > r0) {
         dim3 g(lt_div_up(d.img_w / 4, 256), r1 - r0, n);
         k_overlay<<<g, 256, 0, st>>>(d_frames, d_out, h->ov_map, h->lane_rows, d_draw, d, r0);
