@@ -143,6 +143,20 @@ int64_t lt_launch_count(void);
 int lt_process(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int32_t n_streams,
                const lt_params* params, lt_result* d_results, void* stream);
 
+/* lt_process in two halves, for callers that keep two batches in flight on two CUDA streams:
+ *   lt_process_front: undistort + warp + first-attempt filter (find_lane_points 795-874 up to the binary mask).
+ *                     Stateless; writes the handle's intermediate buffer set `set` (0 or 1; set 1 is allocated on
+ *                     first use and doubles the intermediate memory).
+ *   lt_process_back : searches, second attempt for the streams that failed, state machine, overlay and text
+ *                     (lane_tracker.py:1040-1209) from buffer set `set`; advances the per-stream state.
+ * lt_process(...) == lt_process_front(..., 0, stream) followed by lt_process_back(..., 0, ..., stream).
+ * The caller orders things with its own events: back(k) after front(k); back(k) after back(k-1) (tracking state);
+ * front(k+2) after back(k) (they share a buffer set).  lane_tracker_b200.DevicePipeline does exactly that. */
+int lt_process_front(lt_handle* h, const uint8_t* d_frames, int32_t n_streams, const lt_params* params,
+                     int32_t set, void* stream);
+int lt_process_back(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int32_t n_streams,
+                    const lt_params* params, int32_t set, lt_result* d_results, void* stream);
+
 /* Keep the ordered lane-pixel sets and window centroids of every lt_process call so that
  * lt_read_capture can return them (the reference exposes them as the attributes left_x/left_y/
  * right_x/right_y/left_window_centroids, lane_tracker.py:159-166).  Off by default: the
@@ -182,6 +196,11 @@ int lt_memcpy_rows(lt_handle* h, void* dst, const void* src, int32_t n_frames, i
 #define LT_NSTAGES 16
 int lt_profile_begin(lt_handle* h, int32_t max_calls);
 int lt_profile_read(lt_handle* h, double* h_stage_ms, int32_t* h_calls);
+/* Restrict the marks to the stage boundaries whose bit (1 << stage index, see lt_stage_name) is set; 0 = all.
+ * The time reported for a selected stage then runs from the previous SELECTED boundary of the same call, so select
+ * the boundary before a stage as well (e.g. warp | erode55 | tophat55 to time the two morphology launches with three
+ * events per call instead of a dozen). */
+int lt_profile_select(lt_handle* h, uint32_t stage_mask);
 const char* lt_stage_name(int32_t stage);
 
 /* ---- stage entry points (mirror the reference's public methods) ----------- */

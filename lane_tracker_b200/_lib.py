@@ -83,6 +83,8 @@ SIGNATURES = {
     "lt_default_params": (None, [C.POINTER(lt_params)]),
     "lt_launch_count": (C.c_int64, []),
     "lt_process": (C.c_int, [P, P, P, i32, C.POINTER(lt_params), P, P]),
+    "lt_process_front": (C.c_int, [P, P, i32, C.POINTER(lt_params), i32, P]),
+    "lt_process_back": (C.c_int, [P, P, P, i32, C.POINTER(lt_params), i32, P, P]),
     "lt_set_capture": (C.c_int, [P, i32]),
     "lt_read_capture": (C.c_int, [P, i32, i32, i32, P, i32, C.POINTER(i32), P, C.POINTER(i32)]),
     "lt_set_text_sprites": (C.c_int, [P, P, i32, P, i32, P, P, P, i32, P, i32]),
@@ -90,6 +92,7 @@ SIGNATURES = {
     "lt_memcpy_rows": (C.c_int, [P, P, P, i32, i32, i32, i32, P]),
     "lt_profile_begin": (C.c_int, [P, i32]),
     "lt_profile_read": (C.c_int, [P, C.POINTER(f64), C.POINTER(i32)]),
+    "lt_profile_select": (C.c_int, [P, C.c_uint32]),
     "lt_stage_name": (C.c_char_p, [i32]),
     "lt_remap": (C.c_int, [P, P, P, i32, P]),
     "lt_filter_lane_points": (C.c_int, [P, P, P, i32] + [i32] * 9 + [P]),

@@ -118,8 +118,13 @@ static void init_state(lt_handle* h, lt_state* s) {
 extern "C" int lt_destroy(lt_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->cfg.device);
-    void* ptrs[] = {h->und_map, h->bv_map, h->ov_map, h->bv_desc, h->fused_desc, h->lab_gamma, h->lab_cbrt, h->und_roi, h->pad_alloc[0], h->pad_alloc[1],
-                    h->pad_alloc[2], h->pad_alloc[3], h->pad_alloc[4], h->pad_alloc[5], h->merged, h->mask, h->pixels, h->pix_counts, h->lane_rows,
+    for (int k = 0; k < 2; ++k) {
+        const LtFrontSet& f = h->fs[k];
+        void* fp[] = {f.und_roi, f.pad_alloc[0], f.pad_alloc[1], f.pad_alloc[2], f.pad_alloc[3], f.pad_alloc[4], f.pad_alloc[5],
+                      f.merged, f.mask};
+        for (void* p : fp) if (p) cudaFree(p);
+    }
+    void* ptrs[] = {h->und_map, h->bv_map, h->ov_map, h->bv_desc, h->fused_desc, h->lab_gamma, h->lab_cbrt, h->pixels, h->pix_counts, h->lane_rows,
                     h->avg_x, h->state, h->att, h->retry_list, h->retry_count, h->draw_flags, h->scratch_bv, h->vis_scratch,
                     h->cap_pixels, h->cap_counts, h->cap_cents, h->cap_ncents,
                     h->txt_tables, h->txt_char_start, h->txt_dy, h->txt_dx, h->txt_lut, h->txt_advance, h->txt_pair_overlap,
@@ -129,6 +134,37 @@ extern "C" int lt_destroy(lt_handle* h) {
     delete[] h->prof_ev; delete[] h->prof_stage;
     delete h;
     return 0;
+}
+
+// allocate one set of front-half buffers (LtFrontSet) and give its padded planes their pad values
+static int alloc_front_set(lt_handle* h, int k) {
+    LtFrontSet& f = h->fs[k];
+    if (f.mask) return 0;
+    const LtDims& d = h->d;
+    const size_t S = h->S;
+    int rc = dev_alloc(&f.und_roi, S * (size_t)(d.roi1 - d.roi0) * d.img_w);
+    // padded planes: + one row of slack (the last tile of a row block stages a few entries past the row end)
+    const size_t n = S * h->stream_pad + d.pp;
+    for (int i = 0; i < 6 && !rc; ++i) {
+        rc = dev_alloc(&f.pad_alloc[i], n);
+        if (!rc) cudaMemset(f.pad_alloc[i], i < 2 ? 0xFF : 0x00, n * sizeof(uint32_t));   // pad of erode / dilate
+    }
+    if (!rc) rc = dev_alloc(&f.merged, S * h->stream_mask);
+    if (!rc) rc = dev_alloc(&f.mask, S * h->stream_mask);
+    return rc;
+}
+
+// make set k the one the launchers see (kernel arguments are captured at launch, so switching between calls is safe)
+static void select_set(lt_handle* h, int k) {
+    const LtFrontSet& f = h->fs[k];
+    const size_t origin = (size_t)LT_HALO_Y * h->d.pp + LT_HALO_X;
+    h->und_roi = f.und_roi;
+    for (int i = 0; i < 6; ++i) h->pad_alloc[i] = f.pad_alloc[i];
+    h->planeR = f.pad_alloc[0] + origin; h->planeB = f.pad_alloc[1] + origin;
+    h->tmpR = f.pad_alloc[2] + origin;   h->tmpB = f.pad_alloc[3] + origin;
+    h->topR = f.pad_alloc[4] + origin;   h->topB = f.pad_alloc[5] + origin;
+    h->merged = f.merged; h->mask = f.mask;
+    h->cur_set = k;
 }
 
 extern "C" int lt_create(const lt_config* cfg, lt_handle** out) {
@@ -207,21 +243,8 @@ extern "C" int lt_create(const lt_config* cfg, lt_handle** out) {
     }
     A(bv_desc, nbv);
     if (!rc) rc = lt_launch_build_desc(h, st);
-    A(und_roi, S * (size_t)(d.roi1 - d.roi0) * d.img_w);
-    {
-        // padded planes: + one row of slack (the last tile of a row block stages a few entries past the row end)
-        const size_t n = S * h->stream_pad + d.pp, origin = (size_t)LT_HALO_Y * d.pp + LT_HALO_X;
-        for (int i = 0; i < 6; ++i) {
-            A(pad_alloc[i], n);
-            if (!rc) cudaMemsetAsync(h->pad_alloc[i], i < 2 ? 0xFF : 0x00, n * sizeof(uint32_t), st);   // pad of erode / dilate
-        }
-        if (!rc) {
-            h->planeR = h->pad_alloc[0] + origin; h->planeB = h->pad_alloc[1] + origin;
-            h->tmpR = h->pad_alloc[2] + origin;   h->tmpB = h->pad_alloc[3] + origin;
-            h->topR = h->pad_alloc[4] + origin;   h->topB = h->pad_alloc[5] + origin;
-        }
-    }
-    A(merged, S * h->stream_mask); A(mask, S * h->stream_mask);
+    if (!rc) rc = alloc_front_set(h, 0);
+    if (!rc) select_set(h, 0);
     A(pixels, S * 2 * (size_t)h->pix_cap); A(pix_counts, S * 2);
     A(lane_rows, S * (size_t)d.bv_h); A(avg_x, S * 2 * (size_t)d.bv_h);
     A(state, S); A(att, 2 * S); A(retry_list, S); A(retry_count, 1); A(draw_flags, 2 * S);
@@ -272,16 +295,9 @@ static int check_n(lt_handle* h, int n) {
 // process()
 // ---------------------------------------------------------------------------
 
-extern "C" int lt_process(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int32_t n, const lt_params* params,
-                          lt_result* d_results, void* stream) {
+// find_lane_points (lane_tracker.py:795-874) of the first attempt up to the binary mask, all streams: stateless
+static int process_front(lt_handle* h, const uint8_t* d_frames, int n, const LtAttemptParams& p1, cudaStream_t st) {
     int rc;
-    if ((rc = check_n(h, n))) return rc;
-    if (!d_frames || !params || !d_results) { lt_set_error("null argument"); return -1; }
-    cudaStream_t st = (cudaStream_t)stream;
-    LtAttemptParams p1 = attempt_from(*params), p2 = second_attempt();
-    if ((rc = check_params(h, p1))) return rc;
-    const bool two = (params->n_tries >= 2) || (params->n_tries == -1);
-    // find_lane_points (lane_tracker.py:795-874), first attempt, all streams
     if (h->prof_active && h->prof_calls >= h->prof_max_calls) h->prof_active = 0;
     lt_prof_mark(h, ST_BEGIN, st);
     if (h->remap_mode == 1) {
@@ -292,7 +308,16 @@ extern "C" int lt_process(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out,
         if ((rc = lt_launch_warp(h, nullptr, n, st))) return rc;
     }
     lt_prof_mark(h, ST_WARP, st);
-    if ((rc = lt_launch_filter(h, n, p1, nullptr, nullptr, st))) return rc;
+    return lt_launch_filter(h, n, p1, nullptr, nullptr, st);
+}
+
+// searches, second attempt of the streams that failed, state machine, overlay: advances the per-stream state
+static int process_back(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int n, const lt_params* params,
+                        const LtAttemptParams& p1, lt_result* d_results, cudaStream_t st, bool own_begin) {
+    int rc;
+    const LtAttemptParams p2 = second_attempt();
+    const bool two = (params->n_tries >= 2) || (params->n_tries == -1);
+    if (own_begin) lt_prof_mark(h, ST_BEGIN, st);       // stage times are differences of marks on ONE stream
     LtSearchArgs sa;
     memset(&sa, 0, sizeof(sa));
     sa.mask = h->mask; sa.mode = 0; sa.att = h->att; sa.do_fit = 1;
@@ -330,6 +355,45 @@ extern "C" int lt_process(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out,
     return 0;
 }
 
+static int process_args(lt_handle* h, const uint8_t* d_frames, int n, const lt_params* params, int set, LtAttemptParams* p1) {
+    int rc;
+    if ((rc = check_n(h, n))) return rc;
+    if (!d_frames || !params) { lt_set_error("null argument"); return -1; }
+    if (set != 0 && set != 1) { lt_set_error("buffer set must be 0 or 1"); return -1; }
+    *p1 = attempt_from(*params);
+    if ((rc = check_params(h, *p1))) return rc;
+    if ((rc = alloc_front_set(h, set))) return rc;
+    select_set(h, set);
+    return 0;
+}
+
+extern "C" int lt_process(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int32_t n, const lt_params* params,
+                          lt_result* d_results, void* stream) {
+    int rc;
+    LtAttemptParams p1;
+    if ((rc = process_args(h, d_frames, n, params, 0, &p1))) return rc;
+    if (!d_results) { lt_set_error("null argument"); return -1; }
+    if ((rc = process_front(h, d_frames, n, p1, (cudaStream_t)stream))) return rc;
+    return process_back(h, d_frames, d_out, n, params, p1, d_results, (cudaStream_t)stream, false);
+}
+
+extern "C" int lt_process_front(lt_handle* h, const uint8_t* d_frames, int32_t n, const lt_params* params, int32_t set,
+                                void* stream) {
+    int rc;
+    LtAttemptParams p1;
+    if ((rc = process_args(h, d_frames, n, params, set, &p1))) return rc;
+    return process_front(h, d_frames, n, p1, (cudaStream_t)stream);
+}
+
+extern "C" int lt_process_back(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int32_t n, const lt_params* params,
+                               int32_t set, lt_result* d_results, void* stream) {
+    int rc;
+    LtAttemptParams p1;
+    if ((rc = process_args(h, d_frames, n, params, set, &p1))) return rc;
+    if (!d_results) { lt_set_error("null argument"); return -1; }
+    return process_back(h, d_frames, d_out, n, params, p1, d_results, (cudaStream_t)stream, true);
+}
+
 static const char* STAGE_NAMES[LT_NSTAGES] = {"begin", "undistort", "warp", "erode55", "erode29", "tophat55", "tophat29",
                                                "cross_r", "cross_b", "box", "noise", "open5", "search", "retry_select",
                                                "update_state", "overlay"};
@@ -337,6 +401,7 @@ extern "C" const char* lt_stage_name(int32_t s) { return (s >= 0 && s < LT_NSTAG
 
 void lt_prof_mark(lt_handle* h, int stage, cudaStream_t st) {
     if (!h->prof_active || h->prof_n >= h->prof_cap) return;
+    if (h->prof_mask && !((h->prof_mask >> stage) & 1u)) return;
     h->prof_stage[h->prof_n] = stage;
     cudaEventRecord(h->prof_ev[h->prof_n], st);
     h->prof_n++;
@@ -354,6 +419,12 @@ extern "C" int lt_profile_begin(lt_handle* h, int32_t max_calls) {
         h->prof_ev = ev; h->prof_stage = new int[need]; h->prof_cap = need;
     }
     h->prof_n = 0; h->prof_calls = 0; h->prof_max_calls = max_calls; h->prof_active = 1;
+    return 0;
+}
+
+extern "C" int lt_profile_select(lt_handle* h, uint32_t stage_mask) {
+    if (!h) { lt_set_error("bad argument"); return -1; }
+    h->prof_mask = stage_mask ? (stage_mask | 1u) : 0u;       // stage 0 (begin) always marks
     return 0;
 }
 

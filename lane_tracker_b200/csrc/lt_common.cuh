@@ -53,6 +53,15 @@ struct LtAttemptOut {
     double partial;   // the partial that get_poly_points() will see on success
 };
 
+// The buffers the stateless front half of a frame (undistort, warp, filter) produces and the stateful back half
+// (search, second attempt, state update, overlay) consumes.  A handle owns two sets so that the front half of batch
+// k+1 can run on one CUDA stream while the back half of batch k runs on another (lt_process_front / lt_process_back).
+struct LtFrontSet {
+    uchar4* und_roi;
+    uint32_t* pad_alloc[6];
+    uint32_t* merged; uint32_t* mask;
+};
+
 struct lt_handle {
     lt_config cfg;
     LtDims d;
@@ -76,6 +85,8 @@ struct lt_handle {
     uint32_t* tmpR;   uint32_t* tmpB;       // padded eroded planes; lanes beyond the image / halo: 0
     uint32_t* topR;   uint32_t* topB;       // padded top-hat planes / box row sums; halo and pad rows: 0
     uint32_t* pad_alloc[6];                 // the allocations behind the six padded planes
+    LtFrontSet fs[2];                       // [0] always allocated, [1] on first use; the fields above mirror the selected one
+    int cur_set;
     uint32_t* merged; uint32_t* mask;       // [S][bv_h][mwords]
     uint32_t* pixels;            // [S][2][pix_cap]
     int pix_cap;
@@ -97,6 +108,7 @@ struct lt_handle {
     unsigned long long* txt_bitmaps;   // [nchars][64] rows of 64 bits: glyph pixel (dy + 32, dx + 8)
     unsigned char* txt_pair_overlap;   // [nchars][nchars]: glyph b drawn right after glyph a shares pixels with it
     cudaEvent_t* prof_ev; int* prof_stage; int prof_cap, prof_n, prof_active, prof_calls, prof_max_calls;
+    uint32_t prof_mask;          // 0: every stage boundary is marked; else only the boundaries whose bit is set
     uint8_t* scratch_bv;         // lazily allocated [S][bv_h][bv_w][3] for stage calls
     unsigned char* vis_scratch;  // lazily allocated work area of lt_visualize_search
     size_t stream_pad;           // entries per stream in a padded pair plane

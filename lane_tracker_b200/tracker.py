@@ -177,6 +177,15 @@ class BatchedLaneTracker:
         """Arm in-stream CUDA-event timing of every stage of the next `max_calls` process() calls."""
         check(self.lib.lt_profile_begin(self._h, int(max_calls)))
 
+    def profile_select(self, stages=None):
+        """Mark only the boundaries of the named stages (None: all).  Name the boundary before a stage too."""
+        mask = 0
+        if stages:
+            names = {self.lib.lt_stage_name(i).decode(): i for i in range(_lib.LT_NSTAGES)}
+            for st in stages:
+                mask |= 1 << names[st]
+        check(self.lib.lt_profile_select(self._h, mask))
+
     def profile_read(self):
         """-> ({stage name: total ms}, calls); synchronises."""
         ms = (C.c_double * _lib.LT_NSTAGES)()
@@ -209,6 +218,29 @@ class BatchedLaneTracker:
             raise ValueError("results buffer too small")
         check(self.lib.lt_process(self._h, _ptr(frames), _ptr(out), n, C.byref(p), _ptr(res),
                                   _stream_ptr(self.device)))
+        return n
+
+    def process_front_async(self, frames, buffer_set, params=None, **kw):
+        """First half of ``process_async`` (undistort, warp, first-attempt filter) into intermediate buffer set
+        0 or 1, on the current CUDA stream.  Stateless.  See ``DevicePipeline``."""
+        n = self._check_frames(frames)
+        p = params if params is not None else make_params(**kw)
+        check(self.lib.lt_process_front(self._h, _ptr(frames), n, C.byref(p), int(buffer_set), _stream_ptr(self.device)))
+        return n
+
+    def process_back_async(self, frames, out, buffer_set, params=None, results_dev=None, **kw):
+        """Second half of ``process_async`` (searches, second attempt, state machine, overlay) from intermediate
+        buffer set 0 or 1, on the current CUDA stream.  Advances the per-stream state."""
+        n = self._check_frames(frames)
+        if out is not None and (out.shape != frames.shape or out.dtype != torch.uint8 or not out.is_cuda or
+                                not out.is_contiguous()):
+            raise ValueError("out must match frames")
+        p = params if params is not None else make_params(**kw)
+        res = self._results_dev if results_dev is None else results_dev
+        if res.numel() < n * RESULT_DTYPE.itemsize or not res.is_cuda:
+            raise ValueError("results buffer too small")
+        check(self.lib.lt_process_back(self._h, _ptr(frames), _ptr(out), n, C.byref(p), int(buffer_set), _ptr(res),
+                                       _stream_ptr(self.device)))
         return n
 
     def fetch_results(self, n=None):
@@ -444,6 +476,72 @@ class BatchedLaneTracker:
         return out
 
 
+class DevicePipeline:
+    """Two batches in flight on the device: the stateless front half of batch k+1 (undistort, warp, filter) runs on
+    one CUDA stream while the stateful back half of batch k (searches, state machine, overlay) runs on another.
+    The back half is a chain of small kernels (one CTA per stream) that leaves most SMs idle; the front half of the
+    next batch fills them.  Results are those of sequential ``process`` calls: back halves execute in submission
+    order on one stream, and a buffer set is reused only after the back half that read it has finished.
+
+        pipe = DevicePipeline(tracker)
+        for frames, out in batches:            # CUDA tensors; produced on the current stream
+            done = pipe.submit(frames, out)    # torch.cuda.Event: out / results of this batch are complete
+        pipe.join()                            # the current stream waits for everything submitted
+    """
+
+    def __init__(self, tracker, params=None):
+        self.t = tracker
+        self.params = params if params is not None else make_params()
+        dev = tracker.device
+        self.s_front = torch.cuda.Stream(dev)
+        self.s_back = torch.cuda.Stream(dev)
+        self._k = 0
+        self._back_done = [None, None]          # per buffer set: event of the last back half that used it
+        self._last = None
+        self.results_dev = [torch.zeros(tracker.n_streams * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+                            for _ in range(2)]
+
+    def submit(self, frames, out=None):
+        dev = self.t.device
+        k, bs = self._k, self._k & 1
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))            # frames (and out) belong to the caller until here
+        with torch.cuda.stream(self.s_front):
+            self.s_front.wait_event(ready)
+            if self._back_done[bs] is not None:
+                self.s_front.wait_event(self._back_done[bs])    # set `bs` is free again
+            self.t.process_front_async(frames, bs, params=self.params)
+            front_done = torch.cuda.Event()
+            front_done.record(self.s_front)
+        with torch.cuda.stream(self.s_back):
+            self.s_back.wait_event(front_done)
+            self.s_back.wait_event(ready)
+            self.t.process_back_async(frames, out, bs, params=self.params, results_dev=self.results_dev[bs])
+            done = torch.cuda.Event()
+            done.record(self.s_back)
+        self._back_done[bs] = done
+        self._last = done
+        self._k = k + 1
+        return done
+
+    def last_results_dev(self):
+        """Device buffer holding the lt_result records of the most recently submitted batch."""
+        return self.results_dev[(self._k - 1) & 1]
+
+    def join(self):
+        if self._last is not None:
+            torch.cuda.current_stream(self.t.device).wait_event(self._last)
+
+    def fetch_results(self, n=None):
+        """Results of the most recently submitted batch as a structured array (synchronises)."""
+        n = self.t.n_streams if n is None else n
+        self.join()
+        nbytes = n * RESULT_DTYPE.itemsize
+        self.t._results_host[:nbytes].copy_(self.last_results_dev()[:nbytes], non_blocking=True)
+        torch.cuda.current_stream(self.t.device).synchronize()
+        return self.t._results_host[:nbytes].numpy().view(RESULT_DTYPE).copy()
+
+
 class HostPipeline:
     """Host-to-host streaming through a ``BatchedLaneTracker``: pinned host frames in, annotated frames and
     result records out, with the H2D copy of batch k+1, the kernels of batch k and the D2H copy of batch k-1
@@ -479,7 +577,11 @@ class HostPipeline:
         dev = tracker.device
         w, h = tracker.img_size
         S = tracker.n_streams
-        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        # H2D, front half (stateless kernels), back half (searches, state, overlay), D2H: four streams, so that the
+        # front half of batch k+1 also fills the SMs the small back-half kernels of batch k leave idle
+        self.s_in, self.s_front, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(4))
+        self._k = 0
+        self._set_free = [None, None]   # per intermediate buffer set: event of the last back half that read it
         self.slots = []
         for _ in range(self.depth):
             self.slots.append(dict(
@@ -513,12 +615,22 @@ class HostPipeline:
             else:
                 sl["d_in"][:n].copy_(host_frames, non_blocking=True)
             sl["e_in"].record(self.s_in)
+        bs = self._k & 1
+        self._k += 1
+        with torch.cuda.stream(self.s_front):
+            self.s_front.wait_event(sl["e_in"])
+            if self._set_free[bs] is not None:
+                self.s_front.wait_event(self._set_free[bs])
+            self.t.process_front_async(sl["d_in"][:n], bs, params=self.params)
+            e_front = torch.cuda.Event()
+            e_front.record(self.s_front)
         with torch.cuda.stream(self.s_run):
-            self.s_run.wait_event(sl["e_in"])
+            self.s_run.wait_event(e_front)
             self.s_run.wait_event(sl["e_out"])           # the previous D2H out of this output buffer is done
             d_out = sl["d_in"][:n] if self.inplace else (sl["d_out"][:n] if self.overlay else None)
-            self.t.process_async(sl["d_in"][:n], d_out, params=self.params, results_dev=sl["d_res"])
+            self.t.process_back_async(sl["d_in"][:n], d_out, bs, params=self.params, results_dev=sl["d_res"])
             sl["e_run"].record(self.s_run)
+        self._set_free[bs] = sl["e_run"]
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(sl["e_run"])
             if self.inplace:

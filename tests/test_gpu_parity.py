@@ -806,3 +806,45 @@ def test_debug_view_stage_methods_match_oracle(torch_mod, bt, frames_np):
         lt.triple_split_view([a, b, mask])
     with pytest.raises(NotImplementedError):
         create_split_view((900, 500), [b], [(0, 0)], [(400, 300)], captions=["x"])
+
+
+def test_device_pipeline_matches_sequential_process(torch_mod):
+    """DevicePipeline (front half of batch k+1 on one stream under the back half of batch k on another, two
+    intermediate buffer sets) == sequential process() calls: results, state and annotated frames, including a
+    stream that fails every attempt (second-attempt filter reads the planes of its own buffer set)."""
+    from lane_tracker_b200 import BatchedLaneTracker, DevicePipeline
+    S, T = 3, 7
+    vids = [synth.RoadVideo(s) for s in range(S - 1)]
+    noise = np.random.default_rng(5).integers(0, 256, (720, 1280, 3), dtype=np.uint8)
+    batches = [torch_mod.from_numpy(np.stack([v.frame(t) for v in vids] + [noise])).cuda() for t in range(T)]
+    seq = BatchedLaneTracker(S, **CAL)
+    want = []
+    for b in batches:
+        out = torch_mod.empty_like(b)
+        want.append((seq.process(b, out), out))
+    pip = BatchedLaneTracker(S, **CAL)
+    dp = DevicePipeline(pip)
+    outs = [torch_mod.empty_like(b) for b in batches]
+    got = []
+    for b, o in zip(batches, outs):
+        dp.submit(b, o)
+        got.append(dp.fetch_results(S))
+    # and without synchronising between submissions
+    pip2 = BatchedLaneTracker(S, **CAL)
+    dp2 = DevicePipeline(pip2)
+    outs2 = [torch_mod.empty_like(b) for b in batches]
+    for b, o in zip(batches, outs2):
+        dp2.submit(b, o)
+    last = dp2.fetch_results(S)
+    for t in range(T):
+        for f in want[t][0].dtype.names:
+            assert np.array_equal(want[t][0][f], got[t][f]), (t, f)
+        assert torch_mod.equal(want[t][1], outs[t]) and torch_mod.equal(want[t][1], outs2[t]), t
+    for f in last.dtype.names:
+        assert np.array_equal(want[-1][0][f], last[f]), f
+    assert want[-1][0]["attempts"][S - 1] == 2
+    for s in range(S):
+        a, b = seq.get_state(s), pip2.get_state(s)
+        assert bytes(a[0]) == bytes(b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    for t_ in (seq, pip, pip2):
+        t_.close()
