@@ -21,3 +21,20 @@ for i in range(3):
     res = t.process(d, out, mask_noise=bool(i == 2))
 print("ok", res["valid_lane_lines"], res["attempts"])
 t.close()
+
+# two batches in flight (front / back halves on two streams, both intermediate buffer sets)
+from lane_tracker_b200 import DevicePipeline, LaneTracker  # noqa: E402
+t = BatchedLaneTracker(2, **cal)
+pipe = DevicePipeline(t)
+batches = [torch.from_numpy(np.stack([vid.frame(i), noise])).cuda() for i in range(4)]
+outs = [torch.empty_like(b) for b in batches]
+for b, o in zip(batches, outs):
+    pipe.submit(b, o)
+print("pipelined ok", pipe.fetch_results(2)["valid_lane_lines"])
+t.close()
+
+# debug views: sliding-window view, band view, split view with the resize
+lt = LaneTracker(**cal)
+for i in range(2):
+    canvas = lt.process(vid.frame(i), split_view=True)
+print("debug views ok", canvas.shape)
