@@ -63,7 +63,7 @@ template <int K> __host__ __device__ constexpr int ell_uidx(int w) {
 
 constexpr int MORPH_TW = 192;       // packed columns per CTA (= threads); 3 CTAs/SM x 6 warps at 96 registers/thread
 constexpr int MORPH_CTAS_PER_SM = 3;
-constexpr int MORPH_RB = 8;         // source rows per table build
+constexpr int MORPH_RB = 8;         // source rows per table build (12 measured the same: fewer barriers, more overrun rows)
 
 template <bool IS_MAX> __device__ __forceinline__ uint32_t op2(uint32_t a, uint32_t b) {
     return IS_MAX ? __vmaxu2(a, b) : __vminu2(a, b);
@@ -130,12 +130,12 @@ morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict
     // ---- staging: rows [rbase, rbase + RB) x columns [x0 - HA, x0 + TW + HA) as 16-byte cp.async, three groups of
     // 64 threads each taking every third row; the halo columns / pad rows of the padded planes make every address valid
     constexpr int CH = TE / 4;                                          // 16-byte chunks per staged row
-    static_assert(CH <= 64 && TW == 192 && RB == 8, "staging thread mapping");
+    static_assert(CH <= 64 && TW == 192 && RB % 4 == 0, "staging thread mapping");
     const int sg = tid >> 6, sc = tid & 63;
     const bool s_on = sc < CH;
     const uint32_t* sp = src + (ptrdiff_t)(r_begin + sg) * src_pitch + (x0 - HA + 4 * sc);    // advances RB rows per block
     uint32_t* const sdst = T0 + sg * TEP + 4 * sc;
-    // original rows for the top-hat epilogue: 48 chunks per row, thread -> (row tid / 48 and + 4, chunk tid % 48)
+    // original rows for the top-hat epilogue: 48 chunks per row, thread -> (rows tid / 48, + 4, ..., chunk tid % 48)
     const int orow = tid / 48, oc = tid - orow * 48;
     const bool o_on = TOPHAT && x0 + 4 * oc < d.p2;
     const uint32_t* op = TOPHAT ? orig + (ptrdiff_t)(r_begin - R + orow) * orig_pitch + (x0 + 4 * oc) : nullptr;
@@ -144,15 +144,16 @@ morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict
     auto stage_async = [&](int buf) {
         if (s_on) {
             uint32_t* t = sdst + buf * RB * TEP;
-            cp_async16(t, sp);
-            cp_async16(t + 3 * TEP, sp + 3 * (ptrdiff_t)src_pitch);
-            if (sg < 2) cp_async16(t + 6 * TEP, sp + 6 * (ptrdiff_t)src_pitch);
+#pragma unroll
+            for (int rr = 0; rr < RB; rr += 3)                          // rows sg, sg + 3, sg + 6, ...
+                if (sg + rr < RB) cp_async16(t + rr * TEP, sp + rr * (ptrdiff_t)src_pitch);
         }
         sp += (ptrdiff_t)RB * src_pitch;
         if (TOPHAT) {
             uint32_t* t = odst + buf * RB * TW;
-            if (o_on && (unsigned)oy < (unsigned)d.bv_h) cp_async16(t, op);
-            if (o_on && (unsigned)(oy + 4) < (unsigned)d.bv_h) cp_async16(t + 4 * TW, op + 4 * (ptrdiff_t)orig_pitch);
+#pragma unroll
+            for (int rr = 0; rr < RB; rr += 4)                          // rows orow, orow + 4, ...
+                if (o_on && (unsigned)(oy + rr) < (unsigned)d.bv_h) cp_async16(t + rr * TW, op + rr * (ptrdiff_t)orig_pitch);
             op += (ptrdiff_t)RB * orig_pitch;
             oy += RB;
         }
