@@ -248,36 +248,38 @@ __device__ __forceinline__ uint32_t blend_rgbx(uint32_t t00, uint32_t t01, uint3
 // carry the erosion pad 0xFFFF, and the columns next to the seam are mirrored into the halo of the other strip
 // (column -j holds pixel p2 - j in its hi lane, column p2 + j holds pixel p2 + j in its lo lane).
 __device__ __forceinline__ void store_padded(uint32_t* __restrict__ planeR, uint32_t* __restrict__ planeB, uint32_t r2,
-                                             uint32_t b2, int x, int y, int s, size_t stream_pad, const LtDims& d) {
+                                             uint32_t b2, int x, int y, int s, unsigned stream_pad, const LtDims& d) {
     const bool hi_real = x + d.p2 < d.bv_w;
     if (!hi_real) { r2 |= 0xFFFF0000u; b2 |= 0xFFFF0000u; }
-    const size_t row = (size_t)s * stream_pad + (ptrdiff_t)y * d.pp;
-    planeR[row + x] = r2;
-    planeB[row + x] = b2;
+    uint32_t* pr = planeR + (size_t)((unsigned)s) * stream_pad;  // per-stream base (one 32x32->64 multiply); offsets below fit 32 bits
+    uint32_t* pb = planeB + (size_t)((unsigned)s) * stream_pad;
+    const int o = y * d.pp + x;
+    pr[o] = r2;
+    pb[o] = b2;
     if (x >= d.p2 - LT_HALO_X) {
-        planeR[row + x - d.p2] = (r2 << 16) | 0xFFFFu;
-        planeB[row + x - d.p2] = (b2 << 16) | 0xFFFFu;
+        pr[o - d.p2] = (r2 << 16) | 0xFFFFu;
+        pb[o - d.p2] = (b2 << 16) | 0xFFFFu;
     }
     if (x < LT_HALO_X) {
-        planeR[row + x + d.p2] = (r2 >> 16) | 0xFFFF0000u;      // hi lane of a halo column lies beyond the image
-        planeB[row + x + d.p2] = (b2 >> 16) | 0xFFFF0000u;
+        pr[o + d.p2] = (r2 >> 16) | 0xFFFF0000u;                // hi lane of a halo column lies beyond the image
+        pb[o + d.p2] = (b2 >> 16) | 0xFFFF0000u;
     }
 }
 
 __global__ void __launch_bounds__(256)
 k_warp_planes(const uchar4* __restrict__ und_all, const int2* __restrict__ desc, uint32_t* __restrict__ planeR,
               uint32_t* __restrict__ planeB, uint8_t* __restrict__ bv_rgb,
-              const unsigned short* __restrict__ g, const unsigned short* __restrict__ cb, LtDims d, size_t stream_pad) {
+              const unsigned short* __restrict__ g, const unsigned short* __restrict__ cb, LtDims d, unsigned stream_pad) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y, s = blockIdx.z;
     if (x >= d.p2) return;
-    const uint32_t* und = reinterpret_cast<const uint32_t*>(und_all) + (size_t)s * (d.roi1 - d.roi0) * d.img_w;
+    const uint32_t* und = reinterpret_cast<const uint32_t*>(und_all) + (size_t)((unsigned)s) * (unsigned)((d.roi1 - d.roi0) * d.img_w);
     uint32_t r2 = 0, b2 = 0;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         int px = x + half * d.p2;
         if (px < d.bv_w) {
-            int2 q = __ldg(&desc[(size_t)y * d.bv_w + px]);
+            int2 q = __ldg(&desc[y * d.bv_w + px]);                        // < 2^31 entries
             const uint32_t* base = und + q.x;
             const uint32_t f = (uint32_t)q.y;
             if (!(f >> 10)) {                          // no tap inside the frame: the pixel is black, Lab b of black = 128
@@ -308,7 +310,7 @@ int lt_launch_warp(lt_handle* h, uint8_t* d_bv_rgb, int n, cudaStream_t st) {
     const LtDims& d = h->d;
     dim3 g(lt_div_up(d.p2, 256), d.bv_h, n);
     k_warp_planes<<<g, 256, 0, st>>>(h->und_roi, h->bv_desc, h->planeR, h->planeB, d_bv_rgb, h->lab_gamma,
-                                     h->lab_cbrt, d, h->stream_pad);
+                                     h->lab_cbrt, d, (unsigned)h->stream_pad);
     LT_LAUNCH_CHECK();
     return 0;
 }
@@ -375,7 +377,7 @@ int lt_launch_build_fused_desc(lt_handle* h, cudaStream_t st) {
 __global__ void __launch_bounds__(256)
 k_warp_planes_fused(const uint8_t* __restrict__ frames, const int2* __restrict__ desc, uint32_t* __restrict__ planeR,
                     uint32_t* __restrict__ planeB, uint8_t* __restrict__ bv_rgb,
-                    const unsigned short* __restrict__ g, const unsigned short* __restrict__ cb, LtDims d, size_t stream_pad) {
+                    const unsigned short* __restrict__ g, const unsigned short* __restrict__ cb, LtDims d, unsigned stream_pad) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y, s = blockIdx.z;
     if (x >= d.p2) return;
@@ -408,7 +410,7 @@ int lt_launch_warp_fused(lt_handle* h, const uint8_t* d_frames, uint8_t* d_bv_rg
     const LtDims& d = h->d;
     dim3 g(lt_div_up(d.p2, 256), d.bv_h, n);
     k_warp_planes_fused<<<g, 256, 0, st>>>(d_frames, h->fused_desc, h->planeR, h->planeB, d_bv_rgb, h->lab_gamma,
-                                           h->lab_cbrt, d, h->stream_pad);
+                                           h->lab_cbrt, d, (unsigned)h->stream_pad);
     LT_LAUNCH_CHECK();
     return 0;
 }
@@ -416,7 +418,7 @@ int lt_launch_warp_fused(lt_handle* h, const uint8_t* d_frames, uint8_t* d_bv_rg
 // planes from a caller-supplied bird's-eye RGB image (filter_lane_points API, lane_tracker.py:207-208)
 __global__ void __launch_bounds__(256)
 k_planes_from_bv(const uint8_t* __restrict__ bv_rgb, uint32_t* __restrict__ planeR, uint32_t* __restrict__ planeB,
-                 const unsigned short* __restrict__ g, const unsigned short* __restrict__ cb, LtDims d, size_t stream_pad) {
+                 const unsigned short* __restrict__ g, const unsigned short* __restrict__ cb, LtDims d, unsigned stream_pad) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y, s = blockIdx.z;
     if (x >= d.p2) return;
@@ -437,7 +439,7 @@ k_planes_from_bv(const uint8_t* __restrict__ bv_rgb, uint32_t* __restrict__ plan
 int lt_launch_planes_from_bv(lt_handle* h, const uint8_t* d_bv_rgb, int n, cudaStream_t st) {
     const LtDims& d = h->d;
     dim3 g(lt_div_up(d.p2, 256), d.bv_h, n);
-    k_planes_from_bv<<<g, 256, 0, st>>>(d_bv_rgb, h->planeR, h->planeB, h->lab_gamma, h->lab_cbrt, d, h->stream_pad);
+    k_planes_from_bv<<<g, 256, 0, st>>>(d_bv_rgb, h->planeR, h->planeB, h->lab_gamma, h->lab_cbrt, d, (unsigned)h->stream_pad);
     LT_LAUNCH_CHECK();
     return 0;
 }
