@@ -684,15 +684,28 @@ def test_abi_error_paths_partial_batches_and_lifetime(torch_mod):
     b.process(f0); b.process(f0)
     stages, calls = b.profile_read()
     assert calls == 2 and stages["erode55"] > 0 and stages["tophat55"] > 0 and stages["warp"] > 0
+    # selective marks: only the named boundaries are recorded (and the second buffer set works on its own)
+    b.profile_select(["warp", "erode55", "tophat55"])
+    b.profile_begin(1)
+    b.process_front_async(f0, 1)
+    b.process_back_async(f0, None, 1)
+    stages, calls = b.profile_read()
+    assert calls == 1 and stages["erode55"] > 0 and stages["tophat55"] > 0 and stages["search"] == 0 and stages["cross_r"] == 0
+    b.profile_select(None)
+    with pytest.raises(_lib.LaneTrackerError, match="buffer set"):
+        b.process_front_async(f0, 2)
+    assert b.get_state(0)[0].counter == 5
     b.close()
     b.close()                                     # idempotent
     f2 = f0[:2].contiguous()
     torch_mod.cuda.synchronize()
     free1 = torch_mod.cuda.mem_get_info()[0]      # kernels loaded, torch's cache warm
-    for _ in range(8):                            # handles release their device memory
+    for _ in range(8):                            # handles release their device memory (both buffer sets)
         t = BatchedLaneTracker(2, **CAL)
         t.set_capture(True)
         t.process(f2)
+        t.process_front_async(f2, 1)
+        torch_mod.cuda.synchronize()
         t.close()
     torch_mod.cuda.synchronize()
     assert abs(torch_mod.cuda.mem_get_info()[0] - free1) < 16 << 20
