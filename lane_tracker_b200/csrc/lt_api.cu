@@ -132,6 +132,9 @@ extern "C" int lt_destroy(lt_handle* h) {
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < h->prof_cap; ++i) cudaEventDestroy(h->prof_ev[i]);
     delete[] h->prof_ev; delete[] h->prof_stage;
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
     return 0;
 }
@@ -250,6 +253,11 @@ extern "C" int lt_create(const lt_config* cfg, lt_handle** out) {
     A(state, S); A(att, 2 * S); A(retry_list, S); A(retry_count, 1); A(draw_flags, 2 * S);
 #undef A
     if (rc) { lt_destroy(h); return rc; }
+    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        lt_set_error("cannot create the side stream"); lt_destroy(h); return -2;
+    }
     cudaMemset(h->avg_x, 0, S * 2 * (size_t)d.bv_h * sizeof(int));
     cudaMemset(h->lane_rows, 0, S * (size_t)d.bv_h * sizeof(int2));
     cudaMemset(h->draw_flags, 0, 2 * S * sizeof(int));

@@ -111,6 +111,8 @@ struct lt_handle {
     uint32_t prof_mask;          // 0: every stage boundary is marked; else only the boundaries whose bit is set
     uint8_t* scratch_bv;         // lazily allocated [S][bv_h][bv_w][3] for stage calls
     unsigned char* vis_scratch;  // lazily allocated work area of lt_visualize_search
+    cudaStream_t side;           // carries the horizontal threshold halves next to the vertical ones (lt_launch_filter)
+    cudaEvent_t ev_fork, ev_join;
     size_t stream_pad;           // entries per stream in a padded pair plane
     size_t stream_mask;          // words per stream in a bit mask
 };

@@ -867,8 +867,8 @@ int lt_launch_plane_to_u8(lt_handle* h, const uint32_t* plane, int pitch, uint8_
 // the whole filter for one attempt
 // ---------------------------------------------------------------------------
 
-static int launch_cross(lt_handle* h, const uint32_t* plane, uint32_t* bits, int k, int C, int accumulate, int n,
-                        const int* list, const int* count, cudaStream_t st) {
+static int launch_cross_h(lt_handle* h, const uint32_t* plane, uint32_t* bits, int k, int C, int accumulate, int n,
+                          const int* list, const int* count, cudaStream_t st) {
     const LtDims& d = h->d;
     const int ppitch = d.pp;
     const size_t pstride = h->stream_pad;
@@ -892,6 +892,14 @@ static int launch_cross(lt_handle* h, const uint32_t* plane, uint32_t* bits, int
                                                             h->stream_mask, list, count);
         LT_LAUNCH_CHECK();
     }
+    return 0;
+}
+
+static int launch_cross_v(lt_handle* h, const uint32_t* plane, uint32_t* bits, int k, int C, int n,
+                          const int* list, const int* count, cudaStream_t st) {
+    const LtDims& d = h->d;
+    const int ppitch = d.pp;
+    const size_t pstride = h->stream_pad;
     dim3 gv(d.p2 / 32, lt_div_up(d.bv_h, CV_BAND), n);
     const bool packed = k <= 127 && C >= 0 && k * 255 + C * k + 1 < 32768;
     const bool rowpad = k + CV_CHUNK <= LT_HALO_Y;
@@ -903,6 +911,14 @@ static int launch_cross(lt_handle* h, const uint32_t* plane, uint32_t* bits, int
 #undef LT_CROSS_V
     LT_LAUNCH_CHECK();
     return 0;
+}
+
+// horizontal half writes (or ORs) the words, vertical half ORs into them
+static int launch_cross(lt_handle* h, const uint32_t* plane, uint32_t* bits, int k, int C, int accumulate, int n,
+                        const int* list, const int* count, cudaStream_t st) {
+    int rc = launch_cross_h(h, plane, bits, k, C, accumulate, n, list, count, st);
+    if (rc) return rc;
+    return launch_cross_v(h, plane, bits, k, C, n, list, count, st);
 }
 
 static int launch_box_pair(lt_handle* h, int block_r, int c_r, int block_b, int c_b, int n, const int* list,
@@ -937,10 +953,26 @@ int lt_launch_filter(lt_handle* h, int n, const LtAttemptParams& p, const int* l
         MorphJob t55 = {h->tmpB, h->topB, h->planeB, 0, 0}, t29 = {h->tmpR, h->topR, h->planeR, 0, 0};
         if ((rc = launch_morph_pair<true, true>(h, t55, t29, n, list, count, st))) return rc;
         lt_prof_mark(h, ST_TOPHAT55, st);           // both dilations + top-hat epilogues in one launch
-        if ((rc = launch_cross(h, h->topR, h->merged, p.ksize_r, p.C_r, 0, n, list, count, st))) return rc;
-        lt_prof_mark(h, ST_CROSS_R, st);
-        if ((rc = launch_cross(h, h->topB, h->merged, p.ksize_b, p.C_b, 1, n, list, count, st))) return rc;
-        lt_prof_mark(h, ST_CROSS_B, st);
+        if (list == nullptr && h->side) {
+            // The four threshold halves (R/Lab-b x horizontal/vertical) only OR bits into the merged mask and each
+            // of them fills about half of the issue slots: the horizontal pair runs on a side stream, the vertical
+            // pair on the caller's stream.  (Stage "cross_b" then reports both planes.)
+            LT_CUDA(cudaMemsetAsync(h->merged, 0, (size_t)n * h->stream_mask * sizeof(uint32_t), st));
+            LT_CUDA(cudaEventRecord(h->ev_fork, st));
+            LT_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+            if ((rc = launch_cross_h(h, h->topR, h->merged, p.ksize_r, p.C_r, 1, n, list, count, h->side))) return rc;
+            if ((rc = launch_cross_h(h, h->topB, h->merged, p.ksize_b, p.C_b, 1, n, list, count, h->side))) return rc;
+            LT_CUDA(cudaEventRecord(h->ev_join, h->side));
+            if ((rc = launch_cross_v(h, h->topR, h->merged, p.ksize_r, p.C_r, n, list, count, st))) return rc;
+            if ((rc = launch_cross_v(h, h->topB, h->merged, p.ksize_b, p.C_b, n, list, count, st))) return rc;
+            LT_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+            lt_prof_mark(h, ST_CROSS_B, st);
+        } else {
+            if ((rc = launch_cross(h, h->topR, h->merged, p.ksize_r, p.C_r, 0, n, list, count, st))) return rc;
+            lt_prof_mark(h, ST_CROSS_R, st);
+            if ((rc = launch_cross(h, h->topB, h->merged, p.ksize_b, p.C_b, 1, n, list, count, st))) return rc;
+            lt_prof_mark(h, ST_CROSS_B, st);
+        }
     } else {
         if ((rc = launch_box_pair(h, p.ksize_r, p.C_r, p.ksize_b, p.C_b, n, list, count, st))) return rc;
         lt_prof_mark(h, ST_BOX, st);
