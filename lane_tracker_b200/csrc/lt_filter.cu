@@ -332,7 +332,7 @@ static void choose_bands(lt_handle* h, int n, int tiles, int H, int slots, int* 
         for (int b = 1; b <= 24; ++b) {
             int ra = lt_div_up(H, a), rb = lt_div_up(H, b);
             int na = n * tiles * lt_div_up(H, ra), nb = n * tiles * lt_div_up(H, rb);
-            double ta = (ra + 54) * 0.735, tb = (rb + 28) * 0.412;
+            double ta = (ra + 54) * 0.735, tb = (rb + 28) * 0.513;
             freeat.assign(slots, 0.0);
             // CTAs start in grid order on the earliest free slot
             std::make_heap(freeat.begin(), freeat.end(), std::greater<double>());

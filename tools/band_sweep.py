@@ -14,7 +14,7 @@ def main():
     dev = torch.device("cuda", 0)
     pool = torch.from_numpy(synth.render_streams(S, P, first_seed=0, workers=16)).to(dev).permute(1, 0, 2, 3, 4).contiguous()
     out = torch.empty_like(pool[0])
-    combos = [None] + [(a, b) for a in (2, 3, 4, 5, 6, 7) for b in (1, 2, 3, 4)]
+    combos = [None] + [(a, b) for a in (1, 2, 3) for b in (3, 4, 5, 6, 7, 8, 10)]
     for c in combos:
         if c is None:
             os.environ.pop("LT_MORPH_BANDS", None)
