@@ -26,9 +26,9 @@ def create_split_view(target_size, images, positions, sizes, captions=[], _devic
     import torch
 
     from . import _lib
-    assert len(images) == len(positions) == len(sizes), \
-        "`images`, `positions`, and `sizes` must have the same length, but it is `len(images) == {}`, " \
-        "`len(poisitons) = {}`, `len(sizes) == {}`".format(len(images), len(positions), len(sizes))
+    if not (len(images) == len(positions) == len(sizes)):       # the reference asserts the same condition
+        raise AssertionError("images, positions and sizes must have one entry per panel (got %d, %d, %d)"
+                             % (len(images), len(positions), len(sizes)))
     if captions and any(c is not None for c in captions):
         raise NotImplementedError("captions (cv2.putText at font scale 0.8) are not supported")
     if not torch.cuda.is_available():
