@@ -476,6 +476,51 @@ class BatchedLaneTracker:
         return out
 
 
+class GraphedProcess:
+    """``process_async`` of a fixed batch shape captured once into a CUDA graph and replayed per frame: the chain
+    of ~20 small launches costs one launch.  Pays off for few streams (one stream: 0.23 -> 0.19 ms per frame);
+    ``lt_process`` only enqueues kernels (and forks/joins its side stream with events), so it is capturable.
+
+        g = GraphedProcess(tracker, n_streams)          # static device buffers g.frames / g.out
+        g.frames.copy_(batch, non_blocking=True); g.replay(); results = g.fetch_results()
+    """
+
+    def __init__(self, tracker, n=None, overlay=True, params=None):
+        self.t = tracker
+        n = tracker.n_streams if n is None else int(n)
+        dev = tracker.device
+        w, h = tracker.img_size
+        self.n = n
+        self.frames = torch.zeros((n, h, w, 3), dtype=torch.uint8, device=dev)
+        self.out = torch.empty_like(self.frames) if overlay else None
+        self.results_dev = torch.zeros(n * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        self.params = params if params is not None else make_params()
+        # first-use initialisation (module load, shared-memory attributes) cannot happen inside a capture: run the
+        # chain once for real on a side stream, with the tracking state saved and restored around it
+        saved = [tracker.get_state(s) for s in range(n)]
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            tracker.process_async(self.frames, self.out, params=self.params, results_dev=self.results_dev)
+        side.synchronize()
+        for s, (st, lx, rx) in enumerate(saved):
+            tracker.set_state(s, st, lx, rx)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=side):
+            tracker.process_async(self.frames, self.out, params=self.params, results_dev=self.results_dev)
+        torch.cuda.current_stream(dev).wait_stream(side)
+
+    def replay(self):
+        """Enqueue one frame per stream (read from ``self.frames``) on the current stream."""
+        self.graph.replay()
+
+    def fetch_results(self):
+        nbytes = self.n * RESULT_DTYPE.itemsize
+        self.t._results_host[:nbytes].copy_(self.results_dev[:nbytes], non_blocking=True)
+        torch.cuda.current_stream(self.t.device).synchronize()
+        return self.t._results_host[:nbytes].numpy().view(RESULT_DTYPE).copy()
+
+
 class DevicePipeline:
     """Two batches in flight on the device: the stateless front half of batch k+1 (undistort, warp, filter) runs on
     one CUDA stream while the stateful back half of batch k (searches, state machine, overlay) runs on another.

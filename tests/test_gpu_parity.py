@@ -861,3 +861,41 @@ def test_device_pipeline_matches_sequential_process(torch_mod):
         assert bytes(a[0]) == bytes(b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     for t_ in (seq, pip, pip2):
         t_.close()
+
+
+def test_graphed_process_matches_sequential_process(torch_mod):
+    """GraphedProcess (lt_process captured once into a CUDA graph, side-stream fork/join included) == process():
+    results, frames and state; building the graph leaves the tracking state untouched."""
+    from lane_tracker_b200 import BatchedLaneTracker, GraphedProcess
+    S, T = 2, 6
+    vids = [synth.RoadVideo(20 + s) for s in range(S)]
+    batches = [torch_mod.from_numpy(np.stack([v.frame(t) for v in vids])).cuda() for t in range(T)]
+    seq, gr = BatchedLaneTracker(S, **CAL), BatchedLaneTracker(S, **CAL)
+    want = []
+    for b in batches:
+        o = torch_mod.empty_like(b)
+        want.append((seq.process(b, o), o))
+    gr.process(batches[0], torch_mod.empty_like(batches[0]))        # some state before the capture
+    g = GraphedProcess(gr, S)
+    assert gr.get_state(0)[0].counter == 1 and bytes(gr.get_state(1)[0]) == bytes(seq_state_after_one(seq, CAL, batches[0], 1))
+    for t in range(1, T):
+        g.frames.copy_(batches[t], non_blocking=True)
+        g.replay()
+        r = g.fetch_results()
+        for f in r.dtype.names:
+            assert np.array_equal(r[f], want[t][0][f]), (t, f)
+        assert torch_mod.equal(g.out, want[t][1]), t
+    for s in range(S):
+        a, b = seq.get_state(s), gr.get_state(s)
+        assert bytes(a[0]) == bytes(b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    seq.close(); gr.close()
+
+
+def seq_state_after_one(_seq, cal, batch, stream):
+    """lt_state of `stream` after exactly one process() call on a fresh tracker."""
+    from lane_tracker_b200 import BatchedLaneTracker
+    t = BatchedLaneTracker(int(batch.shape[0]), **cal)
+    t.process(batch)
+    st = t.get_state(stream)[0]
+    t.close()
+    return st
