@@ -488,7 +488,7 @@ k_cross_h(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_al
     const uint32_t kk = (uint32_t)k;
     const uint32_t bias = ((uint32_t)(C * k + 1)) * 0x00010001u;         // pass <=> k*p >= side + C*k + 1
     int x = w0 * 32;
-    uint32_t L = 0, Rs = 0;
+    uint32_t L = bias, Rs = bias;                                        // the running sums carry the compare bias
     for (int i = 1; i <= k; ++i) { L += unpack_pair(trow[x - i]); Rs += unpack_pair(trow[x + i]); }
     uint32_t p = unpack_pair(trow[x]);
     uint32_t* brow = bits_all + (size_t)s * bits_stride + (size_t)min(y, d.bv_h - 1) * d.mwords;
@@ -497,11 +497,10 @@ k_cross_h(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_al
 #pragma unroll 4
         for (int b = 0; b < 32; ++b, ++x) {
             // lanes hold values < 2^15 (k <= 127): bit 15 of ((A | 0x8000) - B) is set iff A >= B, per lane
-            uint32_t T = (p * kk) | 0x80008000u;
-            uint32_t okL = T - (L + bias), okR = T - (Rs + bias);
-            uint32_t ok = okL & okR;
-            wl |= ((ok >> 15) & 1u) << b;
-            wh |= ((ok >> 31) & 1u) << b;
+            uint32_t T = p * kk + 0x80008000u;
+            uint32_t ok = (T - L) & (T - Rs);
+            wl = __funnelshift_r(wl, ok >> 15, 1);                       // shift the pass bit in from the top: after
+            wh = __funnelshift_r(wh, ok >> 31, 1);                       // 32 columns bit b belongs to column b
             uint32_t pn = unpack_pair(trow[x + 1]);
             L = L + p - unpack_pair(trow[x - k]);
             Rs = Rs + unpack_pair(trow[x + k + 1]) - pn;
