@@ -236,11 +236,11 @@ __device__ __forceinline__ uint32_t blend_rgbx(uint32_t t00, uint32_t t01, uint3
     const uint32_t fx = f & 31u, fy = (f >> 5) & 31u, gx = 32u - fx, gy = 32u - fy;
     uint32_t rb0 = (t00 & 0x00FF00FFu) * gx + (t01 & 0x00FF00FFu) * fx;      // lanes <= 255*32
     uint32_t rb1 = (t10 & 0x00FF00FFu) * gx + (t11 & 0x00FF00FFu) * fx;
-    uint32_t g0 = ((t00 >> 8) & 0xFFu) * gx + ((t01 >> 8) & 0xFFu) * fx;
-    uint32_t g1 = ((t10 >> 8) & 0xFFu) * gx + ((t11 >> 8) & 0xFFu) * fx;
+    // G of the two tap rows rides in two 16-bit halves as well (byte 3 of every tap is 0: RGBX / 24-bit values)
+    uint32_t g01 = __byte_perm(t00, t10, 0x3531) * gx + __byte_perm(t01, t11, 0x3531) * fx;
     uint32_t R = ((rb0 & 0xFFFFu) * gy + (rb1 & 0xFFFFu) * fy + 512u) >> 10;
     uint32_t B = ((rb0 >> 16) * gy + (rb1 >> 16) * fy + 512u) >> 10;
-    uint32_t G = (g0 * gy + g1 * fy + 512u) >> 10;
+    uint32_t G = ((g01 & 0xFFFFu) * gy + (g01 >> 16) * fy + 512u) >> 10;
     return R | (G << 8) | (B << 16);
 }
 
