@@ -144,6 +144,8 @@ __device__ __forceinline__ uint32_t blend_rgb(uint32_t a, uint32_t b, uint32_t c
     return out;
 }
 
+__device__ __forceinline__ uint32_t blend_rgbx(uint32_t t00, uint32_t t01, uint32_t t10, uint32_t t11, uint32_t f);
+
 __global__ void __launch_bounds__(256)
 k_undistort_roi(const uint8_t* __restrict__ frames, uchar4* __restrict__ und, const int2* __restrict__ map,
                 LtDims d) {
@@ -152,12 +154,14 @@ k_undistort_roi(const uint8_t* __restrict__ frames, uchar4* __restrict__ und, co
     int s = blockIdx.z;
     if (j >= d.img_w) return;
     const uint8_t* img = frames + (size_t)s * d.img_w * d.img_h * 3;
-    Tap4 t = make_taps(__ldg(&map[(size_t)i * d.img_w + j]));
+    const int2 q = __ldg(&map[i * d.img_w + j]);
+    Tap4 t = make_taps(q);
     uint32_t a = load_rgb(img, d.img_w, d.img_h, t.sy, t.sx);
     uint32_t b = load_rgb(img, d.img_w, d.img_h, t.sy, t.sx + 1);
     uint32_t c = load_rgb(img, d.img_w, d.img_h, t.sy + 1, t.sx);
     uint32_t e = load_rgb(img, d.img_w, d.img_h, t.sy + 1, t.sx + 1);
-    uint32_t o = blend_rgb(a, b, c, e, t);
+    // separable packed form of sum(tap * w): the same integer as the four-weight sum (no intermediate rounding)
+    uint32_t o = blend_rgbx(a, b, c, e, (uint32_t)(q.x & 31) | ((uint32_t)(q.y & 31) << 5));
     und[((size_t)s * (d.roi1 - d.roi0) + (i - d.roi0)) * d.img_w + j] =
         make_uchar4(o & 255, (o >> 8) & 255, (o >> 16) & 255, 0);
 }
