@@ -84,6 +84,10 @@ def test_product_fails_loudly_without_a_gpu():
     from lane_tracker_b200 import LaneTracker, _lib, synth
     with pytest.raises(_lib.LaneTrackerError):
         LaneTracker(**synth.shipped_calibration())
+    import numpy as np
+    from lane_tracker_b200 import create_split_view            # the split-view helper resizes on the GPU: no CPU path
+    with pytest.raises(_lib.LaneTrackerError):
+        create_split_view((64, 64), [np.zeros((32, 32, 3), np.uint8)], [(0, 0)], [(16, 16)])
 
 
 def test_product_never_imports_the_oracle():
