@@ -162,6 +162,11 @@ int lt_process_back(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int32
  * right_x/right_y/left_window_centroids, lane_tracker.py:159-166).  Off by default: the
  * throughput path needs only the moment sums. */
 int lt_set_capture(lt_handle* h, int32_t enable);
+/* Capacity (entries per stream and side) of the ordered pixel lists kept for lt_read_capture.  Default:
+ * max(65536, 64 * bv_h), enough for the sliding-window search (window_width <= 64) and for band searches with
+ * bandwidth <= 32; a band-search row can hold 2 * bandwidth - 1 pixels, and lt_process rejects a bandwidth whose
+ * lists could overflow while capture is on.  Synchronous; reallocates the capture buffers. */
+int lt_set_pixel_capacity(lt_handle* h, int32_t capacity);
 /* attempt: 0 first, 1 second.  h_pixels: (y<<16 | x+32768), up to `capacity` entries;
  * h_count: true count; h_centroids: LT_MAX_LEVELS ints (sliding-window search only). Synchronous. */
 int lt_read_capture(lt_handle* h, int32_t stream_id, int32_t attempt, int32_t side, uint32_t* h_pixels,
@@ -298,7 +303,8 @@ int lt_set_state(lt_handle* h, int32_t stream_id, const lt_state* h_state, const
  *       5 R top-hat, 6 b top-hat, 7 mask u8 {0,255}, 8 merged (pre-open) mask,
  *       9 lane row spans int32 [bv_h][2], 10 geometry int32[9] = {undistorted ROI first,last+1, overlay rows
  *       first,last+1, pair-plane width, mask words per row, pixel-list capacity of lt_read_capture, frame rows the
- *       tracker reads first,last+1}.
+ *       tracker reads first,last+1}, 11 int32[3] = {row bands of the 55x55 and of the 29x29 morphology jobs in the
+ *       last filter launch, SM count of the device}.
  * Copies to HOST memory; synchronous. Returns bytes written or <0. */
 int64_t lt_debug_read(lt_handle* h, int32_t what, int32_t stream_id, void* h_dst, int64_t capacity);
 

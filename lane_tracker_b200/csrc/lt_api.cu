@@ -88,6 +88,20 @@ static int check_params(const lt_handle* h, const LtAttemptParams& a) {
         lt_set_error("partial must lie in [0, 1] and ignore_bottom in [0, warped height]");
         return -1;
     }
+    // the sliding-window walk keeps one centroid / one window per level in fixed-size arrays (LT_MAX_LEVELS): a
+    // parameter set that needs more levels is rejected instead of being searched short (lane_tracker.py:346)
+    const long long nlev = (long long)(a.partial * (double)(h->d.bv_h - a.ignore_bottom) / (double)a.window_height);
+    if (nlev > LT_MAX_LEVELS) {
+        lt_set_error("window_height %d gives %lld search levels; at most %d are supported", a.window_height, nlev, LT_MAX_LEVELS);
+        return -1;
+    }
+    if (a.search_range < 0 || a.search_range > h->d.bv_w || a.ignore_sides < 0 || a.ignore_sides > h->d.bv_w ||
+        a.no_success_limit < 0 || a.bandwidth < 0 || a.bandwidth > h->d.bv_w || !(a.mu == a.mu) ||
+        !(a.start_slice >= 0.0 && a.start_slice <= 1.0)) {
+        lt_set_error("search_range, ignore_sides and bandwidth must lie in [0, warped width], no_success_limit >= 0, "
+                     "start_slice in [0, 1]");
+        return -1;
+    }
     return 0;
 }
 
@@ -126,7 +140,7 @@ extern "C" int lt_destroy(lt_handle* h) {
     }
     void* ptrs[] = {h->und_map, h->bv_map, h->ov_map, h->bv_desc, h->fused_desc, h->lab_gamma, h->lab_cbrt, h->pixels, h->pix_counts, h->lane_rows,
                     h->avg_x, h->state, h->att, h->retry_list, h->retry_count, h->draw_flags, h->scratch_bv, h->vis_scratch,
-                    h->cap_pixels, h->cap_counts, h->cap_cents, h->cap_ncents,
+                    h->cap_pixels, h->cap_counts, h->cap_cents, h->cap_ncents, h->dl_rows, h->dl_flags,
                     h->txt_tables, h->txt_char_start, h->txt_dy, h->txt_dx, h->txt_lut, h->txt_advance, h->txt_pair_overlap,
                     h->txt_bitmaps};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -355,8 +369,19 @@ static int process_back(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, i
     if (d_out) {
         // (copying the untouched rows on a side stream under the search kernels was measured: the copy saturates HBM
         // and slows the search by what it saves -- the plain in-order copy stays)
-        if ((rc = lt_launch_overlay(h, d_frames, d_out, n, h->draw_flags, st))) return rc;
-        if ((rc = lt_launch_text(h, d_out, n, st))) return rc;
+        // draw_lane writes its text into the frame BEFORE the blend (lane_tracker.py:653-662).  With the shipped
+        // geometry the text rows and the rows the lane overlay can reach are disjoint and the order is immaterial;
+        // when they overlap (other calibrations) the text goes first and the blend runs in place over it.
+        const bool text_under_blend = h->txt_nchars > 0 && h->txt_row0 < h->d.ov1 && h->d.ov0 < h->txt_row1;
+        if (text_under_blend) {
+            if (d_out != d_frames)
+                LT_CUDA(cudaMemcpyAsync(d_out, d_frames, (size_t)n * h->d.img_w * h->d.img_h * 3, cudaMemcpyDeviceToDevice, st));
+            if ((rc = lt_launch_text(h, d_out, n, st))) return rc;
+            if ((rc = lt_launch_overlay(h, d_out, d_out, n, h->draw_flags, st))) return rc;
+        } else {
+            if ((rc = lt_launch_overlay(h, d_frames, d_out, n, h->draw_flags, st))) return rc;
+            if ((rc = lt_launch_text(h, d_out, n, st))) return rc;
+        }
         lt_prof_mark(h, ST_OVERLAY, st);
     }
     if (h->prof_active) h->prof_calls++;
@@ -370,6 +395,13 @@ static int process_args(lt_handle* h, const uint8_t* d_frames, int n, const lt_p
     if (set != 0 && set != 1) { lt_set_error("buffer set must be 0 or 1"); return -1; }
     *p1 = attempt_from(*params);
     if ((rc = check_params(h, *p1))) return rc;
+    // captured pixel lists: a band-search row holds up to 2*bandwidth - 1 pixels (attempt 2 uses bandwidth 30)
+    const int bw = p1->bandwidth > 30 ? p1->bandwidth : 30;
+    if (h->capture && (long long)(2 * bw - 1) * h->d.bv_h > (long long)h->pix_cap) {
+        lt_set_error("bandwidth %d can overflow the captured pixel lists (capacity %d): raise it with lt_set_pixel_capacity",
+                     p1->bandwidth, h->pix_cap);
+        return -1;
+    }
     if ((rc = alloc_front_set(h, set))) return rc;
     select_set(h, set);
     return 0;
@@ -462,7 +494,7 @@ extern "C" int lt_set_text_sprites(lt_handle* h, const uint8_t* tables, int32_t 
     for (void* p : old) if (p) cudaFree(p);
     h->txt_pair_overlap = nullptr; h->txt_bitmaps = nullptr;
     h->txt_tables = nullptr; h->txt_char_start = nullptr; h->txt_dy = nullptr; h->txt_dx = nullptr;
-    h->txt_lut = nullptr; h->txt_advance = nullptr; h->txt_nchars = 0;
+    h->txt_lut = nullptr; h->txt_advance = nullptr; h->txt_nchars = 0; h->txt_row0 = h->txt_row1 = 0;
     if (!tables) return 0;
     if (n_tables < 1 || n_chars < 1 || n_pixels < 0 || !char_start || !dy || !dx || !lut || !advance ||
         first_char > '?' || first_char + n_chars <= '?') { lt_set_error("bad sprite data"); return -1; }
@@ -496,6 +528,9 @@ extern "C" int lt_set_text_sprites(lt_handle* h, const uint8_t* tables, int32_t 
             for (int i = char_start[c]; i < char_start[c + 1]; ++i) { lo = dy[i] < lo ? dy[i] : lo; hi = dy[i] > hi ? dy[i] : hi; }
         }
         h->txt_parallel_lines = (hi - lo) < 35 ? 1 : 0;
+        // frame rows the three text lines (baselines 35, 70, 105: lane_tracker.py:653-659) can touch
+        h->txt_row0 = 35 + lo < 0 ? 0 : 35 + lo;
+        h->txt_row1 = 105 + hi + 1 > h->d.img_h ? h->d.img_h : 105 + hi + 1;
     }
     {   // ordered glyph pairs that share pixels, and whether a glyph can reach beyond its immediate neighbour
         std::vector<unsigned char> ov((size_t)n_chars * n_chars, 0);
@@ -573,6 +608,21 @@ extern "C" int lt_set_capture(lt_handle* h, int32_t enable) {
         cudaMemset(h->cap_ncents, 0, 2 * S * 2 * sizeof(int));
     }
     h->capture = enable ? 1 : 0;
+    return 0;
+}
+
+extern "C" int lt_set_pixel_capacity(lt_handle* h, int32_t capacity) {
+    if (!h || capacity < 1) { lt_set_error("bad argument"); return -1; }
+    LT_CUDA(cudaSetDevice(h->cfg.device));
+    LT_CUDA(cudaDeviceSynchronize());
+    if (capacity == h->pix_cap) return 0;
+    h->pix_cap = capacity;
+    if (h->cap_pixels) {
+        cudaFree(h->cap_pixels);
+        h->cap_pixels = nullptr;
+        int rc = dev_alloc(&h->cap_pixels, 2 * (size_t)h->S * 2 * (size_t)h->pix_cap);
+        if (rc) { h->capture = 0; return rc; }
+    }
     return 0;
 }
 
@@ -724,8 +774,18 @@ extern "C" int lt_draw_lane(lt_handle* h, const uint8_t* d_frames, uint8_t* d_ou
     if ((rc = check_n(h, n))) return rc;
     if (!d_frames || !d_out || !d_x || !d_counts) { lt_set_error("null argument"); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
-    if ((rc = lt_launch_lane_rows(h, d_x, d_counts, n, st))) return rc;
-    return lt_launch_overlay(h, d_frames, d_out, n, h->draw_flags, st);
+    // own polygon rows and draw flags: the per-stream ones cache the last valid lane of process() (the polygon a
+    // failing frame re-draws, lane_tracker.py:1160-1166) and must survive a stage call
+    LT_CUDA(cudaSetDevice(h->cfg.device));
+    if (!h->dl_rows) {
+        if ((rc = dev_alloc(&h->dl_rows, (size_t)h->S * h->d.bv_h))) return rc;
+        if ((rc = dev_alloc(&h->dl_flags, (size_t)h->S))) return rc;
+    }
+    lt_handle view = *h;
+    view.lane_rows = h->dl_rows;
+    view.draw_flags = h->dl_flags;
+    if ((rc = lt_launch_lane_rows(&view, d_x, d_counts, n, st))) return rc;
+    return lt_launch_overlay(&view, d_frames, d_out, n, view.draw_flags, st);
 }
 
 // ---------------------------------------------------------------------------
@@ -876,6 +936,12 @@ extern "C" int64_t lt_debug_read(lt_handle* h, int32_t what, int32_t id, void* d
         case 9: src = h->lane_rows + (size_t)id * d.bv_h; bytes = (size_t)d.bv_h * sizeof(int2); break;
         case 10: {
             int v[9] = {d.roi0, d.roi1, d.ov0, d.ov1, d.p2, d.mwords, h->pix_cap, h->src0, h->src1};
+            if (cap < (int64_t)sizeof(v)) { lt_set_error("buffer too small"); return -1; }
+            memcpy(dst, v, sizeof(v));
+            return sizeof(v);
+        }
+        case 11: {   // launch geometry of the last paired morphology launch: bands of the 55x55 / 29x29 jobs, SM count
+            int v[3] = {h->bands_val[0], h->bands_val[1], h->sm_count};
             if (cap < (int64_t)sizeof(v)) { lt_set_error("buffer too small"); return -1; }
             memcpy(dst, v, sizeof(v));
             return sizeof(v);

@@ -894,14 +894,16 @@ static int launch_cross_h(lt_handle* h, const uint32_t* plane, uint32_t* bits, i
     return 0;
 }
 
+// pad_rows_zero: the pad rows of `plane` hold 0 (top-hat planes), i.e. they ARE the filter's BORDER_CONSTANT border and
+// the row-padded fast path may read them; the raw planes carry the erosion pad 0xFFFF there and must be bounds-checked.
 static int launch_cross_v(lt_handle* h, const uint32_t* plane, uint32_t* bits, int k, int C, int n,
-                          const int* list, const int* count, cudaStream_t st) {
+                          const int* list, const int* count, cudaStream_t st, bool pad_rows_zero) {
     const LtDims& d = h->d;
     const int ppitch = d.pp;
     const size_t pstride = h->stream_pad;
     dim3 gv(d.p2 / 32, lt_div_up(d.bv_h, CV_BAND), n);
     const bool packed = k <= 127 && C >= 0 && k * 255 + C * k + 1 < 32768;
-    const bool rowpad = k + CV_CHUNK <= LT_HALO_Y;
+    const bool rowpad = pad_rows_zero && k + CV_CHUNK <= LT_HALO_Y;
 #define LT_CROSS_V(PK, RP) k_cross_v<PK, RP><<<gv, 32, 0, st>>>(plane, bits, d, k, C, ppitch, pstride, h->stream_mask, list, count)
     if (packed && rowpad) LT_CROSS_V(true, true);
     else if (packed) LT_CROSS_V(true, false);
@@ -914,10 +916,10 @@ static int launch_cross_v(lt_handle* h, const uint32_t* plane, uint32_t* bits, i
 
 // horizontal half writes (or ORs) the words, vertical half ORs into them
 static int launch_cross(lt_handle* h, const uint32_t* plane, uint32_t* bits, int k, int C, int accumulate, int n,
-                        const int* list, const int* count, cudaStream_t st) {
+                        const int* list, const int* count, cudaStream_t st, bool pad_rows_zero) {
     int rc = launch_cross_h(h, plane, bits, k, C, accumulate, n, list, count, st);
     if (rc) return rc;
-    return launch_cross_v(h, plane, bits, k, C, n, list, count, st);
+    return launch_cross_v(h, plane, bits, k, C, n, list, count, st, pad_rows_zero);
 }
 
 static int launch_box_pair(lt_handle* h, int block_r, int c_r, int block_b, int c_b, int n, const int* list,
@@ -962,14 +964,14 @@ int lt_launch_filter(lt_handle* h, int n, const LtAttemptParams& p, const int* l
             if ((rc = launch_cross_h(h, h->topR, h->merged, p.ksize_r, p.C_r, 1, n, list, count, h->side))) return rc;
             if ((rc = launch_cross_h(h, h->topB, h->merged, p.ksize_b, p.C_b, 1, n, list, count, h->side))) return rc;
             LT_CUDA(cudaEventRecord(h->ev_join, h->side));
-            if ((rc = launch_cross_v(h, h->topR, h->merged, p.ksize_r, p.C_r, n, list, count, st))) return rc;
-            if ((rc = launch_cross_v(h, h->topB, h->merged, p.ksize_b, p.C_b, n, list, count, st))) return rc;
+            if ((rc = launch_cross_v(h, h->topR, h->merged, p.ksize_r, p.C_r, n, list, count, st, true))) return rc;
+            if ((rc = launch_cross_v(h, h->topB, h->merged, p.ksize_b, p.C_b, n, list, count, st, true))) return rc;
             LT_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
             lt_prof_mark(h, ST_CROSS_B, st);
         } else {
-            if ((rc = launch_cross(h, h->topR, h->merged, p.ksize_r, p.C_r, 0, n, list, count, st))) return rc;
+            if ((rc = launch_cross(h, h->topR, h->merged, p.ksize_r, p.C_r, 0, n, list, count, st, true))) return rc;
             lt_prof_mark(h, ST_CROSS_R, st);
-            if ((rc = launch_cross(h, h->topB, h->merged, p.ksize_b, p.C_b, 1, n, list, count, st))) return rc;
+            if ((rc = launch_cross(h, h->topB, h->merged, p.ksize_b, p.C_b, 1, n, list, count, st, true))) return rc;
             lt_prof_mark(h, ST_CROSS_B, st);
         }
     } else {
@@ -977,7 +979,7 @@ int lt_launch_filter(lt_handle* h, int n, const LtAttemptParams& p, const int* l
         lt_prof_mark(h, ST_BOX, st);
     }
     if (p.mask_noise) {
-        if ((rc = launch_cross(h, h->planeB, h->mask, p.ksize_noise, p.C_noise, 0, n, list, count, st))) return rc;
+        if ((rc = launch_cross(h, h->planeB, h->mask, p.ksize_noise, p.C_noise, 0, n, list, count, st, false))) return rc;
         dim3 g(d.p2 / 32, d.bv_h, n);
         k_noise_combine<<<g, 32, 0, st>>>(h->planeB, h->mask, h->merged, d, p.noise_thresh, d.pp, h->stream_pad,
                                           h->stream_mask, list, count);

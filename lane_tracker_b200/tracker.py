@@ -170,8 +170,27 @@ class BatchedLaneTracker:
         check(self.lib.lt_memcpy_rows(self._h, _ptr(dst), _ptr(src), n, int(row0), int(row1), int(bool(to_device)),
                                       _stream_ptr(self.device)))
 
+    @property
+    def sm_count(self):
+        return self._launch_geometry()[2]
+
+    def morph_bands(self):
+        """(row bands of the 55x55 job, of the 29x29 job) in the last ellipse-morphology launch."""
+        g = self._launch_geometry()
+        return int(g[0]), int(g[1])
+
+    def _launch_geometry(self):
+        g = np.zeros(3, dtype=np.int32)
+        check(self.lib.lt_debug_read(self._h, 11, 0, g.ctypes.data_as(C.c_void_p), g.nbytes))
+        return g
+
     def set_capture(self, enable=True):
         check(self.lib.lt_set_capture(self._h, int(bool(enable))))
+
+    def set_pixel_capacity(self, capacity):
+        """Entries per stream and side of the captured pixel lists (default: enough for bandwidth <= 32)."""
+        check(self.lib.lt_set_pixel_capacity(self._h, int(capacity)))
+        self.geometry["pixel_capacity"] = int(capacity)
 
     def profile_begin(self, max_calls):
         """Arm in-stream CUDA-event timing of every stage of the next `max_calls` process() calls."""
@@ -587,6 +606,16 @@ class DevicePipeline:
         return self.t._results_host[:nbytes].numpy().view(RESULT_DTYPE).copy()
 
 
+def _rows_minus(rows, covered):
+    """Row range `rows` minus the range `covered` (both half-open): up to two non-empty segments."""
+    (ta, tb), (a, b) = rows, covered
+    if tb <= ta:
+        return []
+    if b <= a:
+        return [(ta, tb)]
+    return [seg for seg in ((ta, min(tb, a)), (max(ta, b), tb)) if seg[1] > seg[0]]
+
+
 class HostPipeline:
     """Host-to-host streaming through a ``BatchedLaneTracker``: pinned host frames in, annotated frames and
     result records out, with the H2D copy of batch k+1, the kernels of batch k and the D2H copy of batch k-1
@@ -653,9 +682,8 @@ class HostPipeline:
             if self.inplace:
                 a, b = self.rows_in
                 self.t.copy_rows(sl["d_in"], host_frames, a, b, True)
-                ta, tb = self.rows_text
-                if tb > ta and not (ta >= a and tb <= b):
-                    self.t.copy_rows(sl["d_in"], host_frames, ta, min(tb, a) if ta < a else ta, True)
+                for ta, tb in _rows_minus(self.rows_text, (a, b)):      # text rows outside the rows already sent
+                    self.t.copy_rows(sl["d_in"], host_frames, ta, tb, True)
                 sl["frames"] = host_frames
             else:
                 sl["d_in"][:n].copy_(host_frames, non_blocking=True)
@@ -682,9 +710,8 @@ class HostPipeline:
                 a, b = self.rows_out
                 if b > a:
                     self.t.copy_rows(host_frames, sl["d_in"][:n], a, b, False)
-                ta, tb = self.rows_text
-                if tb > ta and not (ta >= a and tb <= b):
-                    self.t.copy_rows(host_frames, sl["d_in"][:n], ta, min(tb, a) if ta < a else ta, False)
+                for ta, tb in _rows_minus(self.rows_text, (a, b)):      # text rows outside the rows already fetched
+                    self.t.copy_rows(host_frames, sl["d_in"][:n], ta, tb, False)
             elif self.overlay:
                 sl["h_out"][:n].copy_(sl["d_out"][:n], non_blocking=True)
             sl["h_res"].copy_(sl["d_res"], non_blocking=True)
@@ -850,6 +877,9 @@ class LaneTracker:
         a = np.asarray(img)
         if a.shape != (h, w, 3) or a.dtype != np.uint8:
             raise ValueError("img must be uint8 [%d, %d, 3]" % (h, w))
+        need = (2 * max(int(bandwidth), 30) - 1) * self._bt.warped_size[1]   # a band-search row: < 2 * bandwidth pixels
+        if need > self._bt.geometry["pixel_capacity"]:
+            self._bt.set_pixel_capacity(need)
         self._in_host[0].numpy()[...] = a
         self._in_dev.copy_(self._in_host, non_blocking=True)
         warped = self._bt.warp_frame(self._in_dev)[0] if debug else None   # lane_tracker.py:1035 (raw frame)
