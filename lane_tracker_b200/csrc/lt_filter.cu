@@ -550,7 +550,8 @@ k_cross_h_wide(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bi
             pass = (L < t) && (Rs < t);
         }
         uint32_t b = __ballot_sync(0xFFFFFFFFu, pass);
-        if (lane == 0) brow[wd] = accumulate ? (brow[wd] | b) : b;
+        // accumulate: the vertical half may be OR-ing into the same words from another stream -> atomic
+        if (lane == 0) { if (!accumulate) brow[wd] = b; else if (b) atomicOr(&brow[wd], b); }
     }
 }
 
