@@ -19,6 +19,7 @@ SOURCES = {
     "lt_api.cu": [],
     "lt_remap.cu": ["-fmad=false"],
     "lt_filter.cu": [],
+    "lt_morph.cu": [],
     "lt_search.cu": ["-fmad=false"],
     "lt_vis.cu": ["-fmad=false"],
 }

@@ -16,46 +16,7 @@
 #include <functional>
 #include <vector>
 #include "lt_common.cuh"
-
-// ---------------------------------------------------------------------------
-// structuring elements: cv2.getStructuringElement(MORPH_ELLIPSE,(k,k)) row half-widths
-// ---------------------------------------------------------------------------
-
-template <int K> struct Ellipse;
-
-template <> struct Ellipse<55> {
-    static constexpr int R = 27, ND = 17;
-    __host__ __device__ static constexpr int hw(int j) {
-        constexpr int t[55] = {0, 7, 10, 12, 14, 16, 17, 18, 19, 20, 21, 22, 22, 23, 24, 24, 25, 25, 25,
-                               26, 26, 26, 27, 27, 27, 27, 27, 27, 27, 27, 27, 27, 27, 26, 26, 26, 25,
-                               25, 25, 24, 24, 23, 22, 22, 21, 20, 19, 18, 17, 16, 14, 12, 10, 7, 0};
-        return t[j];
-    }
-    __host__ __device__ static constexpr int uniq(int i) {
-        constexpr int t[17] = {0, 7, 10, 12, 14, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27};
-        return t[i];
-    }
-};
-
-template <> struct Ellipse<29> {
-    static constexpr int R = 14, ND = 9;
-    __host__ __device__ static constexpr int hw(int j) {
-        constexpr int t[29] = {0, 5, 7, 9, 10, 11, 11, 12, 13, 13, 13, 14, 14, 14, 14,
-                               14, 14, 14, 13, 13, 13, 12, 11, 11, 10, 9, 7, 5, 0};
-        return t[j];
-    }
-    __host__ __device__ static constexpr int uniq(int i) {
-        constexpr int t[9] = {0, 5, 7, 9, 10, 11, 12, 13, 14};
-        return t[i];
-    }
-};
-
-template <int K> __host__ __device__ constexpr int ell_uidx(int w) {
-    int r = 0;
-    for (int i = 0; i < Ellipse<K>::ND; ++i)
-        if (Ellipse<K>::uniq(i) == w) r = i;
-    return r;
-}
+#include "lt_ellipse.cuh"
 
 // ---------------------------------------------------------------------------
 // the morphology kernel
@@ -949,12 +910,20 @@ int lt_launch_filter(lt_handle* h, int n, const LtAttemptParams& p, const int* l
     const LtDims& d = h->d;
     int rc;
     if (p.filter_type == 0) {
-        MorphJob e55 = {h->planeB, h->tmpB, nullptr, 0, 0}, e29 = {h->planeR, h->tmpR, nullptr, 0, 0};
-        if ((rc = launch_morph_pair<false, false>(h, e55, e29, n, list, count, st))) return rc;
-        lt_prof_mark(h, ST_ERODE55, st);            // both erosions (55x55 on Lab-b, 29x29 on R) in one launch
-        MorphJob t55 = {h->tmpB, h->topB, h->planeB, 0, 0}, t29 = {h->tmpR, h->topR, h->planeR, 0, 0};
-        if ((rc = launch_morph_pair<true, true>(h, t55, t29, n, list, count, st))) return rc;
-        lt_prof_mark(h, ST_TOPHAT55, st);           // both dilations + top-hat epilogues in one launch
+        static const bool legacy = [] { const char* e = getenv("LT_MORPH_IMPL"); return e && e[0] == 'l'; }();
+        if (legacy) {
+            MorphJob e55 = {h->planeB, h->tmpB, nullptr, 0, 0}, e29 = {h->planeR, h->tmpR, nullptr, 0, 0};
+            if ((rc = launch_morph_pair<false, false>(h, e55, e29, n, list, count, st))) return rc;
+            lt_prof_mark(h, ST_ERODE55, st);            // both erosions (55x55 on Lab-b, 29x29 on R) in one launch
+            MorphJob t55 = {h->tmpB, h->topB, h->planeB, 0, 0}, t29 = {h->tmpR, h->topR, h->planeR, 0, 0};
+            if ((rc = launch_morph_pair<true, true>(h, t55, t29, n, list, count, st))) return rc;
+            lt_prof_mark(h, ST_TOPHAT55, st);           // both dilations + top-hat epilogues in one launch
+        } else {
+            if ((rc = lt_launch_morph_pair(h, false, n, list, count, st))) return rc;
+            lt_prof_mark(h, ST_ERODE55, st);            // both erosions (55x55 on Lab-b, 29x29 on R), two concurrent kernels
+            if ((rc = lt_launch_morph_pair(h, true, n, list, count, st))) return rc;
+            lt_prof_mark(h, ST_TOPHAT55, st);           // both dilations + top-hat epilogues
+        }
         if (list == nullptr && h->side) {
             // The four threshold halves (R/Lab-b x horizontal/vertical) only OR bits into the merged mask and each
             // of them fills about half of the issue slots: the horizontal pair runs on a side stream, the vertical

@@ -1,12 +1,14 @@
 #!/bin/bash
-# One gpurun call of the round: parity tests, the pipe probe, a short bench.  Outputs under gpurun_out/.
+# One gpurun call: selected parity tests, then timing tools.  Outputs under gpurun_out/.
 mkdir -p gpurun_out
-tag=${1:-s1}
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${tag}_smi.txt 2>&1
-./tools/_build/pipe_probe > gpurun_out/${tag}_pipe_probe.jsonl 2>&1
-python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1
+tag=${1:-s}
+tests=${2:-"tests/test_gpu_config_parity.py::test_tophat_band_geometries tests/test_gpu_parity.py::test_filter_masks_bit_exact"}
+timeout 900 python -m pytest $tests -x -q > gpurun_out/${tag}_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.log
-tail -15 gpurun_out/${tag}_pytest.log
-python bench.py --steps 100 --warmup 5 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
-echo "bench rc=$?"
-cat gpurun_out/${tag}_pipe_probe.jsonl
+tail -12 gpurun_out/${tag}_pytest.log
+shift; shift
+if [ $# -gt 0 ]; then
+  timeout 900 "$@" > gpurun_out/${tag}_tool.log 2>&1
+  echo "tool rc=$?"
+  tail -40 gpurun_out/${tag}_tool.log
+fi
