@@ -40,6 +40,13 @@ constexpr int TW = 192;             // packed columns per CTA = consumer threads
 #define LT_MORPH_NPW 2
 #endif
 constexpr int NPW = LT_MORPH_NPW;   // producer warps
+#ifndef LT_MORPH_UNROLL4
+#define LT_MORPH_UNROLL4 4
+#endif
+#ifndef LT_MORPH_UNROLL8
+#define LT_MORPH_UNROLL8 4
+#endif
+constexpr int UNROLL4 = LT_MORPH_UNROLL4, UNROLL8 = LT_MORPH_UNROLL8;   // unroll factors of the producers' task loops
 constexpr int NPROD = 32 * NPW;
 constexpr int NTHREADS = TW + NPROD;
 constexpr int RB = 8, RP = RB / 2;  // source rows / row pairs per table build
@@ -207,7 +214,11 @@ k_morph(MorphArgs a, LtDims d) {
             uint32_t* const Tb = TB + b * G::TBUF;
             const uint32_t* const Rw = RAW + b * RB * TEP;
             // ---- T1 (the rows themselves) and T4, four consecutive columns per task
-            for (int q = pt; q < RP * G::CH; q += NPROD) {
+            constexpr int NTASK = RP * G::CH, NIT = (NTASK + NPROD - 1) / NPROD;
+#pragma unroll UNROLL4
+            for (int it = 0; it < NIT; ++it) {
+                const int q = pt + it * NPROD;
+                if (q >= NTASK) break;
                 const int pr = q / G::CH, c = (q - pr * G::CH) * 4;
                 const uint4* ra = reinterpret_cast<const uint4*>(Rw + (2 * pr) * TEP + c);
                 const uint4* rb = reinterpret_cast<const uint4*>(Rw + (2 * pr + 1) * TEP + c);
@@ -234,7 +245,10 @@ k_morph(MorphArgs a, LtDims d) {
             }
             bar_sync(BAR_PROD, NPROD);
             // ---- T8, T16 (, T32) from T4: entry i = op over T4[i + 4k]
-            for (int q = pt; q < RP * G::CH; q += NPROD) {
+#pragma unroll UNROLL8
+            for (int it = 0; it < NIT; ++it) {
+                const int q = pt + it * NPROD;
+                if (q >= NTASK) break;
                 const int pr = q / G::CH, c = (q - pr * G::CH) * 4;
                 const uint4* t = reinterpret_cast<const uint4*>(T4 + pr * TEA + c);
                 uint4 v[G::HAS32 ? 8 : 4];
