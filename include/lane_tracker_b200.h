@@ -304,7 +304,8 @@ int lt_set_state(lt_handle* h, int32_t stream_id, const lt_state* h_state, const
  *       9 lane row spans int32 [bv_h][2], 10 geometry int32[9] = {undistorted ROI first,last+1, overlay rows
  *       first,last+1, pair-plane width, mask words per row, pixel-list capacity of lt_read_capture, frame rows the
  *       tracker reads first,last+1}, 11 int32[3] = {row bands of the 55x55 and of the 29x29 morphology jobs in the
- *       last filter launch, SM count of the device}.
+ *       last filter launch, SM count of the device}, 12 lane row spans of the last lt_draw_lane call (int32 [bv_h][2];
+ *       9 is the per-stream cache that lt_process re-draws on failing frames).
  * Copies to HOST memory; synchronous. Returns bytes written or <0. */
 int64_t lt_debug_read(lt_handle* h, int32_t what, int32_t stream_id, void* h_dst, int64_t capacity);
 

@@ -138,7 +138,7 @@ extern "C" int lt_destroy(lt_handle* h) {
                       f.merged, f.mask};
         for (void* p : fp) if (p) cudaFree(p);
     }
-    void* ptrs[] = {h->und_map, h->bv_map, h->ov_map, h->bv_desc, h->fused_desc, h->lab_gamma, h->lab_cbrt, h->pixels, h->pix_counts, h->lane_rows,
+    void* ptrs[] = {h->und_map, h->bv_map, h->ov_map, h->bv_desc, h->und_desc, h->lab_yz, h->fused_desc, h->lab_gamma, h->lab_cbrt, h->pixels, h->pix_counts, h->lane_rows,
                     h->avg_x, h->state, h->att, h->retry_list, h->retry_count, h->draw_flags, h->scratch_bv, h->vis_scratch,
                     h->cap_pixels, h->cap_counts, h->cap_cents, h->cap_ncents, h->dl_rows, h->dl_flags,
                     h->txt_tables, h->txt_char_start, h->txt_dy, h->txt_dx, h->txt_lut, h->txt_advance, h->txt_pair_overlap,
@@ -260,6 +260,10 @@ extern "C" int lt_create(const lt_config* cfg, lt_handle** out) {
     }
     A(bv_desc, nbv);
     if (!rc) rc = lt_launch_build_desc(h, st);
+    A(und_desc, (size_t)(d.roi1 - d.roi0) * d.img_w);
+    if (!rc) rc = lt_launch_build_und_desc(h, st);
+    A(lab_yz, 768);
+    if (!rc) rc = lt_launch_build_lab_yz(h, st);
     if (!rc) rc = alloc_front_set(h, 0);
     if (!rc) select_set(h, 0);
     A(pixels, S * 2 * (size_t)h->pix_cap); A(pix_counts, S * 2);
@@ -934,6 +938,9 @@ extern "C" int64_t lt_debug_read(lt_handle* h, int32_t what, int32_t id, void* d
             break;
         }
         case 9: src = h->lane_rows + (size_t)id * d.bv_h; bytes = (size_t)d.bv_h * sizeof(int2); break;
+        case 12:    // polygon rows of the last lt_draw_lane stage call (its own scratch, not the per-stream cache)
+            if (!h->dl_rows) { lt_set_error("lt_draw_lane has not been called"); return -1; }
+            src = h->dl_rows + (size_t)id * d.bv_h; bytes = (size_t)d.bv_h * sizeof(int2); break;
         case 10: {
             int v[9] = {d.roi0, d.roi1, d.ov0, d.ov1, d.p2, d.mwords, h->pix_cap, h->src0, h->src1};
             if (cap < (int64_t)sizeof(v)) { lt_set_error("buffer too small"); return -1; }

@@ -79,6 +79,8 @@ struct lt_handle {
     int remap_mode;              // 0 exact two-stage (default), 1 fused single resample
     unsigned short* lab_gamma;   // [256]
     unsigned short* lab_cbrt;    // [3072]
+    uint2* lab_yz;               // [3][256] Lab partial sums per channel value (lt_remap.cu)
+    int2* und_desc;              // [roi rows][img_w] tap descriptors of the undistort (byte offset, fx | fy << 5 | flags << 10)
     // per-stream buffers
     uchar4* und_roi;             // [S][roi rows][img_w]
     uint32_t* planeR; uint32_t* planeB;     // padded [S][bv_h + 2*LT_HALO_Y][pp]; lanes beyond the image / halo: 0xFFFF
@@ -151,6 +153,8 @@ int lt_ensure_smem(const void* func, size_t bytes);
 
 int lt_launch_build_maps(lt_handle* h, cudaStream_t st);
 int lt_launch_build_desc(lt_handle* h, cudaStream_t st);
+int lt_launch_build_lab_yz(lt_handle* h, cudaStream_t st);
+int lt_launch_build_und_desc(lt_handle* h, cudaStream_t st);
 int lt_launch_build_fused_desc(lt_handle* h, cudaStream_t st);
 int lt_launch_warp_fused(lt_handle* h, const uint8_t* d_frames, uint8_t* d_bv_rgb, int n, cudaStream_t st);
 int lt_launch_undistort(lt_handle* h, const uint8_t* d_frames, int n, cudaStream_t st);

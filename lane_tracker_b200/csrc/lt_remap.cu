@@ -145,25 +145,78 @@ __device__ __forceinline__ uint32_t blend_rgb(uint32_t a, uint32_t b, uint32_t c
 }
 
 __device__ __forceinline__ uint32_t blend_rgbx(uint32_t t00, uint32_t t01, uint32_t t10, uint32_t t11, uint32_t f);
+__device__ __forceinline__ uint32_t blend_taps(uint32_t t00, uint32_t t01, uint32_t t10, uint32_t t11, uint32_t wA, uint32_t wB);
+__device__ __forceinline__ void blend_weights(uint32_t f, uint32_t& wA, uint32_t& wB);
+
+// Tap descriptor of every pixel of the undistorted ROI, built once from und_map:
+//   x = BYTE offset of tap (sy, sx) in a frame, y = fx | fy << 5 | in-image flags of the four taps << 10 | "fast" << 14.
+// fast: all four taps are inside the frame and the three aligned 32-bit words that cover a tap pair lie inside it too.
+__global__ void k_build_und_desc(const int2* __restrict__ map, int2* __restrict__ desc, LtDims d) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x, i = d.roi0 + blockIdx.y;
+    if (j >= d.img_w) return;
+    const int2 q = map[(size_t)i * d.img_w + j];
+    Tap4 t = make_taps(q);
+    auto ok = [&](int yy, int xx) { return (unsigned)yy < (unsigned)d.img_h && (unsigned)xx < (unsigned)d.img_w; };
+    uint32_t f = (uint32_t)(q.x & 31) | ((uint32_t)(q.y & 31) << 5);
+    const uint32_t m = (ok(t.sy, t.sx) ? 1u : 0u) | (ok(t.sy, t.sx + 1) ? 2u : 0u) | (ok(t.sy + 1, t.sx) ? 4u : 0u) |
+                       (ok(t.sy + 1, t.sx + 1) ? 8u : 0u);
+    f |= m << 10;
+    long long off = ((long long)t.sy * d.img_w + t.sx) * 3;
+    const long long frame_bytes = (long long)d.img_w * d.img_h * 3;
+    if (m == 15u && ((off + 3LL * d.img_w) & ~3LL) + 12 <= frame_bytes) f |= 1u << 14;
+    if (!m) off = 0;
+    desc[(size_t)(i - d.roi0) * d.img_w + j] = make_int2((int)off, (int)f);
+}
+
+int lt_launch_build_und_desc(lt_handle* h, cudaStream_t st) {
+    const LtDims& d = h->d;
+    dim3 g(lt_div_up(d.img_w, 256), d.roi1 - d.roi0);
+    k_build_und_desc<<<g, 256, 0, st>>>(h->und_map, h->und_desc, d);
+    LT_LAUNCH_CHECK();
+    return 0;
+}
+
+// cv2.undistort of the ROI rows: one thread = one ROI pixel of NSU streams (descriptor decoded once).  Fast path: the
+// six bytes of a tap pair come from three aligned 32-bit words and two funnel shifts instead of six byte loads.
+constexpr int NSU = 8;
 
 __global__ void __launch_bounds__(256)
-k_undistort_roi(const uint8_t* __restrict__ frames, uchar4* __restrict__ und, const int2* __restrict__ map,
-                LtDims d) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    int i = d.roi0 + blockIdx.y;
-    int s = blockIdx.z;
-    if (j >= d.img_w) return;
-    const uint8_t* img = frames + (size_t)s * d.img_w * d.img_h * 3;
-    const int2 q = __ldg(&map[i * d.img_w + j]);
-    Tap4 t = make_taps(q);
-    uint32_t a = load_rgb(img, d.img_w, d.img_h, t.sy, t.sx);
-    uint32_t b = load_rgb(img, d.img_w, d.img_h, t.sy, t.sx + 1);
-    uint32_t c = load_rgb(img, d.img_w, d.img_h, t.sy + 1, t.sx);
-    uint32_t e = load_rgb(img, d.img_w, d.img_h, t.sy + 1, t.sx + 1);
-    // separable packed form of sum(tap * w): the same integer as the four-weight sum (no intermediate rounding)
-    uint32_t o = blend_rgbx(a, b, c, e, (uint32_t)(q.x & 31) | ((uint32_t)(q.y & 31) << 5));
-    und[((size_t)s * (d.roi1 - d.roi0) + (i - d.roi0)) * d.img_w + j] =
-        make_uchar4(o & 255, (o >> 8) & 255, (o >> 16) & 255, 0);
+k_undistort_roi(const uint8_t* __restrict__ frames, uchar4* __restrict__ und, const int2* __restrict__ desc, LtDims d, int n,
+                int aligned) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int roi_px = (d.roi1 - d.roi0) * d.img_w;
+    if (p >= roi_px) return;
+    const int2 q = __ldg(&desc[p]);
+    const uint32_t f = (uint32_t)q.y;
+    uint32_t wA, wB;
+    blend_weights(f, wA, wB);
+    const uint32_t m = (f >> 10) & 15u;
+    const bool fast = aligned && (f >> 14);
+    const size_t frame_bytes = (size_t)d.img_w * d.img_h * 3;
+    const int pitch = d.img_w * 3;
+    const int wi = q.x >> 2, sh = (q.x & 3) * 8, wpitch = pitch >> 2;
+    const int s0 = blockIdx.y * NSU, s1 = min(s0 + NSU, n);
+    uint32_t* out = reinterpret_cast<uint32_t*>(und) + (size_t)s0 * roi_px + p;
+    for (int s = s0; s < s1; ++s, out += roi_px) {
+        const uint8_t* img = frames + (size_t)s * frame_bytes;
+        uint32_t o = 0;
+        if (fast) {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(img) + wi;
+            const uint32_t a0 = __ldg(w), a1 = __ldg(w + 1), a2 = __ldg(w + 2);
+            const uint32_t b0 = __ldg(w + wpitch), b1 = __ldg(w + wpitch + 1), b2 = __ldg(w + wpitch + 2);
+            const uint32_t qa0 = __funnelshift_r(a0, a1, sh), qa1 = __funnelshift_r(a1, a2, sh);     // bytes o..o+3, o+4..o+7
+            const uint32_t qb0 = __funnelshift_r(b0, b1, sh), qb1 = __funnelshift_r(b1, b2, sh);
+            o = blend_taps(qa0, __funnelshift_r(qa0, qa1, 24), qb0, __funnelshift_r(qb0, qb1, 24), wA, wB);
+        } else if (m) {
+            auto tap = [&](uint32_t bit, int off) -> uint32_t {     // BORDER_CONSTANT 0
+                if (!(m & bit)) return 0u;
+                const uint8_t* t = img + q.x + off;
+                return (uint32_t)__ldg(t) | ((uint32_t)__ldg(t + 1) << 8) | ((uint32_t)__ldg(t + 2) << 16);
+            };
+            o = blend_taps(tap(1u, 0), tap(2u, 3), tap(4u, pitch), tap(8u, pitch + 3), wA, wB);
+        }
+        *out = o;                                                   // RGBX
+    }
 }
 
 // cv2.warpPerspective(img, M, warped_size) of the RAW frame (lane_tracker.py:1035, the split view's middle panel)
@@ -188,8 +241,9 @@ int lt_launch_warp_frame(lt_handle* h, const uint8_t* d_frames, uint8_t* d_bv_rg
 
 int lt_launch_undistort(lt_handle* h, const uint8_t* d_frames, int n, cudaStream_t st) {
     const LtDims& d = h->d;
-    dim3 g(lt_div_up(d.img_w, 256), d.roi1 - d.roi0, n);
-    k_undistort_roi<<<g, 256, 0, st>>>(d_frames, h->und_roi, h->und_map, d);
+    dim3 g(lt_div_up((d.roi1 - d.roi0) * d.img_w, 256), lt_div_up(n, NSU));
+    const int aligned = ((uintptr_t)d_frames & 3) == 0 && ((d.img_w * 3) & 3) == 0;     // word loads need 4-byte aligned rows
+    k_undistort_roi<<<g, 256, 0, st>>>(d_frames, h->und_roi, h->und_desc, d, n, aligned);
     LT_LAUNCH_CHECK();
     return 0;
 }
@@ -270,51 +324,135 @@ __device__ __forceinline__ void store_padded(uint32_t* __restrict__ planeR, uint
     }
 }
 
+// ---- the per-frame warp: one thread = one packed column (two bird's-eye pixels) of NSW streams ------------------
+// The tap descriptor of a pixel (8 bytes from the shared table) is decoded once and reused for every stream of the
+// group; the Lab look-up tables live in shared memory in a form that needs two 3-input adds instead of six multiplies:
+//   YZ[c][v] = { coefY[c] * g[v] (+ 2048 for c = 0),  coefZ[c] * g[v] (+ 2048) }      (lane_tracker.py:208)
+#ifndef LT_WARP_NSW
+#define LT_WARP_NSW 8
+#endif
+constexpr int NSW = LT_WARP_NSW;       // streams per thread
+
+struct LabSmem {
+    uint2 yz[3][256];
+    unsigned short cb[3072];
+};
+
+__device__ __forceinline__ void lab_smem_load(LabSmem& L, const uint2* __restrict__ yz, const unsigned short* __restrict__ cb) {
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) (&L.yz[0][0])[i] = __ldg(&yz[i]);
+    const uint32_t* c32 = reinterpret_cast<const uint32_t*>(cb);
+    for (int i = threadIdx.x; i < 1536; i += blockDim.x) reinterpret_cast<uint32_t*>(L.cb)[i] = __ldg(&c32[i]);
+}
+
+__device__ __forceinline__ uint32_t lab_b_smem(uint32_t rgb, const LabSmem& L) {
+    const uint2 a = L.yz[0][rgb & 255], b = L.yz[1][(rgb >> 8) & 255], c = L.yz[2][(rgb >> 16) & 255];
+    const int fY = L.cb[(a.x + b.x + c.x) >> 12], fZ = L.cb[(a.y + b.y + c.y) >> 12];
+    const int v = (200 * (fY - fZ) + 128 * 32768 + 16384) >> 15;
+    return (uint32_t)max(0, min(255, v));
+}
+
+__global__ void k_build_lab_yz(const unsigned short* __restrict__ g, uint2* __restrict__ yz) {
+    const int v = threadIdx.x;                      // 256 threads
+    const uint32_t G = g[v];
+    yz[v] = make_uint2(871u * G + 2048u, 73u * G + 2048u);
+    yz[256 + v] = make_uint2(2929u * G, 448u * G);
+    yz[512 + v] = make_uint2(296u * G, 3575u * G);
+}
+
+// bilinear blend of four RGB taps (byte 3 of a tap may hold anything), OpenCV's fixed point:
+//   out = (t00*w00 + t01*w01 + t10*w10 + t11*w11 + 512) >> 10,   w = (32-fx)(32-fy), fx(32-fy), (32-fx)fy, fx*fy
+// as two IDP.2A (two 16-bit weights x two 8-bit taps + accumulator, FMA pipe) per channel: wA = w00 | w01 << 16 for the
+// upper tap row, wB = w10 | w11 << 16 for the lower one; the tap bytes of a row are paired per channel by two PRMT.
+__device__ __forceinline__ uint32_t blend_taps(uint32_t t00, uint32_t t01, uint32_t t10, uint32_t t11, uint32_t wA, uint32_t wB) {
+    const uint32_t p0 = __byte_perm(t00, t01, 0x5140), q0 = __byte_perm(t00, t01, 0x0062);    // {R,R',G,G'}, {B,B',.,.}
+    const uint32_t p1 = __byte_perm(t10, t11, 0x5140), q1 = __byte_perm(t10, t11, 0x0062);
+    const uint32_t R = __dp2a_lo(wB, p1, __dp2a_lo(wA, p0, 512u)) >> 10;
+    const uint32_t G = __dp2a_hi(wB, p1, __dp2a_hi(wA, p0, 512u)) >> 10;
+    const uint32_t B = __dp2a_lo(wB, q1, __dp2a_lo(wA, q0, 512u)) >> 10;
+    return R | (G << 8) | (B << 16);
+}
+
+__device__ __forceinline__ void blend_weights(uint32_t f, uint32_t& wA, uint32_t& wB) {
+    const uint32_t fx = f & 31u, fy = (f >> 5) & 31u, gx = 32u - fx, gy = 32u - fy;
+    wA = gx * gy | (fx * gy) << 16;
+    wB = gx * fy | (fx * fy) << 16;
+}
+
 __global__ void __launch_bounds__(256)
 k_warp_planes(const uchar4* __restrict__ und_all, const int2* __restrict__ desc, uint32_t* __restrict__ planeR,
-              uint32_t* __restrict__ planeB, uint8_t* __restrict__ bv_rgb,
-              const unsigned short* __restrict__ g, const unsigned short* __restrict__ cb, LtDims d, unsigned stream_pad) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y, s = blockIdx.z;
-    if (x >= d.p2) return;
-    const uint32_t* und = reinterpret_cast<const uint32_t*>(und_all) + (size_t)((unsigned)s) * (unsigned)((d.roi1 - d.roi0) * d.img_w);
-    uint32_t r2 = 0, b2 = 0;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        int px = x + half * d.p2;
-        if (px < d.bv_w) {
-            int2 q = __ldg(&desc[y * d.bv_w + px]);                        // < 2^31 entries
-            const uint32_t* base = und + q.x;
-            const uint32_t f = (uint32_t)q.y;
-            if (!(f >> 10)) {                          // no tap inside the frame: the pixel is black, Lab b of black = 128
-                b2 |= 128u << (16 * half);
-                if (bv_rgb) {
-                    uint8_t* p = bv_rgb + (((size_t)s * d.bv_h + y) * d.bv_w + px) * 3;
-                    p[0] = 0; p[1] = 0; p[2] = 0;
-                }
-                continue;
+              uint32_t* __restrict__ planeB, uint8_t* __restrict__ bv_rgb, const uint2* __restrict__ yz,
+              const unsigned short* __restrict__ cb, LtDims d, unsigned stream_pad, int n) {
+    __shared__ LabSmem L;
+    lab_smem_load(L, yz, cb);
+    __syncthreads();
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;        // flat (row, packed column)
+    if (item >= d.bv_h * d.p2) return;
+    const int y = item / d.p2, x = item - y * d.p2;
+    const int s0 = blockIdx.y * NSW, s1 = min(s0 + NSW, n);
+    const unsigned roi_px = (unsigned)((d.roi1 - d.roi0) * d.img_w);
+    // decode the two descriptors once
+    const bool hi_real = x + d.p2 < d.bv_w;
+    const int2 q0 = __ldg(&desc[y * d.bv_w + x]);
+    const int2 q1 = hi_real ? __ldg(&desc[y * d.bv_w + x + d.p2]) : make_int2(0, 0);
+    const uint32_t f0 = (uint32_t)q0.y, f1 = (uint32_t)q1.y;
+    uint32_t wA0, wB0, wA1, wB1;
+    blend_weights(f0, wA0, wB0);
+    blend_weights(f1, wA1, wB1);
+    const uint32_t m0 = f0 >> 10, m1 = f1 >> 10;                    // in-image flags of the four taps
+    const int o = y * d.pp + x;
+    const bool halo_l = x >= d.p2 - LT_HALO_X, halo_r = x < LT_HALO_X;
+    for (int s = s0; s < s1; ++s) {
+        const uint32_t* und = reinterpret_cast<const uint32_t*>(und_all) + (size_t)((unsigned)s) * roi_px;
+        uint32_t rgb0 = 0, rgb1 = 0;
+        if (m0) {
+            const uint32_t* b = und + q0.x;
+            uint32_t t00, t01, t10, t11;
+            if (m0 == 15u) { t00 = __ldg(b); t01 = __ldg(b + 1); t10 = __ldg(b + d.img_w); t11 = __ldg(b + d.img_w + 1); }
+            else {                                                  // BORDER_CONSTANT 0
+                t00 = (m0 & 1u) ? __ldg(b) : 0u; t01 = (m0 & 2u) ? __ldg(b + 1) : 0u;
+                t10 = (m0 & 4u) ? __ldg(b + d.img_w) : 0u; t11 = (m0 & 8u) ? __ldg(b + d.img_w + 1) : 0u;
             }
-            uint32_t t00 = (f & (1u << 10)) ? __ldg(base) : 0u;               // BORDER_CONSTANT 0
-            uint32_t t01 = (f & (1u << 11)) ? __ldg(base + 1) : 0u;
-            uint32_t t10 = (f & (1u << 12)) ? __ldg(base + d.img_w) : 0u;
-            uint32_t t11 = (f & (1u << 13)) ? __ldg(base + d.img_w + 1) : 0u;
-            uint32_t o = blend_rgbx(t00, t01, t10, t11, f);
-            r2 |= (o & 255u) << (16 * half);
-            b2 |= (uint32_t)lab_b(o, g, cb) << (16 * half);
-            if (bv_rgb) {
-                uint8_t* p = bv_rgb + (((size_t)s * d.bv_h + y) * d.bv_w + px) * 3;
-                p[0] = o & 255; p[1] = (o >> 8) & 255; p[2] = (o >> 16) & 255;
+            rgb0 = blend_taps(t00, t01, t10, t11, wA0, wB0);
+        }
+        if (m1) {
+            const uint32_t* b = und + q1.x;
+            uint32_t t00, t01, t10, t11;
+            if (m1 == 15u) { t00 = __ldg(b); t01 = __ldg(b + 1); t10 = __ldg(b + d.img_w); t11 = __ldg(b + d.img_w + 1); }
+            else {
+                t00 = (m1 & 1u) ? __ldg(b) : 0u; t01 = (m1 & 2u) ? __ldg(b + 1) : 0u;
+                t10 = (m1 & 4u) ? __ldg(b + d.img_w) : 0u; t11 = (m1 & 8u) ? __ldg(b + d.img_w + 1) : 0u;
             }
+            rgb1 = blend_taps(t00, t01, t10, t11, wA1, wB1);
+        }
+        // a pixel without a tap inside the frame is black; Lab b of black = 128
+        uint32_t r2 = (rgb0 & 255u) | ((rgb1 & 255u) << 16);
+        uint32_t b2 = (m0 ? lab_b_smem(rgb0, L) : 128u) | ((m1 ? lab_b_smem(rgb1, L) : 128u) << 16);
+        if (!hi_real) { r2 |= 0xFFFF0000u; b2 |= 0xFFFF0000u; }     // lanes beyond the image: the erosion pad
+        uint32_t* pr = planeR + (size_t)((unsigned)s) * stream_pad;
+        uint32_t* pb = planeB + (size_t)((unsigned)s) * stream_pad;
+        pr[o] = r2;
+        pb[o] = b2;
+        if (halo_l) { pr[o - d.p2] = (r2 << 16) | 0xFFFFu; pb[o - d.p2] = (b2 << 16) | 0xFFFFu; }      // seam-stitched halo columns
+        if (halo_r) { pr[o + d.p2] = (r2 >> 16) | 0xFFFF0000u; pb[o + d.p2] = (b2 >> 16) | 0xFFFF0000u; }
+        if (bv_rgb) {
+            uint8_t* p = bv_rgb + (((size_t)s * d.bv_h + y) * d.bv_w + x) * 3;
+            p[0] = rgb0 & 255; p[1] = (rgb0 >> 8) & 255; p[2] = (rgb0 >> 16) & 255;
+            if (hi_real) { p += (size_t)d.p2 * 3; p[0] = rgb1 & 255; p[1] = (rgb1 >> 8) & 255; p[2] = (rgb1 >> 16) & 255; }
         }
     }
-    store_padded(planeR, planeB, r2, b2, x, y, s, stream_pad, d);
+}
+
+int lt_launch_build_lab_yz(lt_handle* h, cudaStream_t st) {
+    k_build_lab_yz<<<1, 256, 0, st>>>(h->lab_gamma, h->lab_yz);
+    LT_LAUNCH_CHECK();
+    return 0;
 }
 
 int lt_launch_warp(lt_handle* h, uint8_t* d_bv_rgb, int n, cudaStream_t st) {
     const LtDims& d = h->d;
-    dim3 g(lt_div_up(d.p2, 256), d.bv_h, n);
-    k_warp_planes<<<g, 256, 0, st>>>(h->und_roi, h->bv_desc, h->planeR, h->planeB, d_bv_rgb, h->lab_gamma,
-                                     h->lab_cbrt, d, (unsigned)h->stream_pad);
+    dim3 g(lt_div_up(d.bv_h * d.p2, 256), lt_div_up(n, NSW));
+    k_warp_planes<<<g, 256, 0, st>>>(h->und_roi, h->bv_desc, h->planeR, h->planeB, d_bv_rgb, h->lab_yz, h->lab_cbrt, d,
+                                     (unsigned)h->stream_pad, n);
     LT_LAUNCH_CHECK();
     return 0;
 }

@@ -477,7 +477,7 @@ class BatchedLaneTracker:
         return sides, cents
 
     _DEBUG = dict(undistort_map=0, bv_map=1, overlay_map=2, r_plane=3, b_plane=4, r_tophat=5, b_tophat=6,
-                  mask=7, merged=8, lane_rows=9)
+                  mask=7, merged=8, lane_rows=9, draw_lane_rows=12)
 
     def debug_read(self, what, stream_id=0):
         code = self._DEBUG[what]
@@ -487,7 +487,7 @@ class BatchedLaneTracker:
             out = np.zeros((h, w, 2), dtype=np.int32)
         elif code == 1:
             out = np.zeros((bh, bw, 2), dtype=np.int32)
-        elif code == 9:
+        elif code in (9, 12):
             out = np.zeros((bh, 2), dtype=np.int32)
         else:
             out = np.zeros((bh, bw), dtype=np.uint8)

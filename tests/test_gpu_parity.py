@@ -250,7 +250,7 @@ def test_draw_lane_overlay(bt, torch_mod, frames_np):
         want = o.draw_lane(frames_np[t % 4])
         xs, cnt = bt.get_poly_points(np.stack([lf, rf])[None], partial)
         got = bt.draw_lane(torch_mod.as_tensor(frames_np[t % 4][None]).cuda(), xs, cnt).cpu().numpy()[0]
-        rows = bt.debug_read("lane_rows", 0)
+        rows = bt.debug_read("draw_lane_rows", 0)
         lo, hi = o.trace["lane_rows"]
         filled = hi >= lo
         assert np.array_equal(rows[filled, 0], lo[filled]) and np.array_equal(rows[filled, 1], hi[filled]), t

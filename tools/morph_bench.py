@@ -15,8 +15,11 @@ def one():
     from lane_tracker_b200 import BatchedLaneTracker, synth
     S = int(os.environ.get("LT_BENCH_STREAMS", "64"))
     dev = torch.device("cuda", 0)
-    g = torch.Generator(device="cuda").manual_seed(1)
-    pool = torch.randint(0, 256, (2, S, 720, 1280, 3), dtype=torch.uint8, device=dev, generator=g)
+    if os.environ.get("LT_BENCH_SYNTH"):
+        pool = torch.from_numpy(synth.render_streams(S, 2, first_seed=0, workers=16)).to(dev).permute(1, 0, 2, 3, 4).contiguous()
+    else:
+        g = torch.Generator(device="cuda").manual_seed(1)
+        pool = torch.randint(0, 256, (2, S, 720, 1280, 3), dtype=torch.uint8, device=dev, generator=g)
     out = torch.empty_like(pool[0])
     trk = BatchedLaneTracker(S, **synth.shipped_calibration(), device=0)
     for i in range(3):
