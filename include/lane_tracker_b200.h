@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define LT_ABI_VERSION 3
+#define LT_ABI_VERSION 4
 #define LT_MAX_AVERAGE 8          /* capacity of the n_average rings */
 
 typedef struct lt_handle lt_handle;
@@ -261,6 +261,27 @@ int lt_get_poly_points(lt_handle* h, const double* d_fits, int32_t n_streams, do
  * polygon of the given polylines, un-warps and blends it.  d_x/d_counts as above. */
 int lt_draw_lane(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int32_t n_streams,
                  const int32_t* d_x, const int32_t* d_counts, void* stream);
+
+/* LaneTracker.get_curve_radius / get_eccentricity (lane_tracker.py:530-559): per stream the left / right curve radius
+ * in metres at the bottom row (int() truncation, saturated at 2^63 - 1) from the pixel-space fits d_fits [n][2][3], and
+ * the lateral offset from the lane centre in metres from the last vertices of the polylines d_x / d_counts (layout of
+ * lt_get_poly_points).  d_radii [n][2] int64; d_eccentricity [n] double, may be NULL (then d_x / d_counts may be too).
+ * The running mean over n_average frames (:544-549) is bookkeeping of the caller, as in the reference. */
+int lt_lane_metrics(lt_handle* h, const double* d_fits, const int32_t* d_x, const int32_t* d_counts, int32_t n_streams,
+                    int64_t* d_radii, double* d_eccentricity, void* stream);
+
+/* bilateral_adaptive_threshold (lane_tracker.py:14-83) on any single-channel uint8 device image (pitches in bytes):
+ * mode 0 = 'floor', 1 = 'ceil'; true_value / false_value in [0, 255].  Runs on the current device. */
+int lt_bilateral_adaptive_threshold(const uint8_t* d_img, int32_t width, int32_t height, int64_t pitch_in, uint8_t* d_out,
+                                    int64_t pitch_out, int32_t ksize, int32_t C, int32_t mode, int32_t true_value,
+                                    int32_t false_value, void* stream);
+
+/* The cv2.putText overlays of draw_lane (kind 0) / print_failure (kind 1) (lane_tracker.py:653-659, 668-672) drawn in
+ * place on device frames from HOST arrays of per-frame values (radius and eccentricity only read for kind 0; "Frame: n"
+ * shows h_counter - 1 when the handle was created with print_frame_count).  Needs lt_set_text_sprites.  Synchronises
+ * the stream once (staging of the small host arrays). */
+int lt_draw_text(lt_handle* h, uint8_t* d_frames, int32_t n_frames, const int32_t* h_kind, const int64_t* h_radius,
+                 const double* h_eccentricity, const int32_t* h_counter, void* stream);
 
 /* ---- debug views (lane_tracker.py:675-793, utils.py:57-103; not on the per-frame path) ---- */
 

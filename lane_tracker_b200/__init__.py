@@ -6,12 +6,13 @@ importing them without either raises.  ``lane_tracker_b200.synth`` (test/bench d
 """
 from .utils import create_split_view, load_camera_calib, load_warp_params  # noqa: F401
 
-__all__ = ["LaneTracker", "BatchedLaneTracker", "HostPipeline", "DevicePipeline", "GraphedProcess", "load_camera_calib", "load_warp_params",
-           "create_split_view"]
+__all__ = ["LaneTracker", "BatchedLaneTracker", "HostPipeline", "DevicePipeline", "GraphedProcess", "bilateral_adaptive_threshold",
+           "load_camera_calib", "load_warp_params", "create_split_view"]
 
 
 def __getattr__(name):
-    if name in ("LaneTracker", "BatchedLaneTracker", "HostPipeline", "DevicePipeline", "GraphedProcess", "make_params", "RESULT_DTYPE"):
+    if name in ("LaneTracker", "BatchedLaneTracker", "HostPipeline", "DevicePipeline", "GraphedProcess", "make_params", "RESULT_DTYPE",
+                "bilateral_adaptive_threshold"):
         from . import tracker
         return getattr(tracker, name)
     raise AttributeError(name)

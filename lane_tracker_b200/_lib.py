@@ -17,7 +17,7 @@ LIB_PATH = (os.path.join(HERE, "_variants", "liblane_tracker_b200_%s.so" % _vari
 
 LT_MAX_AVERAGE = 8
 LT_MAX_LEVELS = 128
-LT_ABI_VERSION = 3
+LT_ABI_VERSION = 4
 LT_NSTAGES = 16
 
 i32, f64 = C.c_int32, C.c_double
@@ -108,6 +108,9 @@ SIGNATURES = {
     "lt_check_validity": (C.c_int, [P, P, i32, P, P, P]),
     "lt_get_poly_points": (C.c_int, [P, P, i32, f64, P, P, P]),
     "lt_draw_lane": (C.c_int, [P, P, P, i32, P, P, P]),
+    "lt_lane_metrics": (C.c_int, [P, P, P, P, i32, P, P, P]),
+    "lt_bilateral_adaptive_threshold": (C.c_int, [P, i32, i32, C.c_int64, P, C.c_int64, i32, i32, i32, i32, i32, P]),
+    "lt_draw_text": (C.c_int, [P, P, i32, P, P, P, P, P]),
     "lt_warp_frame": (C.c_int, [P, P, i32, P, P]),
     "lt_visualize_search": (C.c_int, [P, C.POINTER(lt_vis), P, P, P, P, P, P]),
     "lt_resize_linear": (C.c_int, [P, i32, i32, i32, C.c_int64, P, i32, i32, C.c_int64, P]),

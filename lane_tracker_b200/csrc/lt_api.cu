@@ -140,7 +140,7 @@ extern "C" int lt_destroy(lt_handle* h) {
     }
     void* ptrs[] = {h->und_map, h->bv_map, h->ov_map, h->bv_desc, h->und_desc, h->lab_yz, h->fused_desc, h->lab_gamma, h->lab_cbrt, h->pixels, h->pix_counts, h->lane_rows,
                     h->avg_x, h->state, h->att, h->retry_list, h->retry_count, h->draw_flags, h->scratch_bv, h->vis_scratch,
-                    h->cap_pixels, h->cap_counts, h->cap_cents, h->cap_ncents, h->dl_rows, h->dl_flags,
+                    h->cap_pixels, h->cap_counts, h->cap_cents, h->cap_ncents, h->dl_rows, h->dl_flags, h->txt_state, h->txt_flags,
                     h->txt_tables, h->txt_char_start, h->txt_dy, h->txt_dx, h->txt_lut, h->txt_advance, h->txt_pair_overlap,
                     h->txt_bitmaps};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -790,6 +790,117 @@ extern "C" int lt_draw_lane(lt_handle* h, const uint8_t* d_frames, uint8_t* d_ou
     view.draw_flags = h->dl_flags;
     if ((rc = lt_launch_lane_rows(&view, d_x, d_counts, n, st))) return rc;
     return lt_launch_overlay(&view, d_frames, d_out, n, view.draw_flags, st);
+}
+
+// get_curve_radius / get_eccentricity (lane_tracker.py:530-559) for caller-supplied fits and polylines.
+// The metric refit of the same pixels is the analytic rescaling of the pixel-space fit (a' = a*mpph/mppv^2,
+// b' = b*mpph/mppv), exactly as k_update_state computes it inside lt_process.
+__global__ void k_lane_metrics(const double* __restrict__ fits, const int* __restrict__ xs, const int* __restrict__ counts, int n,
+                               int W, int H, double mppv, double mpph, long long* __restrict__ radii, double* __restrict__ ecc) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    for (int side = 0; side < 2; ++side) {
+        const double a = fits[(size_t)s * 6 + side * 3], b = fits[(size_t)s * 6 + side * 3 + 1];
+        const double am = a * mpph / (mppv * mppv), bm = b * mpph / mppv;
+        const double g = 2.0 * am * (double)H * mppv + bm;
+        const double r = pow(1.0 + g * g, 1.5) / fabs(2.0 * am);
+        radii[s * 2 + side] = (!(r == r) || r >= 9.2233720368547758e18) ? 0x7FFFFFFFFFFFFFFFLL : (long long)r;   // int(float)
+    }
+    if (ecc) {
+        const int nl = counts ? counts[s * 2] : 0, nr = counts ? counts[s * 2 + 1] : 0;
+        double e = 0.0;
+        if (xs && nl > 0 && nr > 0) {
+            const int mid = W / 2, left = xs[(size_t)s * 2 * H + nl - 1], right = xs[(size_t)s * 2 * H + H + nr - 1];
+            e = __dmul_rn((double)((mid - left) - (right - mid)) / 2.0, mpph);
+        }
+        ecc[s] = e;
+    }
+}
+
+extern "C" int lt_lane_metrics(lt_handle* h, const double* d_fits, const int32_t* d_x, const int32_t* d_counts, int32_t n,
+                               int64_t* d_radii, double* d_eccentricity, void* stream) {
+    int rc;
+    if ((rc = check_any_n(h, n))) return rc;
+    if (!d_fits || !d_radii || (d_eccentricity && (!d_x || !d_counts))) { lt_set_error("null argument"); return -1; }
+    k_lane_metrics<<<lt_div_up(n, 64), 64, 0, (cudaStream_t)stream>>>(d_fits, d_x, d_counts, n, h->d.bv_w, h->d.bv_h, h->cfg.mppv,
+                                                                     h->cfg.mpph, (long long*)d_radii, d_eccentricity);
+    LT_LAUNCH_CHECK();
+    return 0;
+}
+
+// bilateral_adaptive_threshold (lane_tracker.py:14-83) on an arbitrary single-channel image: four zero-padded side sums
+// of k neighbours against k*p -/+ C*k.  (filter2D's CV_16S saturation cannot change the sign the reference tests.)
+__global__ void __launch_bounds__(256)
+k_bilateral_threshold(const uint8_t* __restrict__ img, uint8_t* __restrict__ out, int w, int h, size_t pitch_in, size_t pitch_out,
+                      int k, int C, int ceil_mode, int true_value, int false_value) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const uint8_t* row = img + (size_t)y * pitch_in;
+    int L = 0, R = 0, U = 0, D = 0;
+    for (int i = 1; i <= k; ++i) {
+        if (x - i >= 0) L += __ldg(&row[x - i]);
+        if (x + i < w) R += __ldg(&row[x + i]);
+        if (y - i >= 0) U += __ldg(&img[(size_t)(y - i) * pitch_in + x]);
+        if (y + i < h) D += __ldg(&img[(size_t)(y + i) * pitch_in + x]);
+    }
+    const int kp = k * (int)__ldg(&row[x]), delta = ceil_mode ? -C * k : C * k;
+    bool pass;
+    if (!ceil_mode) pass = ((L - kp + delta < 0) && (R - kp + delta < 0)) || ((U - kp + delta < 0) && (D - kp + delta < 0));
+    else pass = ((L - kp + delta > 0) && (R - kp + delta > 0)) || ((U - kp + delta > 0) && (D - kp + delta > 0));
+    out[(size_t)y * pitch_out + x] = (uint8_t)(pass ? true_value : false_value);
+}
+
+extern "C" int lt_bilateral_adaptive_threshold(const uint8_t* d_img, int32_t width, int32_t height, int64_t pitch_in, uint8_t* d_out,
+                                               int64_t pitch_out, int32_t ksize, int32_t C, int32_t mode, int32_t true_value,
+                                               int32_t false_value, void* stream) {
+    if (!d_img || !d_out) { lt_set_error("null argument"); return -1; }
+    if (width < 1 || height < 1 || pitch_in < width || pitch_out < width || ksize < 1 || ksize > 32767 / 255 * 64) {
+        lt_set_error("lt_bilateral_adaptive_threshold: bad geometry or ksize");
+        return -1;
+    }
+    if (mode != 0 && mode != 1) { lt_set_error("Unexpected mode value. Expected value is 'floor' or 'ceil'."); return -1; }
+    if (true_value < 0 || true_value > 255 || false_value < 0 || false_value > 255) { lt_set_error("mask values must lie in [0, 255]"); return -1; }
+    k_bilateral_threshold<<<dim3(lt_div_up(width, 256), height), 256, 0, (cudaStream_t)stream>>>(
+        d_img, d_out, width, height, (size_t)pitch_in, (size_t)pitch_out, ksize, C, mode, true_value, false_value);
+    LT_LAUNCH_CHECK();
+    return 0;
+}
+
+// The putText overlays of draw_lane (kind 0: "Curve Radius: .. m", "Eccentricity: .. m") and print_failure (kind 1:
+// "Lane Line Detection Failed"), plus "Frame: n" when the tracker was created with print_frame_count
+// (lane_tracker.py:653-659, 668-672), drawn in place on device frames from caller-supplied values.
+extern "C" int lt_draw_text(lt_handle* h, uint8_t* d_frames, int32_t n, const int32_t* h_kind, const int64_t* h_radius,
+                            const double* h_eccentricity, const int32_t* h_counter, void* stream) {
+    int rc;
+    if ((rc = check_n(h, n))) return rc;
+    if (!d_frames || !h_kind || !h_counter) { lt_set_error("null argument"); return -1; }
+    if (!h->txt_tables) { lt_set_error("no text sprites installed (lt_set_text_sprites)"); return -1; }
+    LT_CUDA(cudaSetDevice(h->cfg.device));
+    if (!h->txt_state) {
+        if ((rc = dev_alloc(&h->txt_state, (size_t)h->S))) return rc;
+        if ((rc = dev_alloc(&h->txt_flags, (size_t)h->S))) return rc;
+    }
+    std::vector<LtDevState> st(n);
+    std::vector<int> flags(n);
+    for (int i = 0; i < n; ++i) {
+        memset(&st[i], 0, sizeof(LtDevState));
+        if (h_kind[i] != 0 && h_kind[i] != 1) { lt_set_error("text kind must be 0 (lane) or 1 (failure)"); return -1; }
+        flags[i] = h_kind[i] == 0 ? 1 : 0;
+        if (h_kind[i] == 0) {
+            if (!h_radius || !h_eccentricity) { lt_set_error("lane text needs the radius and the eccentricity"); return -1; }
+            st[i].s.average_curve_radius = h_radius[i];
+            st[i].s.eccentricity = h_eccentricity[i];
+        }
+        st[i].s.counter = h_counter[i];
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    LT_CUDA(cudaMemcpyAsync(h->txt_state, st.data(), (size_t)n * sizeof(LtDevState), cudaMemcpyHostToDevice, s));
+    LT_CUDA(cudaMemcpyAsync(h->txt_flags, flags.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+    LT_CUDA(cudaStreamSynchronize(s));                 // the staging vectors are pageable host memory
+    lt_handle view = *h;
+    view.state = h->txt_state;
+    view.draw_flags = h->txt_flags;
+    return lt_launch_text(&view, d_frames, n, s);
 }
 
 // ---------------------------------------------------------------------------

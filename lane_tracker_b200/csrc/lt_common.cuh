@@ -109,6 +109,7 @@ struct lt_handle {
     int txt_nchars, txt_first, txt_parallel_lines;
     int txt_row0, txt_row1;            // frame rows the text lines can touch: [txt_row0, txt_row1)
     int2* dl_rows; int* dl_flags;      // lazily allocated polygon rows / flags of the lt_draw_lane stage call
+    LtDevState* txt_state; int* txt_flags;   // lazily allocated state / flags the lt_draw_text stage call formats from
     unsigned long long* txt_bitmaps;   // [nchars][64] rows of 64 bits: glyph pixel (dy + 32, dx + 8)
     unsigned char* txt_pair_overlap;   // [nchars][nchars]: glyph b drawn right after glyph a shares pixels with it
     cudaEvent_t* prof_ev; int* prof_stage; int prof_cap, prof_n, prof_active, prof_calls, prof_max_calls;

@@ -50,6 +50,37 @@ def make_params(**kw):
     return out
 
 
+def _float64_mean(v):
+    """np.average of a short list in NumPy's float64 summation order (pairwise unrolled by 8 from 8 elements on)."""
+    if len(v) == 8:
+        return (((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]))) / 8.0
+    acc = v[0]
+    for x in v[1:]:
+        acc = acc + x
+    return acc / len(v)
+
+
+def bilateral_adaptive_threshold(img, ksize=30, C=0, mode='floor', true_value=255, false_value=0, device=None):
+    """Drop-in for the reference's module-level ``bilateral_adaptive_threshold`` (lane_tracker.py:14-83): cross-shaped
+    adaptive threshold of a single-channel uint8 image, computed on the GPU.  NumPy in, NumPy out."""
+    if mode not in ('floor', 'ceil'):
+        raise ValueError("Unexpected mode value. Expected value is 'floor' or 'ceil'.")     # lane_tracker.py:71
+    if not torch.cuda.is_available():
+        raise _lib.LaneTrackerError("lane_tracker_b200 needs a CUDA device; there is no CPU path")
+    lib = _lib.load()
+    a = np.ascontiguousarray(img)
+    if a.ndim != 2 or a.dtype != np.uint8:
+        raise ValueError("img must be a single-channel uint8 image")
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    with torch.cuda.device(dev):
+        d = torch.from_numpy(a).to(dev)
+        out = torch.empty_like(d)
+        check(lib.lt_bilateral_adaptive_threshold(_ptr(d), int(a.shape[1]), int(a.shape[0]), int(a.shape[1]), _ptr(out),
+                                                  int(a.shape[1]), int(ksize), int(C), 0 if mode == 'floor' else 1,
+                                                  int(true_value), int(false_value), _stream_ptr(dev)))
+        return out.cpu().numpy()
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -386,6 +417,28 @@ class BatchedLaneTracker:
         check(self.lib.lt_draw_lane(self._h, _ptr(frames), _ptr(out), n, _ptr(xs), _ptr(counts),
                                     _stream_ptr(self.device)))
         return out
+
+    def lane_metrics(self, fits, xs=None, counts=None):
+        """Curve radii [n, 2] (int64, metres) and eccentricity [n] (metres) of get_curve_radius / get_eccentricity
+        (lane_tracker.py:530-559) from pixel-space fits [n, 2, 3] and the polylines of ``get_poly_points``."""
+        f = torch.as_tensor(np.asarray(fits, dtype=np.float64).reshape(-1, 2, 3)).to(self.device)
+        n = int(f.shape[0])
+        radii = torch.zeros((n, 2), dtype=torch.int64, device=self.device)
+        ecc = torch.zeros((n,), dtype=torch.float64, device=self.device) if xs is not None else None
+        check(self.lib.lt_lane_metrics(self._h, _ptr(f), _ptr(xs), _ptr(counts), n, _ptr(radii), _ptr(ecc),
+                                       _stream_ptr(self.device)))
+        return radii.cpu().numpy(), (ecc.cpu().numpy() if ecc is not None else None)
+
+    def draw_text(self, frames, kinds, radii=None, eccentricities=None, counters=None):
+        """The putText overlays of draw_lane (kind 0) / print_failure (kind 1) in place on device frames
+        (lane_tracker.py:653-659, 668-672)."""
+        n = self._check_frames(frames)
+        k = (C.c_int32 * n)(*[int(v) for v in kinds])
+        r = (C.c_int64 * n)(*[int(v) for v in (radii if radii is not None else [0] * n)])
+        e = (C.c_double * n)(*[float(v) for v in (eccentricities if eccentricities is not None else [0.0] * n)])
+        c = (C.c_int32 * n)(*[int(v) for v in (counters if counters is not None else [0] * n)])
+        check(self.lib.lt_draw_text(self._h, _ptr(frames), n, k, r, e, c, _stream_ptr(self.device)))
+        return frames
 
     # -- debug views ---------------------------------------------------------
     def warp_frame(self, frames):
@@ -754,10 +807,11 @@ class HostPipeline:
 class LaneTracker:
     """Drop-in for the reference ``LaneTracker`` (same constructor, lane_tracker.py:101).
 
-    NumPy arrays in, NumPy arrays out; every computation runs on the GPU.  Differences from the
-    reference, all documented in DESIGN.md: the caller's ``img`` is never modified (the reference
-    draws its text into it).  The debug views (``visualize_search``, ``split_view``) are rendered on the device
-    from the buffers of the last ``process`` call.
+    NumPy arrays in, NumPy arrays out; every computation runs on the GPU.  One deliberate difference from the
+    reference: ``process``, ``draw_lane`` and ``print_failure`` never modify the caller's ``img`` (the reference's
+    ``cv2.putText`` calls draw into the input array, lane_tracker.py:653-659, 668-672, and ``print_failure`` returns that
+    same array); the returned frame is identical.  The debug views (``visualize_search``, ``split_view``) are rendered on
+    the device from the buffers of the last ``process`` call.
     """
 
     # the second attempt's hard-coded search parameters (lane_tracker.py:1081-1099); the debug views of a frame
@@ -864,7 +918,9 @@ class LaneTracker:
                 ignore_bottom=30, bandwidth=25, partial=1.0, n_tries=2, visualize_search=False,
                 split_view=False, diagnostics=False):
         """lane_tracker.py:876-1209.  Returns the annotated frame (new array); with ``visualize_search`` the tuple
-        (frame, search visualisation), with ``split_view`` the three-panel canvas (lane_tracker.py:1161-1173)."""
+        (frame, search visualisation), with ``split_view`` the three-panel canvas (lane_tracker.py:1161-1173).
+        Unlike the reference, the text overlays are NOT also written into the caller's ``img`` (its in-place
+        ``cv2.putText``, lane_tracker.py:653-659 / 668-672): the input array is left untouched."""
         debug = bool(visualize_search | split_view)
         band_coeffs = (self.last_left_coeffs, self.last_right_coeffs)      # what a band search of this frame uses
         p = make_params(ksize_r=ksize_r, C_r=C_r, ksize_b=ksize_b, C_b=C_b, filter_type=filter_type,
@@ -1049,18 +1105,39 @@ class LaneTracker:
         if diagnostics:
             print("x1_diff == {:.2f}, x2_diff == {:.2f}, x3_diff == {:.2f}, valid == {}".format(*diffs[0], valid[0]))
 
+    def get_curve_radius(self):
+        """lane_tracker.py:530-549: curve radii in metres of the current lane pixel sets (left_x/left_y, right_x/right_y),
+        appended to the running mean over n_average frames."""
+        fits = self._bt.fit_poly([[(self.left_y, self.left_x), (self.right_y, self.right_x)]])
+        radii, _ = self._bt.lane_metrics(fits)
+        self.left_curve_radius, self.right_curve_radius = int(radii[0, 0]), int(radii[0, 1])
+        average_curve_radius = int(0.5 * (self.left_curve_radius + self.right_curve_radius))
+        self.average_curve_radii.append(average_curve_radius)
+        if len(self.average_curve_radii) > self.n_average:
+            self.average_curve_radii.pop(0)
+        real_curve_radii = [float(r) for r in self.average_curve_radii if r > 0]
+        self.average_curve_radius = int(_float64_mean(real_curve_radii))
+
+    def get_eccentricity(self):
+        """lane_tracker.py:551-559: lateral offset of the car from the lane centre in metres (left_avg_x / right_avg_x)."""
+        bh = self._bt.warped_size[1]
+        xs = np.zeros((1, 2, bh), dtype=np.int32)
+        cnt = np.array([[len(self.left_avg_x), len(self.right_avg_x)]], dtype=np.int32)
+        xs[0, 0, :cnt[0, 0]] = self.left_avg_x
+        xs[0, 1, :cnt[0, 1]] = self.right_avg_x
+        dev = self._bt.device
+        _, ecc = self._bt.lane_metrics(np.zeros((1, 2, 3)), torch.as_tensor(xs).to(dev), torch.as_tensor(cnt).to(dev))
+        self.eccentricity = float(ecc[0])
+
     def draw_lane(self, img):
-        """lane_tracker.py:629-662: uses left_avg_x / right_avg_x, average_curve_radius, eccentricity."""
+        """lane_tracker.py:629-662: uses left_avg_x / right_avg_x, average_curve_radius, eccentricity.  Text first, then the
+        blend over it, as in the reference; all on the device.  The caller's ``img`` is not modified (the reference draws
+        its text into it)."""
         w, h = self._bt.img_size
         bh = self._bt.warped_size[1]
-        if self._bt.text_enabled and self.average_curve_radius is not None and self.eccentricity is not None:
-            from .text import TextSprites, overlay_strings     # text goes onto the frame before the blend (:653-659)
-            img = np.array(img, copy=True)
-            sp = TextSprites.load()
-            for text, org in overlay_strings(True, self.average_curve_radius, self.eccentricity, self.counter,
-                                             self.print_frame_count):
-                sp.render(img, text, org)
         frames = self._upload(img, (h, w, 3)).unsqueeze(0)
+        if self._bt.text_enabled and self.average_curve_radius is not None and self.eccentricity is not None:
+            self._bt.draw_text(frames, [0], [self.average_curve_radius], [self.eccentricity], [self.counter])
         xs = np.zeros((1, 2, bh), dtype=np.int32)
         cnt = np.array([[len(self.left_avg_x), len(self.right_avg_x)]], dtype=np.int32)
         xs[0, 0, :cnt[0, 0]] = self.left_avg_x
@@ -1070,11 +1147,9 @@ class LaneTracker:
         return out[0].cpu().numpy()
 
     def print_failure(self, img):
-        """lane_tracker.py:664-673: the failure message (and frame number) on a copy of the frame."""
-        from .text import TextSprites, overlay_strings
-        out = np.array(img, copy=True)
+        """lane_tracker.py:664-673: the failure message (and frame number) on a copy of the frame, drawn on the device."""
+        w, h = self._bt.img_size
+        frames = self._upload(img, (h, w, 3)).unsqueeze(0)
         if self._bt.text_enabled:
-            sp = TextSprites.load()
-            for text, org in overlay_strings(False, None, None, self.counter, self.print_frame_count):
-                sp.render(out, text, org)
-        return out
+            self._bt.draw_text(frames, [1], None, None, [self.counter])
+        return frames[0].cpu().numpy()

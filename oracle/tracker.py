@@ -362,7 +362,8 @@ class OracleLaneTracker:
         """The putText calls of draw_lane (:653-659) / print_failure (:668-672), on a copy of the frame."""
         if not self.render_text:
             return img
-        from lane_tracker_b200.text import TextSprites, overlay_strings
+        from lane_tracker_b200.text import TextSprites
+        from oracle.text import overlay_strings, render
         img = img.copy()
         for text, org in overlay_strings(drew_lane, self.average_curve_radius, self.eccentricity, self.counter,
                                          self.print_frame_count):
@@ -373,7 +374,7 @@ class OracleLaneTracker:
             else:
                 if self._sprites is None:
                     self._sprites = TextSprites.load()
-                self._sprites.render(img, text, org)
+                render(self._sprites, img, text, org)
         return img
 
     def draw_lane(self, img):

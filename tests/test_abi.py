@@ -35,7 +35,7 @@ def test_exports_every_declared_symbol(lib):
     for n in names:
         assert hasattr(lib, n), "library does not export %s" % n
         assert n in _lib.SIGNATURES, "binding does not cover %s" % n
-    assert lib.lt_abi_version() == _lib.LT_ABI_VERSION == 3
+    assert lib.lt_abi_version() == _lib.LT_ABI_VERSION == 4
 
 
 def test_struct_layouts_match_header(tmp_path, lib):

@@ -253,3 +253,62 @@ def test_parameter_sets_the_kernels_cannot_honour_are_rejected(torch_mod):
         with pytest.raises(_lib.LaneTrackerError):
             bt.process(d, None, **bad)
     bt.close()
+
+
+def test_dropin_metric_and_text_methods_on_the_device(torch_mod):
+    """get_curve_radius / get_eccentricity (lane_tracker.py:530-559), draw_lane / print_failure with their putText overlays
+    (629-673) and the module-level bilateral_adaptive_threshold (14-83) as drop-in calls, against the oracle / cv2."""
+    import lane_tracker_b200 as ltb
+    from lane_tracker_b200 import LaneTracker
+    warnings.simplefilter("ignore")
+    lt = LaneTracker(**CAL, print_frame_count=True)
+    o = OracleLaneTracker(**CAL, print_frame_count=True)
+    vid = synth.RoadVideo(12)
+    for t in range(3):
+        f = vid.frame(t)
+        assert _mism(lt.process(f), o.process(f.copy())) == 0
+    # the two metric methods, called directly on the state process() left behind
+    lt.average_curve_radii, o.average_curve_radii = list(lt.average_curve_radii), list(o.average_curve_radii)
+    lt.get_curve_radius()
+    o.get_curve_radius()
+    assert (lt.left_curve_radius, lt.right_curve_radius) == (o.left_curve_radius, o.right_curve_radius)
+    assert lt.average_curve_radii == o.average_curve_radii and lt.average_curve_radius == o.average_curve_radius
+    lt.eccentricity = None
+    lt.get_eccentricity()
+    o.get_eccentricity()
+    assert lt.eccentricity == o.eccentricity
+    # draw_lane / print_failure: text + polygon, the caller's frame untouched
+    f = vid.frame(5)
+    keep = f.copy()
+    assert _mism(lt.draw_lane(f), o.draw_lane(f.copy())) == 0
+    assert _mism(lt.print_failure(f), o.print_failure(f.copy())) == 0
+    assert np.array_equal(f, keep)
+    # module-level threshold, both modes, other mask values, a non-bird's-eye image size
+    import cv2
+    rng = np.random.default_rng(8)
+    img = cv2.GaussianBlur(rng.integers(0, 256, (333, 517), dtype=np.uint8), (0, 0), 2.0)
+    for kw in (dict(), dict(ksize=12, C=3), dict(ksize=45, C=2, mode='ceil'), dict(ksize=7, C=0, true_value=200, false_value=9)):
+        want = _reference_bilateral(img, **kw)
+        assert _mism(ltb.bilateral_adaptive_threshold(img, **kw), want) == 0, kw
+    with pytest.raises(ValueError):
+        ltb.bilateral_adaptive_threshold(img, mode='round')
+
+
+def _reference_bilateral(img, ksize=30, C=0, mode='floor', true_value=255, false_value=0):
+    """The reference's own filter2D formulation (lane_tracker.py:61-81), executed with cv2."""
+    import cv2
+    mask = np.full(img.shape, false_value, dtype=np.uint8)
+    kl = np.array([[1] * ksize + [-ksize]], dtype=np.int16)
+    kr = np.array([[-ksize] + [1] * ksize], dtype=np.int16)
+    ku = np.array([[1]] * ksize + [[-ksize]], dtype=np.int16)
+    kd = np.array([[-ksize]] + [[1]] * ksize, dtype=np.int16)
+    delta = C * ksize if mode == 'floor' else -C * ksize
+    lt_ = cv2.filter2D(img, cv2.CV_16S, kl, anchor=(ksize, 0), delta=delta, borderType=cv2.BORDER_CONSTANT)
+    rt_ = cv2.filter2D(img, cv2.CV_16S, kr, anchor=(0, 0), delta=delta, borderType=cv2.BORDER_CONSTANT)
+    ut_ = cv2.filter2D(img, cv2.CV_16S, ku, anchor=(0, ksize), delta=delta, borderType=cv2.BORDER_CONSTANT)
+    dt_ = cv2.filter2D(img, cv2.CV_16S, kd, anchor=(0, 0), delta=delta, borderType=cv2.BORDER_CONSTANT)
+    if mode == 'floor':
+        mask[((0 > lt_) & (0 > rt_)) | ((0 > ut_) & (0 > dt_))] = true_value
+    else:
+        mask[((0 < lt_) & (0 < rt_)) | ((0 < ut_) & (0 < dt_))] = true_value
+    return mask

