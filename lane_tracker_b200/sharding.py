@@ -42,3 +42,34 @@ def gather_results(local_results, total_streams, group=None):
             raise RuntimeError("rank %d returned %d records" % (src_rank, len(arr)))
         parts.append(arr)
     return np.concatenate(parts)
+
+
+def gather_records(local_records, total_streams, group=None, out=None):
+    """Gather the ranks' result records on rank 0 as raw bytes, in stream order, with ONE tensor collective on the host
+    process group (gloo): no pickling, no device collective.  ``local_records``: CPU uint8 tensor (pinned is fine) holding
+    this rank's records back to back; every record has the same size.  Returns a uint8 tensor of all ``total_streams``
+    records on rank 0 (``out`` is reused when given) and None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = len(stream_range(total_streams, world, rank))
+    if mine == 0 or local_records.numel() % mine:
+        raise ValueError("rank %d: %d bytes do not hold %d records" % (rank, local_records.numel(), mine))
+    rec = local_records.numel() // mine
+    largest = len(stream_range(total_streams, world, 0))             # block sizes differ by at most one; rank 0 has the largest
+    send = local_records
+    if mine != largest:
+        send = torch.zeros(largest * rec, dtype=torch.uint8)
+        send[:mine * rec] = local_records
+    bucket = [torch.empty(largest * rec, dtype=torch.uint8) for _ in range(world)] if rank == 0 else None
+    dist.gather(send, bucket, dst=0, group=group)
+    if rank != 0:
+        return None
+    if out is None:
+        out = torch.empty(total_streams * rec, dtype=torch.uint8)
+    pos = 0
+    for r in range(world):
+        k = len(stream_range(total_streams, world, r)) * rec
+        out[pos:pos + k] = bucket[r][:k]
+        pos += k
+    return out

@@ -47,6 +47,11 @@ def _worker(rank, world, port, total, out_path):
     local["n_left"] = np.array(list(ids)) * 10          # stands in for per-stream results
     local["left_fit"][:, 2] = np.array(list(ids)) + 0.5
     got = sharding.gather_results(local, total)
+    raw = sharding.gather_records(torch.from_numpy(local.view(np.uint8).copy()), total)     # the tensor form bench.py uses
+    if rank == 0:
+        assert np.array_equal(raw.numpy().view(RESULT_DTYPE), got)
+    else:
+        assert raw is None
     # timing plumbing of bench.py: max over ranks
     t = torch.tensor([float(rank + 1)], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
