@@ -372,19 +372,25 @@ __device__ __forceinline__ void warp_row_prefix(const uint32_t* __restrict__ pro
 // column segment with running window sums L, R in packed u16x2 registers and emits finished 32-column mask
 // words directly.  Rows sit in different banks (odd half-word pitch), so the walk is conflict-free.
 constexpr int CROSSH_ROWS = 32;
-constexpr int CROSSH_WARPS = 4;
+#ifndef LT_CROSSH_WARPS
+#define LT_CROSSH_WARPS 8
+#endif
+constexpr int CROSSH_WARPS = LT_CROSSH_WARPS;
 
 __device__ __forceinline__ uint32_t unpack_pair(uint32_t v16) {            // (hi<<8 | lo) -> hi<<16 | lo
     return __byte_perm(v16, 0, 0x4140);
 }
 
+// One launch thresholds up to two planes (blockIdx.z): plane 0 with (k0, C0), plane 1 with (k1, C1).
 __global__ void __launch_bounds__(CROSSH_WARPS * 32)
-k_cross_h(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_all, LtDims d, int k, int C,
-          int accumulate, int pitch, int ppitch, size_t plane_stride, size_t bits_stride, const int* __restrict__ list,
-          const int* __restrict__ count) {
+k_cross_h(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plane1, uint32_t* __restrict__ bits_all, LtDims d,
+          int k0, int C0, int k1, int C1, int accumulate, int pitch0, int pitch1, int ppitch, size_t plane_stride,
+          size_t bits_stride, const int* __restrict__ list, const int* __restrict__ count) {
     int slot = blockIdx.y;
     if (count != nullptr && slot >= *count) return;
     int s = list ? list[slot] : slot;
+    const uint32_t* __restrict__ plane_all = blockIdx.z ? plane1 : plane0;
+    const int k = blockIdx.z ? k1 : k0, C = blockIdx.z ? C1 : C0, pitch = blockIdx.z ? pitch1 : pitch0;
     extern __shared__ uint32_t smem[];
     unsigned short* tile = reinterpret_cast<unsigned short*>(smem);     // [32][pitch], entry i <-> packed column i - k
     const int y0 = blockIdx.x * CROSSH_ROWS;
@@ -528,12 +534,16 @@ constexpr int CV_BAND = 128;        // rows per CTA (multiple of 32)
 
 template <bool PACKED, bool ROWPAD>
 __global__ void __launch_bounds__(32)
-k_cross_v(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bits_all, LtDims d, int k, int C,
-          int ppitch, size_t plane_stride, size_t bits_stride, const int* __restrict__ list,
-          const int* __restrict__ count) {
-    int slot = blockIdx.z;
+k_cross_v(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plane1, uint32_t* __restrict__ bits_all, LtDims d,
+          int k0, int C0, int k1, int C1, int nslots, int ppitch, size_t plane_stride, size_t bits_stride,
+          const int* __restrict__ list, const int* __restrict__ count) {
+    // blockIdx.z = plane * nslots + stream slot (two planes in one launch when plane1 != nullptr)
+    const int which = blockIdx.z >= nslots ? 1 : 0;
+    int slot = blockIdx.z - which * nslots;
     if (count != nullptr && slot >= *count) return;
     int s = list ? list[slot] : slot;
+    const uint32_t* __restrict__ plane_all = which ? plane1 : plane0;
+    const int k = which ? k1 : k0, C = which ? C1 : C0;
     const int lane = threadIdx.x;
     const int x = blockIdx.x * 32 + lane;              // packed column; p2 is a multiple of 32
     const int yb0 = blockIdx.y * CV_BAND, yb1 = min(yb0 + CV_BAND, d.bv_h);
@@ -828,22 +838,38 @@ int lt_launch_plane_to_u8(lt_handle* h, const uint32_t* plane, int pitch, uint8_
 // the whole filter for one attempt
 // ---------------------------------------------------------------------------
 
+static bool cross_packed(int k, int C) { return k <= 127 && C >= 0 && k * 255 + C * k + 1 < 32768; }   // packed u16 lanes stay below 2^15
+
+static int crossh_pitch(const LtDims& d, int k) {
+    int pitch = d.p2 + 2 * k + 2;
+    while (((pitch >> 1) & 1) == 0 || (pitch & 1)) ++pitch;       // pitch = 2 * odd: rows land in distinct banks
+    return pitch;
+}
+
+// horizontal half of one plane, or of two planes in one launch (plane1 != nullptr; both must take the packed kernel)
 static int launch_cross_h(lt_handle* h, const uint32_t* plane, uint32_t* bits, int k, int C, int accumulate, int n,
-                          const int* list, const int* count, cudaStream_t st) {
+                          const int* list, const int* count, cudaStream_t st, const uint32_t* plane1 = nullptr, int k1 = 0,
+                          int C1 = 0) {
     const LtDims& d = h->d;
     const int ppitch = d.pp;
     const size_t pstride = h->stream_pad;
-    if (k <= 127 && C >= 0 && k * 255 + C * k + 1 < 32768) {   // packed u16 lanes must stay below 2^15
-        int pitch = d.p2 + 2 * k + 2;
-        while (((pitch >> 1) & 1) == 0 || (pitch & 1)) ++pitch;       // pitch = 2 * odd: rows land in distinct banks
-        size_t smem = (size_t)CROSSH_ROWS * pitch * sizeof(unsigned short);
+    if (cross_packed(k, C) && (!plane1 || cross_packed(k1, C1))) {
+        const int pitch0 = crossh_pitch(d, k), pitch1 = plane1 ? crossh_pitch(d, k1) : pitch0;
+        size_t smem = (size_t)CROSSH_ROWS * (pitch0 > pitch1 ? pitch0 : pitch1) * sizeof(unsigned short);
         int rc = lt_ensure_smem((const void*)k_cross_h, smem);
         if (rc) return rc;
-        dim3 gh(lt_div_up(d.bv_h, CROSSH_ROWS), n);
-        k_cross_h<<<gh, CROSSH_WARPS * 32, smem, st>>>(plane, bits, d, k, C, accumulate, pitch, ppitch, pstride,
-                                                         h->stream_mask, list, count);
+        dim3 gh(lt_div_up(d.bv_h, CROSSH_ROWS), n, plane1 ? 2 : 1);
+        k_cross_h<<<gh, CROSSH_WARPS * 32, smem, st>>>(plane, plane1, bits, d, k, C, k1, C1, accumulate, pitch0, pitch1, ppitch,
+                                                         pstride, h->stream_mask, list, count);
         LT_LAUNCH_CHECK();
-    } else {
+        return 0;
+    }
+    if (plane1) {        // mixed: one plane at a time
+        int rc = launch_cross_h(h, plane, bits, k, C, accumulate, n, list, count, st);
+        if (rc) return rc;
+        return launch_cross_h(h, plane1, bits, k1, C1, 1, n, list, count, st);
+    }
+    {
         int wpad = (d.bv_w + 32) & ~31;
         size_t smem = (size_t)ROWK_WARPS * 2 * wpad * sizeof(uint32_t);
         int rc = lt_ensure_smem((const void*)k_cross_h_wide, smem);
@@ -859,14 +885,19 @@ static int launch_cross_h(lt_handle* h, const uint32_t* plane, uint32_t* bits, i
 // pad_rows_zero: the pad rows of `plane` hold 0 (top-hat planes), i.e. they ARE the filter's BORDER_CONSTANT border and
 // the row-padded fast path may read them; the raw planes carry the erosion pad 0xFFFF there and must be bounds-checked.
 static int launch_cross_v(lt_handle* h, const uint32_t* plane, uint32_t* bits, int k, int C, int n,
-                          const int* list, const int* count, cudaStream_t st, bool pad_rows_zero) {
+                          const int* list, const int* count, cudaStream_t st, bool pad_rows_zero, const uint32_t* plane1 = nullptr,
+                          int k1 = 0, int C1 = 0) {
     const LtDims& d = h->d;
     const int ppitch = d.pp;
     const size_t pstride = h->stream_pad;
-    dim3 gv(d.p2 / 32, lt_div_up(d.bv_h, CV_BAND), n);
-    const bool packed = k <= 127 && C >= 0 && k * 255 + C * k + 1 < 32768;
-    const bool rowpad = pad_rows_zero && k + CV_CHUNK <= LT_HALO_Y;
-#define LT_CROSS_V(PK, RP) k_cross_v<PK, RP><<<gv, 32, 0, st>>>(plane, bits, d, k, C, ppitch, pstride, h->stream_mask, list, count)
+    const bool packed = cross_packed(k, C), rowpad = pad_rows_zero && k + CV_CHUNK <= LT_HALO_Y;
+    if (plane1 && (cross_packed(k1, C1) != packed || (pad_rows_zero && k1 + CV_CHUNK <= LT_HALO_Y) != rowpad)) {
+        int rc = launch_cross_v(h, plane, bits, k, C, n, list, count, st, pad_rows_zero);     // different kernel variants
+        if (rc) return rc;
+        return launch_cross_v(h, plane1, bits, k1, C1, n, list, count, st, pad_rows_zero);
+    }
+    dim3 gv(d.p2 / 32, lt_div_up(d.bv_h, CV_BAND), plane1 ? 2 * n : n);
+#define LT_CROSS_V(PK, RP) k_cross_v<PK, RP><<<gv, 32, 0, st>>>(plane, plane1, bits, d, k, C, k1, C1, n, ppitch, pstride, h->stream_mask, list, count)
     if (packed && rowpad) LT_CROSS_V(true, true);
     else if (packed) LT_CROSS_V(true, false);
     else if (rowpad) LT_CROSS_V(false, true);
@@ -931,11 +962,9 @@ int lt_launch_filter(lt_handle* h, int n, const LtAttemptParams& p, const int* l
             LT_CUDA(cudaMemsetAsync(h->merged, 0, (size_t)n * h->stream_mask * sizeof(uint32_t), st));
             LT_CUDA(cudaEventRecord(h->ev_fork, st));
             LT_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-            if ((rc = launch_cross_h(h, h->topR, h->merged, p.ksize_r, p.C_r, 1, n, list, count, h->side))) return rc;
-            if ((rc = launch_cross_h(h, h->topB, h->merged, p.ksize_b, p.C_b, 1, n, list, count, h->side))) return rc;
+            if ((rc = launch_cross_h(h, h->topR, h->merged, p.ksize_r, p.C_r, 1, n, list, count, h->side, h->topB, p.ksize_b, p.C_b))) return rc;
             LT_CUDA(cudaEventRecord(h->ev_join, h->side));
-            if ((rc = launch_cross_v(h, h->topR, h->merged, p.ksize_r, p.C_r, n, list, count, st, true))) return rc;
-            if ((rc = launch_cross_v(h, h->topB, h->merged, p.ksize_b, p.C_b, n, list, count, st, true))) return rc;
+            if ((rc = launch_cross_v(h, h->topR, h->merged, p.ksize_r, p.C_r, n, list, count, st, true, h->topB, p.ksize_b, p.C_b))) return rc;
             LT_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
             lt_prof_mark(h, ST_CROSS_B, st);
         } else {

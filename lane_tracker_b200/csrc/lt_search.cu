@@ -99,30 +99,68 @@ struct SearchShared {
     int ry[2][2], rn[2][2], rsx[2][2];
 };
 
-// windowed column counts S[i] (np.convolve(ones(ww), colsum), 'full') for i in [a, b) into Sbuf
-__device__ void window_sums(const uint32_t* __restrict__ mask, const LtDims& d, int r0, int r1, int c0, int nc,
-                            int ww, int a, int b, int* Sbuf) {
-    for (int i = a + threadIdx.x; i < b; i += blockDim.x) {
-        int xa = c0 + max(0, i - ww + 1), xb = c0 + min(i, nc - 1);
-        int s = 0;
-        if (xa <= xb)
-            for (int y = r0; y < r1; ++y) s += row_bits(mask + (size_t)y * d.mwords, xa, xb, nullptr);
-        Sbuf[i - a] = s;
+// Column histogram of mask rows [r0, r1) for the 32 columns of mask word `w`, written to out[0..31] (int):
+// the rows are added bit-sliced (six carry-save bit planes hold up to 63 rows, then the planes are flushed).
+__device__ void hist_word(const uint32_t* __restrict__ mask, int mwords, int r0, int r1, int w, int* __restrict__ out) {
+    int cnt[32];
+#pragma unroll
+    for (int b = 0; b < 32; ++b) cnt[b] = 0;
+    for (int g0 = r0; g0 < r1; g0 += 63) {
+        uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0;
+        const int g1 = min(g0 + 63, r1);
+        for (int y = g0; y < g1; ++y) {
+            uint32_t c = __ldg(&mask[(size_t)y * mwords + w]), t;
+            t = p0 & c; p0 ^= c; c = t;
+            t = p1 & c; p1 ^= c; c = t;
+            t = p2 & c; p2 ^= c; c = t;
+            t = p3 & c; p3 ^= c; c = t;
+            t = p4 & c; p4 ^= c; c = t;
+            p5 ^= c;
+        }
+#pragma unroll
+        for (int b = 0; b < 32; ++b)
+            cnt[b] += (int)(((p0 >> b) & 1u) | (((p1 >> b) & 1u) << 1) | (((p2 >> b) & 1u) << 2) | (((p3 >> b) & 1u) << 3) |
+                            (((p4 >> b) & 1u) << 4) | (((p5 >> b) & 1u) << 5));
     }
+#pragma unroll
+    for (int b = 0; b < 32; ++b) out[b] = cnt[b];
 }
 
-// max of Sbuf[0..n) and first/last index attaining it -> sh.s_max/s_first/s_last
-__device__ void block_argmax(const int* Sbuf, int n, SearchShared& sh) {
-    if (threadIdx.x == 0) { sh.s_max = -1; sh.s_first = 0x7FFFFFFF; sh.s_last = -1; }
-    __syncthreads();
-    int m = -1;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) m = max(m, Sbuf[i]);
-    if (m >= 0) atomicMax(&sh.s_max, m);
-    __syncthreads();
-    int gm = sh.s_max;
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-        if (Sbuf[i] == gm) { atomicMin(&sh.s_first, i); atomicMax(&sh.s_last, i); }
-    __syncthreads();
+// In-place: P[0] = 0, P[x + 1] = cnt[0] + ... + cnt[x] for the counts stored at P[1..W]; one warp.
+__device__ void warp_prefix_inplace(int* P, int W, int lane) {
+    const int per = (W + 31) / 32, b = min(lane * per, W), e = min(b + per, W);
+    int s = 0;
+    for (int x = b; x < e; ++x) s += P[1 + x];
+    int inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    int run = inc - s;
+    for (int x = b; x < e; ++x) { run += P[1 + x]; P[1 + x] = run; }
+    if (lane == 0) P[0] = 0;
+    __syncwarp();
+}
+
+// Windowed column counts (np.convolve(ones(ww), colsum) 'full') of the columns [c0, c0 + nc) from the prefix sums P:
+//   S[i] = sum col[max(0, i - ww + 1) .. min(i, nc - 1)],  col[j] = count of column c0 + j
+__device__ __forceinline__ int window_sum(const int* P, int c0, int nc, int ww, int i) {
+    const int a = max(0, i - ww + 1), b = min(i, nc - 1);
+    return a <= b ? P[c0 + b + 1] - P[c0 + a] : 0;
+}
+
+// max of S[sa..sb) and the first / last index (relative to sa) attaining it; one warp, result uniform over the lanes
+__device__ void warp_argmax(const int* P, int c0, int nc, int ww, int sa, int sb, int lane, int& smax, int& sfirst, int& slast) {
+    int m = -1, f = 0x7FFFFFFF, l = -1;
+    for (int i = sa + lane; i < sb; i += 32) {
+        const int v = window_sum(P, c0, nc, ww, i);
+        if (v > m) { m = v; f = i - sa; l = i - sa; }
+        else if (v == m) l = i - sa;
+    }
+    smax = __reduce_max_sync(0xFFFFFFFFu, m);
+    sfirst = __reduce_min_sync(0xFFFFFFFFu, m == smax ? f : 0x7FFFFFFF);
+    slast = __reduce_max_sync(0xFFFFFFFFu, m == smax ? l : -1);
 }
 
 // Solve the 3x3 normal equations (Gaussian elimination, partial pivoting).
@@ -255,7 +293,7 @@ __device__ int poly_points(const double* cf, double partial, int W, int H, int* 
 
 __global__ void __launch_bounds__(SEARCH_THREADS)
 k_search(LtDims d, LtAttemptParams p, LtSearchArgs a, const LtDevState* __restrict__ state, int n_reset, lt_validity V,
-         size_t bits_stride, const int* __restrict__ list, const int* __restrict__ count) {
+         size_t bits_stride, const int* __restrict__ list, const int* __restrict__ count, int lev_chunk) {
     int slot = blockIdx.x;
     if (count != nullptr && slot >= *count) return;
     const int s = list ? list[slot] : slot;
@@ -293,84 +331,110 @@ k_search(LtDims d, LtAttemptParams p, LtSearchArgs a, const LtDevState* __restri
 
     if (mode == 1) {
         // ------------------------------------------------------ sliding window search
+        // Column histograms of every level are built by the whole CTA (bit-sliced, one task per level x mask word) and
+        // turned into prefix sums; the walk itself -- sequential by nature: every level's search range depends on the
+        // centroids found below it -- then needs two prefix-sum reads per candidate position and is done by warp 0
+        // alone with shuffle reductions, without any CTA barrier.
         const int ww = p.window_width, wh = p.window_height, hw = ww / 2;
         const int Hh = H - p.ignore_bottom;
         const int cxi = W / 2;
         const int y0 = (int)mul64(sub64(1.0, p.start_slice), (double)Hh);
         const int nlev = min((int)__ddiv_rn(mul64(p.partial, (double)Hh), (double)wh), LT_MAX_LEVELS);
-        // walk state lives in registers of thread 0 (the other threads only evaluate window sums)
+        const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+        const int PW = W + 1;                                   // prefix-sum row: P[0..W]
+        int* Pbuf = Sbuf + (W + 64);                            // [levels_per_chunk][PW]
+        // walk state: replicated in the registers of every lane of warp 0 (all lanes compute the same values)
         int c[2] = {0, 0}, miss[2] = {0, 0}, rmin[2] = {-p.search_range, -p.search_range};
         int rmax[2] = {p.search_range, p.search_range}, ndiff[2] = {0, 0}, lastdiff[2] = {0, 0};
-        for (int side = 0; side < 2; ++side) {
-            int lo0 = side == 0 ? p.ignore_sides : cxi, hi0 = side == 0 ? cxi : W - p.ignore_sides;
-            int r0, r1, c0, c1;
+        int nroi[2] = {0, 0}, ncent[2] = {0, 0};
+        {   // ---- level 0: one histogram of rows [y0, Hh) serves both sides
+            int r0, r1;
             pyslice(y0, Hh, H, r0, r1);
-            pyslice(lo0, hi0, W, c0, c1);
-            int nc = c1 - c0, nS = nc > 0 ? nc + ww - 1 : 0;
-            window_sums(mask, d, r0, r1, c0, nc, ww, 0, nS, Sbuf);
+            for (int w = tid; w < d.mwords; w += blockDim.x) hist_word(mask, d.mwords, r0, r1, w, Pbuf + 1 + w * 32);
             __syncthreads();
-            block_argmax(Sbuf, nS, sh);
-            if (tid == 0) {
-                if (nS > 0 && sh.s_max > 0) {
-                    c[side] = (sh.s_first + sh.s_last) / 2 - hw + lo0;
-                    Roi r; int ra = Hh - wh;
-                    pyslice(ra, Hh, H, r.r0, r.r1);
-                    pyslice(c[side] - hw, c[side] + hw, W, r.c0, r.c1);
-                    r.xoff = (c[side] - hw) - r.c0;
-                    rois[side][sh.nroi[side]++] = r;
-                } else {
-                    c[side] = (int)mul64((double)W, side == 0 ? 0.4 : 0.6);
+            if (warp == 0) {
+                warp_prefix_inplace(Pbuf, W, lane);
+                for (int side = 0; side < 2; ++side) {
+                    const int lo0 = side == 0 ? p.ignore_sides : cxi, hi0 = side == 0 ? cxi : W - p.ignore_sides;
+                    int c0, c1;
+                    pyslice(lo0, hi0, W, c0, c1);
+                    const int nc = c1 - c0, nS = nc > 0 ? nc + ww - 1 : 0;
+                    int smax, sfirst, slast;
+                    warp_argmax(Pbuf, c0, nc, ww, 0, nS, lane, smax, sfirst, slast);
+                    if (nS > 0 && smax > 0) {
+                        c[side] = (sfirst + slast) / 2 - hw + lo0;
+                        Roi r; const int ra = Hh - wh;
+                        pyslice(ra, Hh, H, r.r0, r.r1);
+                        pyslice(c[side] - hw, c[side] + hw, W, r.c0, r.c1);
+                        r.xoff = (c[side] - hw) - r.c0;
+                        if (lane == 0) rois[side][nroi[side]] = r;
+                        nroi[side]++;
+                    } else {
+                        c[side] = (int)mul64((double)W, side == 0 ? 0.4 : 0.6);
+                    }
+                    if (lane == 0) cents[side][0] = c[side];
+                    ncent[side] = 1;
                 }
-                cents[side][0] = c[side];
-                sh.ncent[side] = 1;
             }
             __syncthreads();
         }
         const int nS = W + ww - 1;
-        for (int level = 1; level < nlev; ++level) {
-            const int ra = Hh - (1 + level) * wh, rb = Hh - level * wh;
-            int r0, r1;
-            pyslice(ra, rb, H, r0, r1);
-            for (int side = 0; side < 2; ++side) {
-                // broadcast thread 0's walk state for this side
-                if (tid == 0) { scratch[0] = c[side]; scratch[1] = rmin[side]; scratch[2] = rmax[side]; scratch[3] = miss[side]; }
-                __syncthreads();
-                const int cc = scratch[0], mn = scratch[1], mx = scratch[2], ms = scratch[3];
-                __syncthreads();
-                if (ms >= p.no_success_limit) continue;
-                const int lo = max(cc + mn + hw, 0), hi = min(cc + mx + hw, W);
-                int sa, sb;
-                pyslice(lo, hi, nS, sa, sb);
-                window_sums(mask, d, r0, r1, 0, W, ww, sa, sb, Sbuf);
-                __syncthreads();
-                block_argmax(Sbuf, sb - sa, sh);
-                if (tid == 0) {
-                    const int o = 1 - side;
-                    if (sb > sa && sh.s_max > 0) {
-                        int mc = (sh.s_first + sh.s_last + 1) / 2;            // ceil of the midpoint
-                        int prev = cents[side][sh.ncent[side] - 1];
-                        c[side] = mc + lo - hw;
-                        cents[side][sh.ncent[side]++] = c[side];
-                        lastdiff[side] = c[side] - prev;
-                        ndiff[side]++;
-                        miss[side] = 0;
-                        Roi r;
-                        r.r0 = r0; r.r1 = r1;
-                        pyslice(c[side] - hw, c[side] + hw, W, r.c0, r.c1);
-                        r.xoff = (c[side] - hw) - r.c0;
-                        if (sh.nroi[side] < LT_MAX_LEVELS) rois[side][sh.nroi[side]++] = r;
-                        int dd = (int)mul64(p.mu, (double)lastdiff[side]);
-                        rmin[side] += dd; rmax[side] += dd;
-                    } else {
-                        if (ndiff[o] > 0 && miss[o] == 0) c[side] += lastdiff[o];
-                        cents[side][sh.ncent[side]++] = c[side];
-                        miss[side]++;
-                        if (miss[side] >= p.no_success_limit) sh.ncent[side] = max(sh.ncent[side] - p.no_success_limit, 0);
+        for (int l0 = 1; l0 < nlev; l0 += lev_chunk) {
+            const int nl = min(lev_chunk, nlev - l0);
+            // histograms of the chunk's levels: task = (level, mask word)
+            for (int t = tid; t < nl * d.mwords; t += blockDim.x) {
+                const int lv = t / d.mwords, w = t - lv * d.mwords, level = l0 + lv;
+                int r0, r1;
+                pyslice(Hh - (1 + level) * wh, Hh - level * wh, H, r0, r1);
+                hist_word(mask, d.mwords, r0, r1, w, Pbuf + (size_t)lv * PW + 1 + w * 32);
+            }
+            __syncthreads();
+            for (int lv = warp; lv < nl; lv += nwarp) warp_prefix_inplace(Pbuf + (size_t)lv * PW, W, lane);
+            __syncthreads();
+            if (warp == 0) {
+                for (int lv = 0; lv < nl; ++lv) {
+                    const int level = l0 + lv;
+                    const int* P = Pbuf + (size_t)lv * PW;
+                    int r0, r1;
+                    pyslice(Hh - (1 + level) * wh, Hh - level * wh, H, r0, r1);
+                    for (int side = 0; side < 2; ++side) {
+                        if (miss[side] >= p.no_success_limit) continue;
+                        const int lo = max(c[side] + rmin[side] + hw, 0), hi = min(c[side] + rmax[side] + hw, W);
+                        int sa, sb;
+                        pyslice(lo, hi, nS, sa, sb);
+                        int smax, sfirst, slast;
+                        warp_argmax(P, 0, W, ww, sa, sb, lane, smax, sfirst, slast);
+                        const int o = 1 - side;
+                        if (sb > sa && smax > 0) {
+                            const int mc = (sfirst + slast + 1) / 2;            // ceil of the midpoint
+                            const int prev = c[side];                           // == cents[side][ncent - 1]
+                            c[side] = mc + lo - hw;
+                            if (lane == 0) cents[side][ncent[side]] = c[side];
+                            ncent[side]++;
+                            lastdiff[side] = c[side] - prev;
+                            ndiff[side]++;
+                            miss[side] = 0;
+                            Roi r;
+                            r.r0 = r0; r.r1 = r1;
+                            pyslice(c[side] - hw, c[side] + hw, W, r.c0, r.c1);
+                            r.xoff = (c[side] - hw) - r.c0;
+                            if (nroi[side] < LT_MAX_LEVELS) { if (lane == 0) rois[side][nroi[side]] = r; nroi[side]++; }
+                            const int dd = (int)mul64(p.mu, (double)lastdiff[side]);
+                            rmin[side] += dd; rmax[side] += dd;
+                        } else {
+                            if (ndiff[o] > 0 && miss[o] == 0) c[side] += lastdiff[o];
+                            if (lane == 0) cents[side][ncent[side]] = c[side];
+                            ncent[side]++;
+                            miss[side]++;
+                            if (miss[side] >= p.no_success_limit) ncent[side] = max(ncent[side] - p.no_success_limit, 0);
+                        }
                     }
                 }
-                __syncthreads();
             }
+            __syncthreads();
         }
+        if (tid == 0) { sh.nroi[0] = nroi[0]; sh.nroi[1] = nroi[1]; sh.ncent[0] = ncent[0]; sh.ncent[1] = ncent[1]; }
+        __syncthreads();
         // expand the ROI lists into per-row windows in visiting order
         if (tid < 2) {
             int side = tid, v = 0;
@@ -519,10 +583,14 @@ static size_t search_smem(const LtDims& d) { return (size_t)(10 * d.bv_h + d.bv_
 
 int lt_launch_search(lt_handle* h, int n, const LtAttemptParams& p, const LtSearchArgs& a, const int* list,
                      const int* count, cudaStream_t st) {
-    size_t smem = search_smem(h->d);
-    { int rc = lt_ensure_smem((const void*)k_search, smem); if (rc) return rc; }
     if (p.window_width < 1 || p.window_height < 1) { lt_set_error("window size must be positive"); return -1; }
-    k_search<<<n, SEARCH_THREADS, smem, st>>>(h->d, p, a, h->state, h->cfg.n_reset, h->val, h->stream_mask, list, count);
+    // + prefix-sum rows of the sliding-window levels: as many levels per chunk as fit next to the per-row tables
+    const size_t base = search_smem(h->d), per_level = (size_t)(h->d.bv_w + 1) * sizeof(int), budget = 200 * 1024;
+    int lev_chunk = base + per_level < budget ? (int)((budget - base) / per_level) : 1;
+    lev_chunk = lev_chunk < 1 ? 1 : (lev_chunk > LT_MAX_LEVELS ? LT_MAX_LEVELS : lev_chunk);
+    const size_t smem = base + (size_t)lev_chunk * per_level;
+    { int rc = lt_ensure_smem((const void*)k_search, smem); if (rc) return rc; }
+    k_search<<<n, SEARCH_THREADS, smem, st>>>(h->d, p, a, h->state, h->cfg.n_reset, h->val, h->stream_mask, list, count, lev_chunk);
     LT_LAUNCH_CHECK();
     return 0;
 }
