@@ -648,26 +648,25 @@ k_box_h(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plane1
     }
 }
 
+constexpr int BOXV_BAND = 64;        // rows per CTA (two 32-row groups)
+
 __global__ void __launch_bounds__(32)
 k_box_v(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plane1, const uint32_t* __restrict__ hs0,
         const uint32_t* __restrict__ hs1, uint32_t* __restrict__ bits_all, LtDims d, int half0, int half1, int c0, int c1,
-        int band_rows, int ppitch, size_t plane_stride, size_t hs_stride, size_t bits_stride,
+        int ppitch, size_t plane_stride, size_t hs_stride, size_t bits_stride,
         const int* __restrict__ list, const int* __restrict__ count, int nslots) {
-    // one thread per packed column; the thresholds of the R and the Lab-b plane are OR-ed in registers and the mask
-    // word is written once (lane_tracker.py:217-218 + the OR at :233)
+    // one thread per packed column; the thresholds of the R and the Lab-b plane are OR-ed in registers (lane r keeps
+    // the mask words of rows yb0 + r and yb0 + 32 + r) and every mask word is written exactly once
+    // (lane_tracker.py:217-218 + the OR at :233)
     const int nsl = count ? *count : nslots;
     for (int slot = blockIdx.z; slot < nsl; slot += gridDim.z) {
         const int s = list ? list[slot] : slot;
         const int lane = threadIdx.x;
         const int x = blockIdx.x * 32 + lane;
-        const int yb0 = blockIdx.y * band_rows, yb1 = min(yb0 + band_rows, d.bv_h);
+        const int yb0 = blockIdx.y * BOXV_BAND, yb1 = min(yb0 + BOXV_BAND, d.bv_h);
         uint32_t* bits = bits_all + (size_t)s * bits_stride;
         const bool hi_ok = x + d.p2 < d.bv_w;
-        for (int y = yb0 + lane; y < yb1; y += 32) {                    // clear, then OR the two planes in
-            uint32_t* brow = bits + (size_t)y * d.mwords;
-            brow[blockIdx.x] = 0u; brow[blockIdx.x + (d.p2 >> 5)] = 0u;
-        }
-        __syncwarp();
+        uint32_t kl[2] = {0u, 0u}, kh[2] = {0u, 0u};
         for (int pl = 0; pl < 2; ++pl) {
             const uint32_t* P = (pl ? plane1 : plane0) + (size_t)s * plane_stride + x;
             const uint32_t* Hs = (pl ? hs1 : hs0) + (size_t)s * hs_stride + x;
@@ -682,16 +681,21 @@ k_box_v(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plane1
                 bool pl_ = ((int)(p & 0xFFFFu) - ml) > c;
                 bool ph = hi_ok && (((int)(p >> 16) - mh) > c);
                 uint32_t bl = __ballot_sync(0xFFFFFFFFu, pl_), bh = __ballot_sync(0xFFFFFFFFu, ph);
-                if (lane == 0) {
-                    uint32_t* brow = bits + (size_t)y * d.mwords;
-                    brow[blockIdx.x] |= bl;
-                    brow[blockIdx.x + (d.p2 >> 5)] |= bh;
-                }
+                const int g = (y - yb0) >> 5;
+                if (lane == ((y - yb0) & 31)) { kl[g] |= bl; kh[g] |= bh; }
                 uint32_t a = ldh(y + half + 1), b = ldh(y - half);
                 Sl += (a & 0xFFFFu) - (b & 0xFFFFu);
                 Sh += (a >> 16) - (b >> 16);
             }
-            __syncwarp();
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int y = yb0 + 32 * g + lane;
+            if (y < yb1) {
+                uint32_t* brow = bits + (size_t)y * d.mwords;
+                brow[blockIdx.x] = kl[g];
+                brow[blockIdx.x + (d.p2 >> 5)] = kh[g];
+            }
         }
     }
 }
@@ -928,10 +932,9 @@ static int launch_box_pair(lt_handle* h, int block_r, int c_r, int block_b, int 
     k_box_h<<<gh, ROWK_WARPS * 32, smem, st>>>(h->planeR, h->planeB, h->topR, h->topB, d, block_r / 2, block_b / 2, d.pp,
                                                h->stream_pad, h->stream_pad, list, count, n);
     LT_LAUNCH_CHECK();
-    int band_rows = 64;
-    dim3 gv(d.p2 / 32, lt_div_up(d.bv_h, band_rows), zs);
+    dim3 gv(d.p2 / 32, lt_div_up(d.bv_h, BOXV_BAND), zs);
     k_box_v<<<gv, 32, 0, st>>>(h->planeR, h->planeB, h->topR, h->topB, h->merged, d, block_r / 2, block_b / 2, c_r, c_b,
-                               band_rows, d.pp, h->stream_pad, h->stream_pad, h->stream_mask, list, count, n);
+                               d.pp, h->stream_pad, h->stream_pad, h->stream_mask, list, count, n);
     LT_LAUNCH_CHECK();
     return 0;
 }

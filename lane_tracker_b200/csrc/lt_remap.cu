@@ -329,7 +329,7 @@ __device__ __forceinline__ void store_padded(uint32_t* __restrict__ planeR, uint
 // group; the Lab look-up tables live in shared memory in a form that needs two 3-input adds instead of six multiplies:
 //   YZ[c][v] = { coefY[c] * g[v] (+ 2048 for c = 0),  coefZ[c] * g[v] (+ 2048) }      (lane_tracker.py:208)
 #ifndef LT_WARP_NSW
-#define LT_WARP_NSW 8
+#define LT_WARP_NSW 16
 #endif
 constexpr int NSW = LT_WARP_NSW;       // streams per thread
 
