@@ -159,7 +159,9 @@ static int alloc_front_set(lt_handle* h, int k) {
     if (f.mask) return 0;
     const LtDims& d = h->d;
     const size_t S = h->S;
-    int rc = dev_alloc(&f.und_roi, S * (size_t)(d.roi1 - d.roi0) * d.img_w);
+    const size_t und_words = (size_t)lt_div_up((int)S, LT_UND_GROUP) * lt_und_group_words(d);
+    int rc = dev_alloc(&f.und_roi, und_words);
+    if (!rc) cudaMemset(f.und_roi, 0, und_words * sizeof(uint32_t));      // the zero border is never written again
     // padded planes: + one row of slack (the last tile of a row block stages a few entries past the row end)
     const size_t n = S * h->stream_pad + d.pp;
     for (int i = 0; i < 6 && !rc; ++i) {

@@ -33,6 +33,12 @@ struct LtDims {
 constexpr int LT_HALO_X = 32;     // multiple of 4 (16-byte staging) >= 28
 constexpr int LT_HALO_Y = 48;     // >= 27 + MORPH_RB - 1; the row-padded fast path of k_cross_v needs k + 8
 
+// Undistorted ROI buffer (lt_remap.cu): groups of LT_UND_GROUP streams, stream-minor, zero-bordered; words per group.
+constexpr int LT_UND_GROUP = 16;
+static inline size_t lt_und_group_words(const LtDims& d) {
+    return ((size_t)(d.roi1 - d.roi0 + 3) * (d.img_w + 1) + 2) * LT_UND_GROUP;
+}
+
 // Per-stream tracking state on the device (lane_tracker.py:139-176).
 struct LtDevState {
     lt_state s;
@@ -57,7 +63,7 @@ struct LtAttemptOut {
 // (search, second attempt, state update, overlay) consumes.  A handle owns two sets so that the front half of batch
 // k+1 can run on one CUDA stream while the back half of batch k runs on another (lt_process_front / lt_process_back).
 struct LtFrontSet {
-    uchar4* und_roi;
+    uint32_t* und_roi;
     uint32_t* pad_alloc[6];
     uint32_t* merged; uint32_t* mask;
 };
@@ -82,7 +88,7 @@ struct lt_handle {
     uint2* lab_yz;               // [3][256] Lab partial sums per channel value (lt_remap.cu)
     int2* und_desc;              // [roi rows][img_w] tap descriptors of the undistort (byte offset, fx | fy << 5 | flags << 10)
     // per-stream buffers
-    uchar4* und_roi;             // [S][roi rows][img_w]
+    uint32_t* und_roi;           // [ceil(S / 16)][lt_und_group_words]: RGBX, stream-minor, zero-bordered (lt_remap.cu)
     uint32_t* planeR; uint32_t* planeB;     // padded [S][bv_h + 2*LT_HALO_Y][pp]; lanes beyond the image / halo: 0xFFFF
     uint32_t* tmpR;   uint32_t* tmpB;       // padded eroded planes; lanes beyond the image / halo: 0
     uint32_t* topR;   uint32_t* topB;       // padded top-hat planes / box row sums; halo and pad rows: 0

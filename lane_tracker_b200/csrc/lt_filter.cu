@@ -367,18 +367,23 @@ __device__ __forceinline__ void warp_row_prefix(const uint32_t* __restrict__ pro
     __syncwarp();
 }
 
-// Horizontal half of the cross threshold.  A CTA stages 32 plane rows (zero-padded halo of k columns, the two
-// strips stitched) into shared memory as (lo, hi) byte pairs; thread (row = lane, segment = warp) then walks its
-// column segment with running window sums L, R in packed u16x2 registers and emits finished 32-column mask
-// words directly.  Rows sit in different banks (odd half-word pitch), so the walk is conflict-free.
+// Horizontal half of the cross threshold.  A CTA copies 32 rows of a padded plane into shared memory as they are
+// (pair-packed 32-bit entries, 4-byte cp.async: the whole tile is in flight at once and no register is touched), then
+// builds the k halo entries either side of every row from the row itself -- the two strips of a pair plane are
+// neighbours in the image: column -j = {0, entry[p2 - j].lo}, column p2 + j = {entry[j].hi, 0} -- and zeroes the high
+// lanes that lie beyond the image.  Thread (row = lane, segment = warp) then walks its column segment with running
+// window sums L, R in packed u16x2 registers and emits finished 32-column mask words from two shift registers.
+// The row pitch is odd, so the 32 rows of a warp sit in 32 different banks and the walk is conflict-free.
 constexpr int CROSSH_ROWS = 32;
 #ifndef LT_CROSSH_WARPS
 #define LT_CROSSH_WARPS 8
 #endif
 constexpr int CROSSH_WARPS = LT_CROSSH_WARPS;
+static_assert(CROSSH_ROWS <= LT_HALO_Y, "a tile may run into the pad rows below the plane");
 
-__device__ __forceinline__ uint32_t unpack_pair(uint32_t v16) {            // (hi<<8 | lo) -> hi<<16 | lo
-    return __byte_perm(v16, 0, 0x4140);
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc) : "memory");
 }
 
 // One launch thresholds up to two planes (blockIdx.z): plane 0 with (k0, C0), plane 1 with (k1, C1).
@@ -391,89 +396,59 @@ k_cross_h(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plan
     int s = list ? list[slot] : slot;
     const uint32_t* __restrict__ plane_all = blockIdx.z ? plane1 : plane0;
     const int k = blockIdx.z ? k1 : k0, C = blockIdx.z ? C1 : C0, pitch = blockIdx.z ? pitch1 : pitch0;
-    extern __shared__ uint32_t smem[];
-    unsigned short* tile = reinterpret_cast<unsigned short*>(smem);     // [32][pitch], entry i <-> packed column i - k
+    extern __shared__ uint32_t tile[];                                   // [32][pitch], entry i <-> packed column i - k
     const int y0 = blockIdx.x * CROSSH_ROWS;
-    const uint32_t* src = plane_all + (size_t)s * plane_stride;
-    const int ncol = d.p2 + 2 * k;
-    const int xint = d.bv_w - d.p2;
-    // packed column gx -> 16-bit (hi byte, lo byte) pair of one plane row; zero outside the image
-    auto fetch = [&](const uint32_t* __restrict__ row, int gx) -> uint32_t {
-        int off = gx, mode = 0;                                   // 0: both lanes, 1: hi <- entry.lo, 2: lo only, 3: lo <- entry.hi
-        if (gx < 0) { off = gx + d.p2; mode = 1; }
-        else if (gx >= d.p2) { off = gx - d.p2; mode = (gx < d.bv_w) ? 3 : 4; }
-        else if (gx >= xint) mode = 2;
-        if (mode == 4 || off < 0 || off >= d.p2) return 0u;
-        uint32_t e = __ldg(&row[off]);
-        if (mode == 0) return (e & 0xFFu) | ((e >> 8) & 0xFF00u);
-        if (mode == 1) return (e & 0xFFu) << 8;
-        if (mode == 2) return e & 0xFFu;
-        return (e >> 16) & 0xFFu;
-    };
-    const int xv = xint & ~3;                                    // [0, xv): both lanes real, 16-byte vector loads
+    const uint32_t* src = plane_all + (size_t)s * plane_stride + y0 * ppitch;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // rows below the plane are pad rows of the padded layout: every address is valid, their verdicts are dropped
+    for (int r = warp; r < CROSSH_ROWS; r += CROSSH_WARPS) {
+        const uint32_t* g = src + r * ppitch;
+        uint32_t* t = tile + r * pitch + k;
+        for (int x = lane; x < d.p2; x += 32) cp_async4(t + x, g + x);
+    }
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
     {
-        // each warp stages rows warp, warp+4, ...: one 16 B chunk of all its 8 rows in flight per lane
-        constexpr int RPW = CROSSH_ROWS / CROSSH_WARPS;
-        const int wq = threadIdx.x >> 5, ln = threadIdx.x & 31;
-        for (int g0 = ln * 4; g0 < xv; g0 += 128) {
-            uint4 v[RPW];
-#pragma unroll
-            for (int j = 0; j < RPW; ++j) {
-                const int y = y0 + wq + j * CROSSH_WARPS;
-                v[j] = (y < d.bv_h) ? __ldg(reinterpret_cast<const uint4*>(src + (size_t)y * ppitch + g0)) : make_uint4(0, 0, 0, 0);
-            }
-#pragma unroll
-            for (int j = 0; j < RPW; ++j) {
-                unsigned short* o = tile + (wq + j * CROSSH_WARPS) * pitch + k + g0;
-                o[0] = (unsigned short)__byte_perm(v[j].x, 0, 0x4420);
-                o[1] = (unsigned short)__byte_perm(v[j].y, 0, 0x4420);
-                o[2] = (unsigned short)__byte_perm(v[j].z, 0, 0x4420);
-                o[3] = (unsigned short)__byte_perm(v[j].w, 0, 0x4420);
-            }
-        }
-        // halo columns and the tail where the high strip leaves the image: generic path, all rows of the warp batched
-        const int nrest = k + (ncol - k - xv);
-        for (int j0 = ln; j0 < nrest; j0 += 32) {
-            const int i = j0 < k ? j0 : j0 + xv;
-            uint32_t v[RPW];
-#pragma unroll
-            for (int j = 0; j < RPW; ++j) {
-                const int y = y0 + wq + j * CROSSH_WARPS;
-                v[j] = (y < d.bv_h) ? fetch(src + (size_t)y * ppitch, i - k) : 0u;
-            }
-#pragma unroll
-            for (int j = 0; j < RPW; ++j) tile[(wq + j * CROSSH_WARPS) * pitch + i] = (unsigned short)v[j];
+        const int xint = d.bv_w - d.p2;                                  // high lanes of columns >= xint lie beyond the image
+        const int nfix = d.p2 - xint, per_row = 2 * k + 1 + nfix;
+        for (int e = threadIdx.x; e < CROSSH_ROWS * per_row; e += blockDim.x) {
+            const int r = e / per_row, j = e - r * per_row;
+            uint32_t* t = tile + r * pitch + k;
+            if (j < nfix) t[xint + j] &= 0xFFFFu;
+            else if (j < nfix + k) { const int q = j - nfix + 1; t[-q] = t[d.p2 - q] << 16; }          // column -q
+            else { const int q = j - nfix - k; t[d.p2 + q] = (q < xint ? t[q] >> 16 : 0u); }           // column p2 + q, q = 0..k
         }
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int y = y0 + lane;
     const int nw = d.p2 >> 5;                                            // words per strip
     const int w0 = (warp * nw) / CROSSH_WARPS, w1 = ((warp + 1) * nw) / CROSSH_WARPS;
     if (w0 >= w1) return;
-    const unsigned short* trow = tile + lane * pitch + k;                // trow[x] = packed column x
+    const uint32_t* trow = tile + lane * pitch + k;                      // trow[x] = packed column x
     const uint32_t kk = (uint32_t)k;
     const uint32_t bias = ((uint32_t)(C * k + 1)) * 0x00010001u;         // pass <=> k*p >= side + C*k + 1
     int x = w0 * 32;
     uint32_t L = bias, Rs = bias;                                        // the running sums carry the compare bias
-    for (int i = 1; i <= k; ++i) { L += unpack_pair(trow[x - i]); Rs += unpack_pair(trow[x + i]); }
-    uint32_t p = unpack_pair(trow[x]);
+    for (int i = 1; i <= k; ++i) { L += trow[x - i]; Rs += trow[x + i]; }
+    uint32_t p = trow[x];
     uint32_t* brow = bits_all + (size_t)s * bits_stride + (size_t)min(y, d.bv_h - 1) * d.mwords;
     for (int w = w0; w < w1; ++w) {
         uint32_t wl = 0, wh = 0;
-#pragma unroll 4
+#pragma unroll 8
         for (int b = 0; b < 32; ++b, ++x) {
             // lanes hold values < 2^15 (k <= 127): bit 15 of ((A | 0x8000) - B) is set iff A >= B, per lane
-            uint32_t T = p * kk + 0x80008000u;
-            uint32_t ok = (T - L) & (T - Rs);
-            wl = __funnelshift_r(wl, ok >> 15, 1);                       // shift the pass bit in from the top: after
-            wh = __funnelshift_r(wh, ok >> 31, 1);                       // 32 columns bit b belongs to column b
-            uint32_t pn = unpack_pair(trow[x + 1]);
-            L = L + p - unpack_pair(trow[x - k]);
-            Rs = Rs + unpack_pair(trow[x + k + 1]) - pn;
+            const uint32_t T = p * kk + 0x80008000u;
+            const uint32_t ok = (T - L) & (T - Rs);
+            wl = __funnelshift_l(ok * 0x10000u, wl, 1);                  // newest column in bit 0 (reversed below)
+            wh = __funnelshift_l(ok, wh, 1);
+            const uint32_t pn = trow[x + 1];
+            L = L + p - trow[x - k];
+            Rs = Rs + trow[x + k + 1] - pn;
             p = pn;
         }
         if (y < d.bv_h) {
+            wl = __brev(wl); wh = __brev(wh);
             // bits of columns >= bv_w in the high strip are forced to 0
             int hbase = (d.p2 + w * 32);
             uint32_t valid = hbase + 32 <= d.bv_w ? 0xFFFFFFFFu : (hbase >= d.bv_w ? 0u : ((1u << (d.bv_w - hbase)) - 1u));
@@ -523,20 +498,59 @@ k_cross_h_wide(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bi
 }
 
 // Vertical half: one thread per packed column walks a band of rows with running sums U, D (packed u16x2);
-// the plane rows each step needs are fetched CV_CHUNK steps ahead so that the loads stay in flight.
+// the plane rows each step needs are fetched CV_CHUNK steps ahead so that the loads stay in flight (32-bit row offsets
+// from one base pointer: the address arithmetic is IMAD / IMAD.WIDE on the FMA pipe, the walk itself is ALU-pipe bound).
 // PACKED: k*255 + C*k + 1 < 2^15, the compare is done on both lanes at once with a guard bit.
 // ROWPAD: k + CV_CHUNK <= LT_HALO_Y, every row the walk touches exists in the padded plane (pad rows are zero, which
 //         is the filter's border), so loads carry no bounds logic.
-// The pass bits of a row are gathered with one ballot per strip; lane (y mod 32) keeps the words of row y and every
-// 32 rows all lanes flush theirs with one RED.OR each (instead of a divergent single-lane store per row).
+// Every lane shifts the pass bits of its own column into two registers (one per strip); after 32 rows the warp holds
+// two 32x32 bit matrices column-major, transposes them with five shuffle stages each, and lane r flushes the two
+// mask words of row r with one RED.OR each -- no per-row ballot.
 constexpr int CV_CHUNK = 8;
-constexpr int CV_BAND = 128;        // rows per CTA (multiple of 32)
+#ifndef LT_CV_BAND
+#define LT_CV_BAND 288
+#endif
+constexpr int CV_BAND = LT_CV_BAND;  // rows per CTA (multiple of 32)
+static_assert(CV_BAND % 32 == 0 && CV_BAND % CV_CHUNK == 0 && 32 % CV_CHUNK == 0, "band geometry");
+
+// w[lane r] bit c  ->  w[lane c] bit r
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t w, int lane) {
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, w, j);
+        const bool up = (lane & j) != 0;
+        const uint32_t sh = up ? (o >> j) : (o << j);
+        const uint32_t keep = up ? ~m : m;
+        w = (w & keep) | (sh & ~keep);
+    }
+    return w;
+}
+
+// Each warp keeps the rows its walk needs in a shared-memory RING (one 128-byte slot per row, lane = column:
+// conflict-free, and a thread only ever reads what it fetched itself, so no barrier is needed).  Rows enter the ring
+// by 4-byte cp.async CV_PF chunks ahead of the walk: every plane row is fetched from L2/HBM once per band (instead of
+// three times, as p[y+k+1], p[y+1] and p[y-k]) and 8 * (CV_PF + 1) rows per warp are in flight without holding registers.
+#ifndef LT_CV_PF
+#define LT_CV_PF 4
+#endif
+constexpr int CV_PF = LT_CV_PF;      // prefetch distance in chunks
+
+__device__ __forceinline__ void cp_async4_zfill(void* smem_dst, const void* gsrc, bool valid) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(sa), "l"(gsrc), "r"(valid ? 4 : 0) : "memory");
+}
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+static int crossv_ring_rows(int k) {                  // rows y - k .. y + k + 1 of a chunk + the chunks in flight, whole chunks
+    return (2 * k + 1 + CV_CHUNK * (CV_PF + 1) + CV_CHUNK - 1) / CV_CHUNK * CV_CHUNK;
+}
 
 template <bool PACKED, bool ROWPAD>
 __global__ void __launch_bounds__(32)
 k_cross_v(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plane1, uint32_t* __restrict__ bits_all, LtDims d,
           int k0, int C0, int k1, int C1, int nslots, int ppitch, size_t plane_stride, size_t bits_stride,
-          const int* __restrict__ list, const int* __restrict__ count) {
+          const int* __restrict__ list, const int* __restrict__ count, int ring_rows) {
     // blockIdx.z = plane * nslots + stream slot (two planes in one launch when plane1 != nullptr)
     const int which = blockIdx.z >= nslots ? 1 : 0;
     int slot = blockIdx.z - which * nslots;
@@ -547,66 +561,102 @@ k_cross_v(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plan
     const int lane = threadIdx.x;
     const int x = blockIdx.x * 32 + lane;              // packed column; p2 is a multiple of 32
     const int yb0 = blockIdx.y * CV_BAND, yb1 = min(yb0 + CV_BAND, d.bv_h);
-    const char* P = reinterpret_cast<const char*>(plane_all + (size_t)s * plane_stride + x);
-    const ptrdiff_t pitchB = (ptrdiff_t)ppitch * 4;
+    const uint32_t* __restrict__ P = plane_all + (size_t)s * plane_stride + x;
     uint32_t* bits = bits_all + (size_t)s * bits_stride;
     const bool hi_ok = x + d.p2 < d.bv_w;
-    auto ld = [&](int r) -> uint32_t {
-        if (ROWPAD) return __ldg(reinterpret_cast<const uint32_t*>(P + r * pitchB));
-        return ((unsigned)r < (unsigned)d.bv_h) ? __ldg(reinterpret_cast<const uint32_t*>(P + r * pitchB)) : 0u;
+    extern __shared__ uint32_t ring[];                 // [ring_rows + CV_CHUNK][32]
+    // Ring geometry: ring_rows (R) is a multiple of CV_CHUNK, plane row r lives in slot (r - (yb0 + k + 1)) mod R, so the
+    // rows a chunk ADDS (y + k + 1) start at slot 0 and stay chunk-aligned: they never wrap inside a chunk.  The two other
+    // read pointers are not aligned; CV_CHUNK mirror slots behind the ring repeat slots 0 .. CV_CHUNK - 1 (fetched
+    // together with them), so reading `pointer + j` never needs a wrap test.
+    const int R = ring_rows;
+    uint32_t* const rl = ring + lane;
+    auto fetch = [&](int slot_row, int r) {            // plane row r -> ring slot (row offsets fit 32 bits)
+        if (ROWPAD) r = min(r, d.bv_h + LT_HALO_Y - 1);                             // (prefetch past the pad rows: never used)
+        const bool ok = ROWPAD || (unsigned)r < (unsigned)d.bv_h;
+        cp_async4_zfill(rl + slot_row * 32, P + (ok ? r * ppitch : 0), ok);
     };
+    auto fetch_chunk = [&](int slot_row, int r0) {     // the CV_CHUNK rows a chunk adds, slot_row is chunk-aligned
+#pragma unroll
+        for (int j = 0; j < CV_CHUNK; ++j) fetch(slot_row + j, r0 + j);
+        if (slot_row == 0) {
+#pragma unroll
+            for (int j = 0; j < CV_CHUNK; ++j) fetch(R + j, r0 + j);                 // mirror of slots 0 .. CV_CHUNK - 1
+        }
+    };
+    // prologue: rows yb0 - k .. yb0 + k go to slots R - 2k - 1 .. R - 1, then the new rows of the first CV_PF chunks
+    for (int i = 0; i <= 2 * k; ++i) fetch(R - 2 * k - 1 + i, yb0 - k + i);
+    int r_pf = 0;                                      // slot of the next chunk to fetch
+    int y_pf = yb0 + k + 1;                            // its first plane row
+#pragma unroll
+    for (int c = 0; c < CV_PF; ++c) {
+        fetch_chunk(r_pf, y_pf);
+        cp_async_commit();
+        r_pf += CV_CHUNK; if (r_pf >= R) r_pf -= R;
+        y_pf += CV_CHUNK;
+    }
     const int Ck = C * k;
     const uint32_t kk = (uint32_t)k, bias = (uint32_t)(Ck + 1) * 0x00010001u;
     // running sums carry the compare bias: pass <=> k*p >= U + C*k + 1 (and the same for D), per lane
-    uint32_t U = PACKED ? bias : 0u, D = U;
-    for (int i0 = 1; i0 <= k; i0 += CV_CHUNK) {  // initial window sums, CV_CHUNK rows per side in flight
-        uint32_t a[CV_CHUNK], b[CV_CHUNK];
-#pragma unroll
-        for (int j = 0; j < CV_CHUNK; ++j) {
-            bool ok = i0 + j <= k;
-            a[j] = ok ? ld(yb0 - i0 - j) : 0u;
-            b[j] = ok ? ld(yb0 + i0 + j) : 0u;
-        }
-#pragma unroll
-        for (int j = 0; j < CV_CHUNK; ++j) { U += a[j]; D += b[j]; }
-    }
-    uint32_t p = ld(yb0);
-    uint32_t keep_l = 0, keep_h = 0;
+    uint32_t U = PACKED ? bias : 0u, D = U, p = 0;
+    int r_new = 0, r_cur = R - k, r_old = R - 2 * k - 1;   // slots of rows y + k + 1, y + 1, y - k   (y = yc + j)
+    uint32_t wl = 0, wh = 0;                           // pass bits of this column, newest row in bit 0
     for (int yc = yb0; yc < yb1; yc += CV_CHUNK) {
-        uint32_t pc[CV_CHUNK], pu[CV_CHUNK], pd[CV_CHUNK];
-#pragma unroll
-        for (int j = 0; j < CV_CHUNK; ++j) { pc[j] = ld(yc + j + 1); pu[j] = ld(yc + j - k); pd[j] = ld(yc + j + k + 1); }
+        fetch_chunk(r_pf, y_pf);                       // (rows beyond the band are fetched and never used)
+        cp_async_commit();
+        r_pf += CV_CHUNK; if (r_pf >= R) r_pf -= R;
+        y_pf += CV_CHUNK;
+        cp_async_wait_group<CV_PF>();                  // the rows this chunk adds (and everything older) have landed
+        if (yc == yb0) {
+            // initial window sums from the ring: rows yb0 - k .. yb0 - 1 above, yb0 + 1 .. yb0 + k below
+            const uint32_t* f = rl + (R - 2 * k - 1) * 32;
+            for (int i = 0; i < k; ++i) { U += f[i * 32]; D += f[(k + 1 + i) * 32]; }
+            p = f[k * 32];
+        }
+        const uint32_t* const pn = rl + r_new * 32;
+        const uint32_t* const pcur = rl + r_cur * 32;
+        const uint32_t* const pold = rl + r_old * 32;
 #pragma unroll
         for (int j = 0; j < CV_CHUNK; ++j) {
-            bool pl, ph;
+            const uint32_t pc = pcur[j * 32], pu = pold[j * 32], pd = pn[j * 32];
             if (PACKED) {
                 // lanes hold values < 2^15: bit 15 of ((A | 0x8000) - B) is set iff A >= B, per lane
-                uint32_t T = p * kk + 0x80008000u;
-                uint32_t ok = (T - U) & (T - D);
-                pl = (ok & 0x8000u) != 0;
-                ph = hi_ok && ((int)ok < 0);
+                const uint32_t T = p * kk + 0x80008000u;
+                const uint32_t ok = (T - U) & (T - D);
+                wl = __funnelshift_l(ok * 0x10000u, wl, 1);        // bit 15 (IMAD.SHL on the FMA pipe) -> bit 0 of wl << 1
+                wh = __funnelshift_l(ok, wh, 1);                   // bit 31
             } else {
-                int tl = k * (int)(p & 0xFFFFu) - Ck, th = k * (int)(p >> 16) - Ck;
-                pl = ((int)(U & 0xFFFFu) < tl) && ((int)(D & 0xFFFFu) < tl);
-                ph = hi_ok && ((int)(U >> 16) < th) && ((int)(D >> 16) < th);
+                const int tl = k * (int)(p & 0xFFFFu) - Ck, th = k * (int)(p >> 16) - Ck;
+                const bool pl = ((int)(U & 0xFFFFu) < tl) && ((int)(D & 0xFFFFu) < tl);
+                const bool ph = ((int)(U >> 16) < th) && ((int)(D >> 16) < th);
+                wl = (wl << 1) | (pl ? 1u : 0u);
+                wh = (wh << 1) | (ph ? 1u : 0u);
             }
-            uint32_t bl = __ballot_sync(0xFFFFFFFFu, pl), bh = __ballot_sync(0xFFFFFFFFu, ph);
-            if (lane == ((yc + j) & 31)) { keep_l = bl; keep_h = bh; }
-            U = U + p - pu[j];                    // lanes stay in [0, 65535]: add first, then subtract
-            D = D + pd[j] - pc[j];
-            p = pc[j];
+            U = U + p - pu;                       // lanes stay in [0, 65535]: add first, then subtract
+            D = D + pd - pc;
+            p = pc;
         }
+        r_new += CV_CHUNK; if (r_new >= R) r_new -= R;
+        r_cur += CV_CHUNK; if (r_cur >= R) r_cur -= R;
+        r_old += CV_CHUNK; if (r_old >= R) r_old -= R;
         const int ynext = yc + CV_CHUNK;
-        if ((ynext & 31) == 0 || ynext >= yb1) {        // lane r holds row (ynext - 1 rounded down to 32) + r
-            const int y = ((ynext - 1) & ~31) + lane;
+        if ((ynext & 31) == 0 || ynext >= yb1) {
+            // rows [ybase, ynext) are in the low (ynext - ybase) bits, newest first: bit (ynext - 1 - y) <-> row y
+            const int ybase = (ynext - 1) & ~31;
+            const int sh = 32 - (ynext - ybase);                   // 0 for a full group
+            uint32_t ml = __brev(wl << sh), mh = hi_ok ? __brev(wh << sh) : 0u;      // bit r <-> row ybase + r
+            ml = warp_transpose32(ml, lane);                       // lane r: bit c <-> column blockIdx.x * 32 + c of row ybase + r
+            mh = warp_transpose32(mh, lane);
+            const int y = ybase + lane;
             if (y < yb1) {
                 uint32_t* brow = bits + (size_t)y * d.mwords;     // fire-and-forget RED.OR: no load to wait for
-                if (keep_l) atomicOr(&brow[blockIdx.x], keep_l);
-                if (keep_h) atomicOr(&brow[blockIdx.x + (d.p2 >> 5)], keep_h);
+                if (ml) atomicOr(&brow[blockIdx.x], ml);
+                if (mh) atomicOr(&brow[blockIdx.x + (d.p2 >> 5)], mh);
             }
-            keep_l = keep_h = 0;
+            wl = wh = 0;
         }
     }
+    cp_async_wait_all();
 }
 
 // ---------------------------------------------------------------------------
@@ -845,10 +895,9 @@ int lt_launch_plane_to_u8(lt_handle* h, const uint32_t* plane, int pitch, uint8_
 static bool cross_packed(int k, int C) { return k <= 127 && C >= 0 && k * 255 + C * k + 1 < 32768; }   // packed u16 lanes stay below 2^15
 
 static int crossh_pitch(const LtDims& d, int k) {
-    int pitch = d.p2 + 2 * k + 2;
-    while (((pitch >> 1) & 1) == 0 || (pitch & 1)) ++pitch;       // pitch = 2 * odd: rows land in distinct banks
-    return pitch;
+    return (d.p2 + 2 * k + 2) | 1;                                 // odd: the 32 rows of a warp land in distinct banks
 }
+constexpr size_t CROSSH_SMEM_MAX = 200 * 1024;
 
 // horizontal half of one plane, or of two planes in one launch (plane1 != nullptr; both must take the packed kernel)
 static int launch_cross_h(lt_handle* h, const uint32_t* plane, uint32_t* bits, int k, int C, int accumulate, int n,
@@ -857,9 +906,11 @@ static int launch_cross_h(lt_handle* h, const uint32_t* plane, uint32_t* bits, i
     const LtDims& d = h->d;
     const int ppitch = d.pp;
     const size_t pstride = h->stream_pad;
-    if (cross_packed(k, C) && (!plane1 || cross_packed(k1, C1))) {
+    const size_t tile0 = (size_t)CROSSH_ROWS * crossh_pitch(d, k) * sizeof(uint32_t);
+    const size_t tile1 = plane1 ? (size_t)CROSSH_ROWS * crossh_pitch(d, k1) * sizeof(uint32_t) : 0;
+    if (cross_packed(k, C) && (!plane1 || cross_packed(k1, C1)) && tile0 <= CROSSH_SMEM_MAX && tile1 <= CROSSH_SMEM_MAX) {
         const int pitch0 = crossh_pitch(d, k), pitch1 = plane1 ? crossh_pitch(d, k1) : pitch0;
-        size_t smem = (size_t)CROSSH_ROWS * (pitch0 > pitch1 ? pitch0 : pitch1) * sizeof(unsigned short);
+        size_t smem = tile0 > tile1 ? tile0 : tile1;
         int rc = lt_ensure_smem((const void*)k_cross_h, smem);
         if (rc) return rc;
         dim3 gh(lt_div_up(d.bv_h, CROSSH_ROWS), n, plane1 ? 2 : 1);
@@ -901,7 +952,11 @@ static int launch_cross_v(lt_handle* h, const uint32_t* plane, uint32_t* bits, i
         return launch_cross_v(h, plane1, bits, k1, C1, n, list, count, st, pad_rows_zero);
     }
     dim3 gv(d.p2 / 32, lt_div_up(d.bv_h, CV_BAND), plane1 ? 2 * n : n);
-#define LT_CROSS_V(PK, RP) k_cross_v<PK, RP><<<gv, 32, 0, st>>>(plane, plane1, bits, d, k, C, k1, C1, n, ppitch, pstride, h->stream_mask, list, count)
+    const int kmax = (plane1 && k1 > k) ? k1 : k;
+    const int ring_rows = crossv_ring_rows(kmax);
+    const size_t ring_bytes = (size_t)(ring_rows + CV_CHUNK) * 32 * sizeof(uint32_t);      // + the mirror slots
+#define LT_CROSS_V(PK, RP) do { int rc_ = lt_ensure_smem((const void*)k_cross_v<PK, RP>, ring_bytes); if (rc_) return rc_; \
+        k_cross_v<PK, RP><<<gv, 32, ring_bytes, st>>>(plane, plane1, bits, d, k, C, k1, C1, n, ppitch, pstride, h->stream_mask, list, count, ring_rows); } while (0)
     if (packed && rowpad) LT_CROSS_V(true, true);
     else if (packed) LT_CROSS_V(true, false);
     else if (rowpad) LT_CROSS_V(false, true);

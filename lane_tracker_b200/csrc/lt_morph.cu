@@ -46,6 +46,9 @@ constexpr int NPW = LT_MORPH_NPW;   // producer warps
 #ifndef LT_MORPH_UNROLL8
 #define LT_MORPH_UNROLL8 4
 #endif
+#ifndef LT_MORPH_T32_FROM_T16
+#define LT_MORPH_T32_FROM_T16 0
+#endif
 constexpr int UNROLL4 = LT_MORPH_UNROLL4, UNROLL8 = LT_MORPH_UNROLL8;   // unroll factors of the producers' task loops
 constexpr int NPROD = 32 * NPW;
 constexpr int NTHREADS = TW + NPROD;
@@ -244,16 +247,19 @@ k_morph(MorphArgs a, LtDims d) {
                 *reinterpret_cast<uint4*>(T4 + pr * TEA + c) = t4;
             }
             bar_sync(BAR_PROD, NPROD);
-            // ---- T8, T16 (, T32) from T4: entry i = op over T4[i + 4k]
+            // ---- T8, T16 from T4 (entry i = op over T4[i + 4k]); T32 either straight from T4 as well (one phase, 8 vector
+            // loads and 13 min/max-pipe operations per entry) or from T16 in a third phase (T32[i] = op(T16[i], T16[i + 16]):
+            // one more producer barrier, 9 operations per entry)
+            constexpr bool T32_DIRECT = G::HAS32 && !LT_MORPH_T32_FROM_T16;
 #pragma unroll UNROLL8
             for (int it = 0; it < NIT; ++it) {
                 const int q = pt + it * NPROD;
                 if (q >= NTASK) break;
                 const int pr = q / G::CH, c = (q - pr * G::CH) * 4;
                 const uint4* t = reinterpret_cast<const uint4*>(T4 + pr * TEA + c);
-                uint4 v[G::HAS32 ? 8 : 4];
+                uint4 v[T32_DIRECT ? 8 : 4];
 #pragma unroll
-                for (int k = 0; k < (G::HAS32 ? 8 : 4); ++k) v[k] = t[k];
+                for (int k = 0; k < (T32_DIRECT ? 8 : 4); ++k) v[k] = t[k];
                 uint32_t o8[4], o16[4], o32[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -262,7 +268,7 @@ k_morph(MorphArgs a, LtDims d) {
                     const uint32_t a16 = op3<IS_MAX>(a8, w(2) << 8, w(3) << 8), b16 = op3<IS_MAX>(b8, w(2), w(3));
                     o8[e] = __byte_perm(a8, b8, 0x7351);          // value bytes back to {a.lo, b.lo, a.hi, b.hi}
                     o16[e] = __byte_perm(a16, b16, 0x7351);
-                    if (G::HAS32) {
+                    if (T32_DIRECT) {
                         const uint32_t a32 = op3<IS_MAX>(a16, op2<IS_MAX>(w(4) << 8, w(5) << 8), op2<IS_MAX>(w(6) << 8, w(7) << 8));
                         const uint32_t b32 = op3<IS_MAX>(b16, op2<IS_MAX>(w(4), w(5)), op2<IS_MAX>(w(6), w(7)));
                         o32[e] = __byte_perm(a32, b32, 0x7351);
@@ -271,7 +277,23 @@ k_morph(MorphArgs a, LtDims d) {
                 uint32_t* o = Tb + RP * TEA + pr * TEA + c;
                 *reinterpret_cast<uint4*>(o) = make_uint4(o8[0], o8[1], o8[2], o8[3]);
                 *reinterpret_cast<uint4*>(o + RP * TEA) = make_uint4(o16[0], o16[1], o16[2], o16[3]);
-                if (G::HAS32) *reinterpret_cast<uint4*>(o + 2 * RP * TEA) = make_uint4(o32[0], o32[1], o32[2], o32[3]);
+                if (T32_DIRECT) *reinterpret_cast<uint4*>(o + 2 * RP * TEA) = make_uint4(o32[0], o32[1], o32[2], o32[3]);
+            }
+            if (G::HAS32 && !T32_DIRECT) {
+                bar_sync(BAR_PROD, NPROD);
+                // entries whose window runs past the tabulated columns read slack / the next pair's row: never used by the walk
+#pragma unroll UNROLL8
+                for (int it = 0; it < NIT; ++it) {
+                    const int q = pt + it * NPROD;
+                    if (q >= NTASK) break;
+                    const int pr = q / G::CH, c = (q - pr * G::CH) * 4;
+                    const uint32_t* t16 = Tb + 2 * RP * TEA + pr * TEA + c;
+                    const uint4 u = *reinterpret_cast<const uint4*>(t16), v = *reinterpret_cast<const uint4*>(t16 + 16);
+                    auto m = [](uint32_t x, uint32_t y) {
+                        return __byte_perm(op2<IS_MAX>(x << 8, y << 8), op2<IS_MAX>(x, y), 0x7351);
+                    };
+                    *reinterpret_cast<uint4*>(Tb + 3 * RP * TEA + pr * TEA + c) = make_uint4(m(u.x, v.x), m(u.y, v.y), m(u.z, v.z), m(u.w, v.w));
+                }
             }
             if (TOPHAT) cp_async_wait_all();             // OG[b] (and the long-issued next rows) have landed
             bar_arrive(BAR_FULL + b, NTHREADS);

@@ -176,46 +176,75 @@ int lt_launch_build_und_desc(lt_handle* h, cudaStream_t st) {
     return 0;
 }
 
-// cv2.undistort of the ROI rows: one thread = one ROI pixel of NSU streams (descriptor decoded once).  Fast path: the
-// six bytes of a tap pair come from three aligned 32-bit words and two funnel shifts instead of six byte loads.
-constexpr int NSU = 8;
+// Layout of the undistorted ROI ("und") buffer, per group of NSW = 16 streams:
+//     word ((r * UP + c) * NSW + s)     r = row - roi0 + 1,  c = column + 1,  UP = img_w + 1,  s = stream within the group
+// i.e. STREAM-MINOR (the 16 streams of one pixel are 64 contiguous bytes: a thread that handles one pixel of all the
+// streams of a group moves them with 16-byte vectors) and ZERO-BORDERED: column c = 0 of every row (which is also
+// column img_w + 1 of the row above), row r = 0 and the two rows below the ROI are never written and stay 0 from the
+// allocation.  They are cv2.warpPerspective's BORDER_CONSTANT: a tap outside the frame reads a zero word, so the warp
+// needs neither in-image flags nor branches; a pixel with no tap inside the frame points at the two zero rows.
+constexpr int NSW = LT_UND_GROUP;      // streams per group
 
+// cv2.undistort of the ROI rows: one thread = one ROI pixel of the NSW streams of a group (descriptor decoded once; the
+// 32 lanes of a warp read 32 neighbouring pixels of one frame: whole sectors).  The stream-minor output goes through
+// shared memory so that a warp stores 512 contiguous bytes.  Fast path: the six bytes of a tap pair come from three
+// aligned 32-bit words and two funnel shifts.
 __global__ void __launch_bounds__(256)
-k_undistort_roi(const uint8_t* __restrict__ frames, uchar4* __restrict__ und, const int2* __restrict__ desc, LtDims d, int n,
-                int aligned) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+k_undistort_roi(const uint8_t* __restrict__ frames, uint32_t* __restrict__ und, const int2* __restrict__ desc, LtDims d, int n,
+                int aligned, size_t group_words) {
+    __shared__ uint4 tile[256 * (NSW / 4)];            // [pixel][chunk of four streams], chunk index rotated by the pixel
+    const int p0 = blockIdx.x * blockDim.x, p = p0 + threadIdx.x;
     const int roi_px = (d.roi1 - d.roi0) * d.img_w;
-    if (p >= roi_px) return;
-    const int2 q = __ldg(&desc[p]);
-    const uint32_t f = (uint32_t)q.y;
-    uint32_t wA, wB;
-    blend_weights(f, wA, wB);
-    const uint32_t m = (f >> 10) & 15u;
-    const bool fast = aligned && (f >> 14);
-    const size_t frame_bytes = (size_t)d.img_w * d.img_h * 3;
-    const int pitch = d.img_w * 3;
-    const int wi = q.x >> 2, sh = (q.x & 3) * 8, wpitch = pitch >> 2;
-    const int s0 = blockIdx.y * NSU, s1 = min(s0 + NSU, n);
-    uint32_t* out = reinterpret_cast<uint32_t*>(und) + (size_t)s0 * roi_px + p;
-    for (int s = s0; s < s1; ++s, out += roi_px) {
-        const uint8_t* img = frames + (size_t)s * frame_bytes;
-        uint32_t o = 0;
-        if (fast) {
-            const uint32_t* w = reinterpret_cast<const uint32_t*>(img) + wi;
-            const uint32_t a0 = __ldg(w), a1 = __ldg(w + 1), a2 = __ldg(w + 2);
-            const uint32_t b0 = __ldg(w + wpitch), b1 = __ldg(w + wpitch + 1), b2 = __ldg(w + wpitch + 2);
-            const uint32_t qa0 = __funnelshift_r(a0, a1, sh), qa1 = __funnelshift_r(a1, a2, sh);     // bytes o..o+3, o+4..o+7
-            const uint32_t qb0 = __funnelshift_r(b0, b1, sh), qb1 = __funnelshift_r(b1, b2, sh);
-            o = blend_taps(qa0, __funnelshift_r(qa0, qa1, 24), qb0, __funnelshift_r(qb0, qb1, 24), wA, wB);
-        } else if (m) {
-            auto tap = [&](uint32_t bit, int off) -> uint32_t {     // BORDER_CONSTANT 0
-                if (!(m & bit)) return 0u;
-                const uint8_t* t = img + q.x + off;
-                return (uint32_t)__ldg(t) | ((uint32_t)__ldg(t + 1) << 8) | ((uint32_t)__ldg(t + 2) << 16);
-            };
-            o = blend_taps(tap(1u, 0), tap(2u, 3), tap(4u, pitch), tap(8u, pitch + 3), wA, wB);
+    const int s0 = blockIdx.y * NSW, ns = min(NSW, n - s0);
+    if (p < roi_px) {
+        const int2 q = __ldg(&desc[p]);
+        const uint32_t f = (uint32_t)q.y;
+        uint32_t wA, wB;
+        blend_weights(f, wA, wB);
+        const uint32_t m = (f >> 10) & 15u;
+        const bool fast = aligned && (f >> 14);
+        const size_t frame_bytes = (size_t)d.img_w * d.img_h * 3;
+        const int pitch = d.img_w * 3;
+        const int wi = q.x >> 2, sh = (q.x & 3) * 8, wpitch = pitch >> 2;
+#pragma unroll
+        for (int c = 0; c < NSW / 4; ++c) {
+            uint32_t o[4] = {0u, 0u, 0u, 0u};
+            if (4 * c < ns) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (4 * c + k >= ns) break;
+                    const uint8_t* img = frames + (size_t)(s0 + 4 * c + k) * frame_bytes;
+                    if (fast) {
+                        const uint32_t* w = reinterpret_cast<const uint32_t*>(img) + wi;
+                        const uint32_t a0 = __ldg(w), a1 = __ldg(w + 1), a2 = __ldg(w + 2);
+                        const uint32_t b0 = __ldg(w + wpitch), b1 = __ldg(w + wpitch + 1), b2 = __ldg(w + wpitch + 2);
+                        const uint32_t qa0 = __funnelshift_r(a0, a1, sh), qa1 = __funnelshift_r(a1, a2, sh);     // bytes o..o+3, o+4..o+7
+                        const uint32_t qb0 = __funnelshift_r(b0, b1, sh), qb1 = __funnelshift_r(b1, b2, sh);
+                        o[k] = blend_taps(qa0, __funnelshift_r(qa0, qa1, 24), qb0, __funnelshift_r(qb0, qb1, 24), wA, wB);
+                    } else if (m) {
+                        auto tap = [&](uint32_t bit, int off) -> uint32_t {     // BORDER_CONSTANT 0
+                            if (!(m & bit)) return 0u;
+                            const uint8_t* tp = img + q.x + off;
+                            return (uint32_t)__ldg(tp) | ((uint32_t)__ldg(tp + 1) << 8) | ((uint32_t)__ldg(tp + 2) << 16);
+                        };
+                        o[k] = blend_taps(tap(1u, 0), tap(2u, 3), tap(4u, pitch), tap(8u, pitch + 3), wA, wB);
+                    }
+                }
+            }
+            // rotate the chunk slot by half the pixel index: the 16-byte accesses of a quarter warp land in distinct banks
+            tile[threadIdx.x * (NSW / 4) + ((c + (threadIdx.x >> 1)) & (NSW / 4 - 1))] = make_uint4(o[0], o[1], o[2], o[3]);
         }
-        *out = o;                                                   // RGBX
+    }
+    __syncthreads();
+    uint32_t* const base = und + (size_t)blockIdx.y * group_words;
+#pragma unroll
+    for (int r = 0; r < NSW / 4; ++r) {
+        const int e = r * 256 + threadIdx.x;           // (pixel, chunk) in output order
+        const int px = e >> 2, c = e & 3, pp = p0 + px;
+        if (pp >= roi_px) break;
+        const int i = pp / d.img_w, j = pp - i * d.img_w;
+        uint4* out = reinterpret_cast<uint4*>(base + ((size_t)(i + 1) * (d.img_w + 1) + (j + 1)) * NSW);
+        out[c] = tile[px * (NSW / 4) + ((c + (px >> 1)) & (NSW / 4 - 1))];
     }
 }
 
@@ -241,9 +270,9 @@ int lt_launch_warp_frame(lt_handle* h, const uint8_t* d_frames, uint8_t* d_bv_rg
 
 int lt_launch_undistort(lt_handle* h, const uint8_t* d_frames, int n, cudaStream_t st) {
     const LtDims& d = h->d;
-    dim3 g(lt_div_up((d.roi1 - d.roi0) * d.img_w, 256), lt_div_up(n, NSU));
+    dim3 g(lt_div_up((d.roi1 - d.roi0) * d.img_w, 256), lt_div_up(n, NSW));
     const int aligned = ((uintptr_t)d_frames & 3) == 0 && ((d.img_w * 3) & 3) == 0;     // word loads need 4-byte aligned rows
-    k_undistort_roi<<<g, 256, 0, st>>>(d_frames, h->und_roi, h->und_desc, d, n, aligned);
+    k_undistort_roi<<<g, 256, 0, st>>>(d_frames, h->und_roi, h->und_desc, d, n, aligned, lt_und_group_words(d));
     LT_LAUNCH_CHECK();
     return 0;
 }
@@ -262,22 +291,22 @@ __device__ __forceinline__ int lab_b(uint32_t rgb, const unsigned short* __restr
     return max(0, min(255, b));
 }
 
-// Per bird's-eye pixel tap descriptor, built once from bv_map: x = index of tap (sy, sx) in the undistorted ROI
-// buffer, y = fx | fy << 5 | in-image flags of the four taps << 10.  Saves the per-frame bounds logic.
+// Per bird's-eye pixel tap descriptor, built once from bv_map: x = pixel index (r * UP + c) of tap (sy, sx) in the
+// zero-bordered und layout above, y = fx | fy << 5.  Taps outside the frame fall on zero words of that layout (column 0 /
+// row 0 / the rows below the ROI); a pixel without any tap inside the frame points at the two all-zero rows.
 __global__ void k_build_bv_desc(const int2* __restrict__ map, int2* __restrict__ desc, LtDims d) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= d.bv_w) return;
-    Tap4 t = make_taps(map[(size_t)y * d.bv_w + x]);
-    int2 q = map[(size_t)y * d.bv_w + x];
+    const int2 q = map[(size_t)y * d.bv_w + x];
+    Tap4 t = make_taps(q);
     auto ok = [&](int yy, int xx) {
         return (unsigned)yy < (unsigned)d.img_h && (unsigned)xx < (unsigned)d.img_w && yy >= d.roi0 && yy < d.roi1;
     };
-    uint32_t f = (uint32_t)(q.x & 31) | ((uint32_t)(q.y & 31) << 5);
-    f |= (ok(t.sy, t.sx) ? 1u : 0u) << 10 | (ok(t.sy, t.sx + 1) ? 1u : 0u) << 11 |
-         (ok(t.sy + 1, t.sx) ? 1u : 0u) << 12 | (ok(t.sy + 1, t.sx + 1) ? 1u : 0u) << 13;
-    long long idx = (long long)(t.sy - d.roi0) * d.img_w + t.sx;
-    if (!(f >> 10)) idx = 0;
-    desc[(size_t)y * d.bv_w + x] = make_int2((int)idx, (int)f);
+    const bool any = ok(t.sy, t.sx) || ok(t.sy, t.sx + 1) || ok(t.sy + 1, t.sx) || ok(t.sy + 1, t.sx + 1);
+    const int up = d.img_w + 1, rows = d.roi1 - d.roi0;
+    // with a tap inside the frame: sy in [roi0 - 1, roi1 - 1] and sx in [-1, img_w - 1] (the ROI is the hull of such taps)
+    const int idx = any ? (t.sy - d.roi0 + 1) * up + (t.sx + 1) : (rows + 1) * up;
+    desc[(size_t)y * d.bv_w + x] = make_int2(idx, (int)((uint32_t)(q.x & 31) | ((uint32_t)(q.y & 31) << 5)));
 }
 
 int lt_launch_build_desc(lt_handle* h, cudaStream_t st) {
@@ -324,15 +353,12 @@ __device__ __forceinline__ void store_padded(uint32_t* __restrict__ planeR, uint
     }
 }
 
-// ---- the per-frame warp: one thread = one packed column (two bird's-eye pixels) of NSW streams ------------------
-// The tap descriptor of a pixel (8 bytes from the shared table) is decoded once and reused for every stream of the
-// group; the Lab look-up tables live in shared memory in a form that needs two 3-input adds instead of six multiplies:
+// ---- the per-frame warp: one thread = one packed column (two bird's-eye pixels) of the NSW streams of a group -----
+// The tap descriptors of the two pixels (8 bytes each from the shared table) are decoded once; the four taps of a pixel
+// are fetched for four streams at a time with 16-byte loads from the stream-minor und layout (no flags, no branches:
+// out-of-frame taps read its zero border).  The Lab look-up tables live in shared memory in a form that needs two
+// 3-input adds instead of six multiplies:
 //   YZ[c][v] = { coefY[c] * g[v] (+ 2048 for c = 0),  coefZ[c] * g[v] (+ 2048) }      (lane_tracker.py:208)
-#ifndef LT_WARP_NSW
-#define LT_WARP_NSW 16
-#endif
-constexpr int NSW = LT_WARP_NSW;       // streams per thread
-
 struct LabSmem {
     uint2 yz[3][256];
     unsigned short cb[3072];
@@ -344,8 +370,8 @@ __device__ __forceinline__ void lab_smem_load(LabSmem& L, const uint2* __restric
     for (int i = threadIdx.x; i < 1536; i += blockDim.x) reinterpret_cast<uint32_t*>(L.cb)[i] = __ldg(&c32[i]);
 }
 
-__device__ __forceinline__ uint32_t lab_b_smem(uint32_t rgb, const LabSmem& L) {
-    const uint2 a = L.yz[0][rgb & 255], b = L.yz[1][(rgb >> 8) & 255], c = L.yz[2][(rgb >> 16) & 255];
+__device__ __forceinline__ uint32_t lab_b_smem(uint32_t R, uint32_t G, uint32_t B, const LabSmem& L) {
+    const uint2 a = L.yz[0][R], b = L.yz[1][G], c = L.yz[2][B];
     const int fY = L.cb[(a.x + b.x + c.x) >> 12], fZ = L.cb[(a.y + b.y + c.y) >> 12];
     const int v = (200 * (fY - fZ) + 128 * 32768 + 16384) >> 15;
     return (uint32_t)max(0, min(255, v));
@@ -363,12 +389,18 @@ __global__ void k_build_lab_yz(const unsigned short* __restrict__ g, uint2* __re
 //   out = (t00*w00 + t01*w01 + t10*w10 + t11*w11 + 512) >> 10,   w = (32-fx)(32-fy), fx(32-fy), (32-fx)fy, fx*fy
 // as two IDP.2A (two 16-bit weights x two 8-bit taps + accumulator, FMA pipe) per channel: wA = w00 | w01 << 16 for the
 // upper tap row, wB = w10 | w11 << 16 for the lower one; the tap bytes of a row are paired per channel by two PRMT.
-__device__ __forceinline__ uint32_t blend_taps(uint32_t t00, uint32_t t01, uint32_t t10, uint32_t t11, uint32_t wA, uint32_t wB) {
+__device__ __forceinline__ void blend_taps3(uint32_t t00, uint32_t t01, uint32_t t10, uint32_t t11, uint32_t wA, uint32_t wB,
+                                            uint32_t& R, uint32_t& G, uint32_t& B) {
     const uint32_t p0 = __byte_perm(t00, t01, 0x5140), q0 = __byte_perm(t00, t01, 0x0062);    // {R,R',G,G'}, {B,B',.,.}
     const uint32_t p1 = __byte_perm(t10, t11, 0x5140), q1 = __byte_perm(t10, t11, 0x0062);
-    const uint32_t R = __dp2a_lo(wB, p1, __dp2a_lo(wA, p0, 512u)) >> 10;
-    const uint32_t G = __dp2a_hi(wB, p1, __dp2a_hi(wA, p0, 512u)) >> 10;
-    const uint32_t B = __dp2a_lo(wB, q1, __dp2a_lo(wA, q0, 512u)) >> 10;
+    R = __dp2a_lo(wB, p1, __dp2a_lo(wA, p0, 512u)) >> 10;
+    G = __dp2a_hi(wB, p1, __dp2a_hi(wA, p0, 512u)) >> 10;
+    B = __dp2a_lo(wB, q1, __dp2a_lo(wA, q0, 512u)) >> 10;
+}
+
+__device__ __forceinline__ uint32_t blend_taps(uint32_t t00, uint32_t t01, uint32_t t10, uint32_t t11, uint32_t wA, uint32_t wB) {
+    uint32_t R, G, B;
+    blend_taps3(t00, t01, t10, t11, wA, wB, R, G, B);
     return R | (G << 8) | (B << 16);
 }
 
@@ -378,66 +410,70 @@ __device__ __forceinline__ void blend_weights(uint32_t f, uint32_t& wA, uint32_t
     wB = gx * fy | (fx * fy) << 16;
 }
 
+__device__ __forceinline__ uint32_t u4_at(const uint4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+
+constexpr int WARP_ITEMS = 64;        // packed columns per pass of a CTA (x 4 stream chunks = 256 threads)
+#ifndef LT_WARP_NB
+#define LT_WARP_NB 8
+#endif
+constexpr int WARP_NB = LT_WARP_NB;   // passes per CTA (the Lab tables are loaded once per CTA)
+
+template <bool RGB_OUT>
 __global__ void __launch_bounds__(256)
-k_warp_planes(const uchar4* __restrict__ und_all, const int2* __restrict__ desc, uint32_t* __restrict__ planeR,
+k_warp_planes(const uint32_t* __restrict__ und_all, const int2* __restrict__ desc, uint32_t* __restrict__ planeR,
               uint32_t* __restrict__ planeB, uint8_t* __restrict__ bv_rgb, const uint2* __restrict__ yz,
-              const unsigned short* __restrict__ cb, LtDims d, unsigned stream_pad, int n) {
+              const unsigned short* __restrict__ cb, LtDims d, unsigned stream_pad, int n, size_t group_words) {
     __shared__ LabSmem L;
     lab_smem_load(L, yz, cb);
     __syncthreads();
-    const int item = blockIdx.x * blockDim.x + threadIdx.x;        // flat (row, packed column)
-    if (item >= d.bv_h * d.p2) return;
-    const int y = item / d.p2, x = item - y * d.p2;
-    const int s0 = blockIdx.y * NSW, s1 = min(s0 + NSW, n);
-    const unsigned roi_px = (unsigned)((d.roi1 - d.roi0) * d.img_w);
-    // decode the two descriptors once
-    const bool hi_real = x + d.p2 < d.bv_w;
-    const int2 q0 = __ldg(&desc[y * d.bv_w + x]);
-    const int2 q1 = hi_real ? __ldg(&desc[y * d.bv_w + x + d.p2]) : make_int2(0, 0);
-    const uint32_t f0 = (uint32_t)q0.y, f1 = (uint32_t)q1.y;
-    uint32_t wA0, wB0, wA1, wB1;
-    blend_weights(f0, wA0, wB0);
-    blend_weights(f1, wA1, wB1);
-    const uint32_t m0 = f0 >> 10, m1 = f1 >> 10;                    // in-image flags of the four taps
-    const int o = y * d.pp + x;
-    const bool halo_l = x >= d.p2 - LT_HALO_X, halo_r = x < LT_HALO_X;
-    for (int s = s0; s < s1; ++s) {
-        const uint32_t* und = reinterpret_cast<const uint32_t*>(und_all) + (size_t)((unsigned)s) * roi_px;
-        uint32_t rgb0 = 0, rgb1 = 0;
-        if (m0) {
-            const uint32_t* b = und + q0.x;
-            uint32_t t00, t01, t10, t11;
-            if (m0 == 15u) { t00 = __ldg(b); t01 = __ldg(b + 1); t10 = __ldg(b + d.img_w); t11 = __ldg(b + d.img_w + 1); }
-            else {                                                  // BORDER_CONSTANT 0
-                t00 = (m0 & 1u) ? __ldg(b) : 0u; t01 = (m0 & 2u) ? __ldg(b + 1) : 0u;
-                t10 = (m0 & 4u) ? __ldg(b + d.img_w) : 0u; t11 = (m0 & 8u) ? __ldg(b + d.img_w + 1) : 0u;
+    // thread = (packed column, chunk of four streams): the four threads of a column are neighbours in the warp, so a warp
+    // gathers 8 columns x 64 contiguous bytes per tap (every fetched sector fully used) and stores 32 contiguous bytes
+    // per stream
+    const int c = threadIdx.x & 3, il = threadIdx.x >> 2;
+    const int s0 = blockIdx.y * NSW + 4 * c, ns = min(4, n - s0);
+    if (ns <= 0) return;
+    const int up4 = (d.img_w + 1) * (NSW / 4);                      // one und row in 16-byte units
+    const uint4* und = reinterpret_cast<const uint4*>(und_all + (size_t)blockIdx.y * group_words) + c;
+    const int total = d.bv_h * d.p2;
+#pragma unroll 1
+    for (int b = 0; b < WARP_NB; ++b) {
+        const int item = (blockIdx.x * WARP_NB + b) * WARP_ITEMS + il;  // flat (row, packed column)
+        if (item >= total) return;
+        const int y = item / d.p2, x = item - y * d.p2;
+        const bool hi_real = x + d.p2 < d.bv_w;
+        const int2 q0 = __ldg(&desc[y * d.bv_w + x]);
+        const int2 q1 = __ldg(&desc[y * d.bv_w + (hi_real ? x + d.p2 : x)]);
+        const uint4* t0 = und + (size_t)(unsigned)q0.x * (NSW / 4);
+        const uint4* t1 = und + (size_t)(unsigned)q1.x * (NSW / 4);
+        // four streams of the four taps of both pixels: 8 x 16 bytes in flight
+        const uint4 a00 = __ldg(t0), a01 = __ldg(t0 + NSW / 4), a10 = __ldg(t0 + up4), a11 = __ldg(t0 + up4 + NSW / 4);
+        const uint4 b00 = __ldg(t1), b01 = __ldg(t1 + NSW / 4), b10 = __ldg(t1 + up4), b11 = __ldg(t1 + up4 + NSW / 4);
+        uint32_t wA0, wB0, wA1, wB1;
+        blend_weights((uint32_t)q0.y, wA0, wB0);
+        blend_weights((uint32_t)q1.y, wA1, wB1);
+        const unsigned o = (unsigned)(y * d.pp + x);
+        const bool halo_l = x >= d.p2 - LT_HALO_X, halo_r = x < LT_HALO_X;
+        const uint32_t beyond = hi_real ? 0u : 0xFFFF0000u;         // lanes beyond the image: the erosion pad
+        uint32_t* pr = planeR + (size_t)(unsigned)s0 * stream_pad + o;
+        uint32_t* pb = planeB + (size_t)(unsigned)s0 * stream_pad + o;
+#pragma unroll
+        for (int k = 0; k < 4; ++k, pr += stream_pad, pb += stream_pad) {
+            if (k >= ns) break;
+            uint32_t R0, G0, B0, R1, G1, B1;
+            blend_taps3(u4_at(a00, k), u4_at(a01, k), u4_at(a10, k), u4_at(a11, k), wA0, wB0, R0, G0, B0);
+            blend_taps3(u4_at(b00, k), u4_at(b01, k), u4_at(b10, k), u4_at(b11, k), wA1, wB1, R1, G1, B1);
+            // (a pixel without a tap inside the frame is black; Lab b of black = 128 comes out of the tables)
+            const uint32_t r2 = R0 | (R1 << 16) | beyond;
+            const uint32_t b2 = lab_b_smem(R0, G0, B0, L) | (lab_b_smem(R1, G1, B1, L) << 16) | beyond;
+            pr[0] = r2;
+            pb[0] = b2;
+            if (halo_l) { pr[-d.p2] = (r2 << 16) | 0xFFFFu; pb[-d.p2] = (b2 << 16) | 0xFFFFu; }      // seam-stitched halo columns
+            if (halo_r) { pr[d.p2] = (r2 >> 16) | 0xFFFF0000u; pb[d.p2] = (b2 >> 16) | 0xFFFF0000u; }
+            if (RGB_OUT) {
+                uint8_t* p = bv_rgb + (((size_t)(s0 + k) * d.bv_h + y) * d.bv_w + x) * 3;
+                p[0] = R0; p[1] = G0; p[2] = B0;
+                if (hi_real) { p += (size_t)d.p2 * 3; p[0] = R1; p[1] = G1; p[2] = B1; }
             }
-            rgb0 = blend_taps(t00, t01, t10, t11, wA0, wB0);
-        }
-        if (m1) {
-            const uint32_t* b = und + q1.x;
-            uint32_t t00, t01, t10, t11;
-            if (m1 == 15u) { t00 = __ldg(b); t01 = __ldg(b + 1); t10 = __ldg(b + d.img_w); t11 = __ldg(b + d.img_w + 1); }
-            else {
-                t00 = (m1 & 1u) ? __ldg(b) : 0u; t01 = (m1 & 2u) ? __ldg(b + 1) : 0u;
-                t10 = (m1 & 4u) ? __ldg(b + d.img_w) : 0u; t11 = (m1 & 8u) ? __ldg(b + d.img_w + 1) : 0u;
-            }
-            rgb1 = blend_taps(t00, t01, t10, t11, wA1, wB1);
-        }
-        // a pixel without a tap inside the frame is black; Lab b of black = 128
-        uint32_t r2 = (rgb0 & 255u) | ((rgb1 & 255u) << 16);
-        uint32_t b2 = (m0 ? lab_b_smem(rgb0, L) : 128u) | ((m1 ? lab_b_smem(rgb1, L) : 128u) << 16);
-        if (!hi_real) { r2 |= 0xFFFF0000u; b2 |= 0xFFFF0000u; }     // lanes beyond the image: the erosion pad
-        uint32_t* pr = planeR + (size_t)((unsigned)s) * stream_pad;
-        uint32_t* pb = planeB + (size_t)((unsigned)s) * stream_pad;
-        pr[o] = r2;
-        pb[o] = b2;
-        if (halo_l) { pr[o - d.p2] = (r2 << 16) | 0xFFFFu; pb[o - d.p2] = (b2 << 16) | 0xFFFFu; }      // seam-stitched halo columns
-        if (halo_r) { pr[o + d.p2] = (r2 >> 16) | 0xFFFF0000u; pb[o + d.p2] = (b2 >> 16) | 0xFFFF0000u; }
-        if (bv_rgb) {
-            uint8_t* p = bv_rgb + (((size_t)s * d.bv_h + y) * d.bv_w + x) * 3;
-            p[0] = rgb0 & 255; p[1] = (rgb0 >> 8) & 255; p[2] = (rgb0 >> 16) & 255;
-            if (hi_real) { p += (size_t)d.p2 * 3; p[0] = rgb1 & 255; p[1] = (rgb1 >> 8) & 255; p[2] = (rgb1 >> 16) & 255; }
         }
     }
 }
@@ -450,9 +486,13 @@ int lt_launch_build_lab_yz(lt_handle* h, cudaStream_t st) {
 
 int lt_launch_warp(lt_handle* h, uint8_t* d_bv_rgb, int n, cudaStream_t st) {
     const LtDims& d = h->d;
-    dim3 g(lt_div_up(d.bv_h * d.p2, 256), lt_div_up(n, NSW));
-    k_warp_planes<<<g, 256, 0, st>>>(h->und_roi, h->bv_desc, h->planeR, h->planeB, d_bv_rgb, h->lab_yz, h->lab_cbrt, d,
-                                     (unsigned)h->stream_pad, n);
+    dim3 g(lt_div_up(d.bv_h * d.p2, WARP_ITEMS * WARP_NB), lt_div_up(n, NSW));
+    if (d_bv_rgb)
+        k_warp_planes<true><<<g, 256, 0, st>>>(h->und_roi, h->bv_desc, h->planeR, h->planeB, d_bv_rgb, h->lab_yz, h->lab_cbrt, d,
+                                               (unsigned)h->stream_pad, n, lt_und_group_words(d));
+    else
+        k_warp_planes<false><<<g, 256, 0, st>>>(h->und_roi, h->bv_desc, h->planeR, h->planeB, nullptr, h->lab_yz, h->lab_cbrt, d,
+                                                (unsigned)h->stream_pad, n, lt_und_group_words(d));
     LT_LAUNCH_CHECK();
     return 0;
 }
