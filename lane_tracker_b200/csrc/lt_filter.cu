@@ -367,23 +367,23 @@ __device__ __forceinline__ void warp_row_prefix(const uint32_t* __restrict__ pro
     __syncwarp();
 }
 
-// Horizontal half of the cross threshold.  A CTA copies 32 rows of a padded plane into shared memory as they are
-// (pair-packed 32-bit entries, 4-byte cp.async: the whole tile is in flight at once and no register is touched), then
-// builds the k halo entries either side of every row from the row itself -- the two strips of a pair plane are
-// neighbours in the image: column -j = {0, entry[p2 - j].lo}, column p2 + j = {entry[j].hi, 0} -- and zeroes the high
-// lanes that lie beyond the image.  Thread (row = lane, segment = warp) then walks its column segment with running
-// window sums L, R in packed u16x2 registers and emits finished 32-column mask words from two shift registers.
-// The row pitch is odd, so the 32 rows of a warp sit in 32 different banks and the walk is conflict-free.
+// Horizontal half of the cross threshold.  A CTA stages 32 rows of a padded plane in shared memory as (lo, hi) BYTE
+// pairs (top-hat values are bytes: half the footprint of the 32-bit pair entries, so five CTAs fit an SM): 16-byte loads,
+// two PRMT and two 32-bit stores per four columns.  The K halo entries either side of a row are then built from the row
+// itself -- the two strips of a pair plane are neighbours in the image: column -q = {0, entry[p2 - q].lo}, column
+// p2 + q = {entry[q].hi, 0} -- and the high lanes that lie beyond the image are zeroed.  Thread (row = lane,
+// segment = warp) walks its column segment with running window sums L, R in packed u16x2 registers and emits finished
+// 32-column mask words from two shift registers.  Rows sit in different banks (the row pitch is 2 * odd half-words), so
+// the walk is conflict-free.
 constexpr int CROSSH_ROWS = 32;
 #ifndef LT_CROSSH_WARPS
 #define LT_CROSSH_WARPS 8
 #endif
 constexpr int CROSSH_WARPS = LT_CROSSH_WARPS;
-static_assert(CROSSH_ROWS <= LT_HALO_Y, "a tile may run into the pad rows below the plane");
+static_assert(CROSSH_ROWS <= LT_HALO_Y && CROSSH_ROWS % CROSSH_WARPS == 0, "a tile may run into the pad rows below the plane");
 
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc) : "memory");
+__device__ __forceinline__ uint32_t unpack_pair(uint32_t v16) {            // (hi<<8 | lo) -> hi<<16 | lo
+    return __byte_perm(v16, 0, 0x4140);
 }
 
 // One launch thresholds up to two planes (blockIdx.z): plane 0 with (k0, C0), plane 1 with (k1, C1).
@@ -396,28 +396,38 @@ k_cross_h(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plan
     int s = list ? list[slot] : slot;
     const uint32_t* __restrict__ plane_all = blockIdx.z ? plane1 : plane0;
     const int k = blockIdx.z ? k1 : k0, C = blockIdx.z ? C1 : C0, pitch = blockIdx.z ? pitch1 : pitch0;
-    extern __shared__ uint32_t tile[];                                   // [32][pitch], entry i <-> packed column i - k
+    const int K = (k + 1) & ~1;                                          // even: packed column 0 starts a 32-bit word
+    extern __shared__ uint32_t smem[];
+    unsigned short* tile = reinterpret_cast<unsigned short*>(smem);     // [32][pitch], entry i <-> packed column i - K
     const int y0 = blockIdx.x * CROSSH_ROWS;
     const uint32_t* src = plane_all + (size_t)s * plane_stride + y0 * ppitch;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // rows below the plane are pad rows of the padded layout: every address is valid, their verdicts are dropped
-    for (int r = warp; r < CROSSH_ROWS; r += CROSSH_WARPS) {
-        const uint32_t* g = src + r * ppitch;
-        uint32_t* t = tile + r * pitch + k;
-        for (int x = lane; x < d.p2; x += 32) cp_async4(t + x, g + x);
+    {
+        // warp w stages rows w, w + 8, ...: one 16-byte chunk of each of its rows in flight per lane.  Rows below the
+        // plane are pad rows of the padded layout: every address is valid, their verdicts are dropped.
+        constexpr int RPW = CROSSH_ROWS / CROSSH_WARPS;
+        for (int g0 = lane * 4; g0 < d.p2; g0 += 128) {
+            uint4 v[RPW];
+#pragma unroll
+            for (int j = 0; j < RPW; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(src + (warp + j * CROSSH_WARPS) * ppitch + g0));
+#pragma unroll
+            for (int j = 0; j < RPW; ++j) {
+                uint32_t* o = reinterpret_cast<uint32_t*>(tile + (warp + j * CROSSH_WARPS) * pitch + K + g0);
+                o[0] = __byte_perm(v[j].x, v[j].y, 0x6420);             // {lo0, hi0, lo1, hi1}
+                o[1] = __byte_perm(v[j].z, v[j].w, 0x6420);
+            }
+        }
     }
-    cp_async_commit();
-    cp_async_wait_all();
     __syncthreads();
     {
         const int xint = d.bv_w - d.p2;                                  // high lanes of columns >= xint lie beyond the image
         const int nfix = d.p2 - xint, per_row = 2 * k + 1 + nfix;
         for (int e = threadIdx.x; e < CROSSH_ROWS * per_row; e += blockDim.x) {
             const int r = e / per_row, j = e - r * per_row;
-            uint32_t* t = tile + r * pitch + k;
-            if (j < nfix) t[xint + j] &= 0xFFFFu;
-            else if (j < nfix + k) { const int q = j - nfix + 1; t[-q] = t[d.p2 - q] << 16; }          // column -q
-            else { const int q = j - nfix - k; t[d.p2 + q] = (q < xint ? t[q] >> 16 : 0u); }           // column p2 + q, q = 0..k
+            unsigned short* t = tile + r * pitch + K;
+            if (j < nfix) t[xint + j] &= 0x00FFu;
+            else if (j < nfix + k) { const int q = j - nfix + 1; t[-q] = (unsigned short)((t[d.p2 - q] & 0xFFu) << 8); }   // column -q
+            else { const int q = j - nfix - k; t[d.p2 + q] = (unsigned short)(q < xint ? t[q] >> 8 : 0u); }               // column p2 + q, q = 0..k
         }
     }
     __syncthreads();
@@ -425,13 +435,13 @@ k_cross_h(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plan
     const int nw = d.p2 >> 5;                                            // words per strip
     const int w0 = (warp * nw) / CROSSH_WARPS, w1 = ((warp + 1) * nw) / CROSSH_WARPS;
     if (w0 >= w1) return;
-    const uint32_t* trow = tile + lane * pitch + k;                      // trow[x] = packed column x
+    const unsigned short* trow = tile + lane * pitch + K;                // trow[x] = packed column x
     const uint32_t kk = (uint32_t)k;
     const uint32_t bias = ((uint32_t)(C * k + 1)) * 0x00010001u;         // pass <=> k*p >= side + C*k + 1
     int x = w0 * 32;
     uint32_t L = bias, Rs = bias;                                        // the running sums carry the compare bias
-    for (int i = 1; i <= k; ++i) { L += trow[x - i]; Rs += trow[x + i]; }
-    uint32_t p = trow[x];
+    for (int i = 1; i <= k; ++i) { L += unpack_pair(trow[x - i]); Rs += unpack_pair(trow[x + i]); }
+    uint32_t p = unpack_pair(trow[x]);
     uint32_t* brow = bits_all + (size_t)s * bits_stride + (size_t)min(y, d.bv_h - 1) * d.mwords;
     for (int w = w0; w < w1; ++w) {
         uint32_t wl = 0, wh = 0;
@@ -442,9 +452,9 @@ k_cross_h(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plan
             const uint32_t ok = (T - L) & (T - Rs);
             wl = __funnelshift_l(ok * 0x10000u, wl, 1);                  // newest column in bit 0 (reversed below)
             wh = __funnelshift_l(ok, wh, 1);
-            const uint32_t pn = trow[x + 1];
-            L = L + p - trow[x - k];
-            Rs = Rs + trow[x + k + 1] - pn;
+            const uint32_t pn = unpack_pair(trow[x + 1]);
+            L = L + p - unpack_pair(trow[x - k]);
+            Rs = Rs + unpack_pair(trow[x + k + 1]) - pn;
             p = pn;
         }
         if (y < d.bv_h) {
@@ -532,7 +542,7 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t w, int lane) {
 // by 4-byte cp.async CV_PF chunks ahead of the walk: every plane row is fetched from L2/HBM once per band (instead of
 // three times, as p[y+k+1], p[y+1] and p[y-k]) and 8 * (CV_PF + 1) rows per warp are in flight without holding registers.
 #ifndef LT_CV_PF
-#define LT_CV_PF 4
+#define LT_CV_PF 3
 #endif
 constexpr int CV_PF = LT_CV_PF;      // prefetch distance in chunks
 
@@ -894,8 +904,10 @@ int lt_launch_plane_to_u8(lt_handle* h, const uint32_t* plane, int pitch, uint8_
 
 static bool cross_packed(int k, int C) { return k <= 127 && C >= 0 && k * 255 + C * k + 1 < 32768; }   // packed u16 lanes stay below 2^15
 
-static int crossh_pitch(const LtDims& d, int k) {
-    return (d.p2 + 2 * k + 2) | 1;                                 // odd: the 32 rows of a warp land in distinct banks
+static int crossh_pitch(const LtDims& d, int k) {                  // in half-words
+    int pitch = d.p2 + 2 * ((k + 1) & ~1) + 4;
+    while (((pitch >> 1) & 1) == 0 || (pitch & 1)) ++pitch;       // pitch = 2 * odd: rows are word aligned and land in distinct banks
+    return pitch;
 }
 constexpr size_t CROSSH_SMEM_MAX = 200 * 1024;
 
@@ -906,8 +918,8 @@ static int launch_cross_h(lt_handle* h, const uint32_t* plane, uint32_t* bits, i
     const LtDims& d = h->d;
     const int ppitch = d.pp;
     const size_t pstride = h->stream_pad;
-    const size_t tile0 = (size_t)CROSSH_ROWS * crossh_pitch(d, k) * sizeof(uint32_t);
-    const size_t tile1 = plane1 ? (size_t)CROSSH_ROWS * crossh_pitch(d, k1) * sizeof(uint32_t) : 0;
+    const size_t tile0 = (size_t)CROSSH_ROWS * crossh_pitch(d, k) * sizeof(unsigned short);
+    const size_t tile1 = plane1 ? (size_t)CROSSH_ROWS * crossh_pitch(d, k1) * sizeof(unsigned short) : 0;
     if (cross_packed(k, C) && (!plane1 || cross_packed(k1, C1)) && tile0 <= CROSSH_SMEM_MAX && tile1 <= CROSSH_SMEM_MAX) {
         const int pitch0 = crossh_pitch(d, k), pitch1 = plane1 ? crossh_pitch(d, k1) : pitch0;
         size_t smem = tile0 > tile1 ? tile0 : tile1;

@@ -185,17 +185,24 @@ int lt_launch_build_und_desc(lt_handle* h, cudaStream_t st) {
 // needs neither in-image flags nor branches; a pixel with no tap inside the frame points at the two zero rows.
 constexpr int NSW = LT_UND_GROUP;      // streams per group
 
-// cv2.undistort of the ROI rows: one thread = one ROI pixel of the NSW streams of a group (descriptor decoded once; the
-// 32 lanes of a warp read 32 neighbouring pixels of one frame: whole sectors).  The stream-minor output goes through
-// shared memory so that a warp stores 512 contiguous bytes.  Fast path: the six bytes of a tap pair come from three
-// aligned 32-bit words and two funnel shifts.
+// cv2.undistort of the ROI rows: one thread = one ROI pixel of UND_SPC streams (descriptor decoded once; the 32 lanes of
+// a warp read 32 neighbouring pixels of one frame: whole sectors).  The stream-minor output goes through shared memory
+// so that a warp stores whole 32-byte sectors.  Fast path: the six bytes of a tap pair come from three aligned 32-bit
+// words and two funnel shifts.
+#ifndef LT_UND_SPC
+#define LT_UND_SPC 8
+#endif
+constexpr int UND_SPC = LT_UND_SPC;    // streams per CTA: 4, 8 or 16 (a CTA covers UND_SPC / 4 of the four 16-byte chunks of a pixel)
+constexpr int UND_CH = UND_SPC / 4;
+static_assert(UND_SPC == 4 || UND_SPC == 8 || UND_SPC == 16, "streams per CTA");
+
 __global__ void __launch_bounds__(256)
 k_undistort_roi(const uint8_t* __restrict__ frames, uint32_t* __restrict__ und, const int2* __restrict__ desc, LtDims d, int n,
                 int aligned, size_t group_words) {
-    __shared__ uint4 tile[256 * (NSW / 4)];            // [pixel][chunk of four streams], chunk index rotated by the pixel
+    __shared__ uint4 tile[256 * UND_CH];               // [pixel][chunk of four streams], chunk slot rotated by the pixel
     const int p0 = blockIdx.x * blockDim.x, p = p0 + threadIdx.x;
     const int roi_px = (d.roi1 - d.roi0) * d.img_w;
-    const int s0 = blockIdx.y * NSW, ns = min(NSW, n - s0);
+    const int s0 = blockIdx.y * UND_SPC, ns = min(UND_SPC, n - s0);
     if (p < roi_px) {
         const int2 q = __ldg(&desc[p]);
         const uint32_t f = (uint32_t)q.y;
@@ -207,7 +214,7 @@ k_undistort_roi(const uint8_t* __restrict__ frames, uint32_t* __restrict__ und, 
         const int pitch = d.img_w * 3;
         const int wi = q.x >> 2, sh = (q.x & 3) * 8, wpitch = pitch >> 2;
 #pragma unroll
-        for (int c = 0; c < NSW / 4; ++c) {
+        for (int c = 0; c < UND_CH; ++c) {
             uint32_t o[4] = {0u, 0u, 0u, 0u};
             if (4 * c < ns) {
 #pragma unroll
@@ -231,20 +238,21 @@ k_undistort_roi(const uint8_t* __restrict__ frames, uint32_t* __restrict__ und, 
                     }
                 }
             }
-            // rotate the chunk slot by half the pixel index: the 16-byte accesses of a quarter warp land in distinct banks
-            tile[threadIdx.x * (NSW / 4) + ((c + (threadIdx.x >> 1)) & (NSW / 4 - 1))] = make_uint4(o[0], o[1], o[2], o[3]);
+            // rotate the chunk slot with the pixel index: the 16-byte accesses of a quarter warp land in distinct banks
+            tile[threadIdx.x * UND_CH + ((c + (threadIdx.x * UND_CH >> 3)) & (UND_CH - 1))] = make_uint4(o[0], o[1], o[2], o[3]);
         }
     }
     __syncthreads();
-    uint32_t* const base = und + (size_t)blockIdx.y * group_words;
+    // the UND_CH chunks of this CTA inside the pixel's 64 bytes: streams s0 .. s0 + UND_SPC - 1 of group s0 / NSW
+    uint32_t* const base = und + (size_t)(s0 / NSW) * group_words + (s0 % NSW);
 #pragma unroll
-    for (int r = 0; r < NSW / 4; ++r) {
+    for (int r = 0; r < UND_CH; ++r) {
         const int e = r * 256 + threadIdx.x;           // (pixel, chunk) in output order
-        const int px = e >> 2, c = e & 3, pp = p0 + px;
+        const int px = e / UND_CH, c = e % UND_CH, pp = p0 + px;
         if (pp >= roi_px) break;
         const int i = pp / d.img_w, j = pp - i * d.img_w;
         uint4* out = reinterpret_cast<uint4*>(base + ((size_t)(i + 1) * (d.img_w + 1) + (j + 1)) * NSW);
-        out[c] = tile[px * (NSW / 4) + ((c + (px >> 1)) & (NSW / 4 - 1))];
+        out[c] = tile[px * UND_CH + ((c + (px * UND_CH >> 3)) & (UND_CH - 1))];
     }
 }
 
@@ -270,7 +278,7 @@ int lt_launch_warp_frame(lt_handle* h, const uint8_t* d_frames, uint8_t* d_bv_rg
 
 int lt_launch_undistort(lt_handle* h, const uint8_t* d_frames, int n, cudaStream_t st) {
     const LtDims& d = h->d;
-    dim3 g(lt_div_up((d.roi1 - d.roi0) * d.img_w, 256), lt_div_up(n, NSW));
+    dim3 g(lt_div_up((d.roi1 - d.roi0) * d.img_w, 256), lt_div_up(n, UND_SPC));
     const int aligned = ((uintptr_t)d_frames & 3) == 0 && ((d.img_w * 3) & 3) == 0;     // word loads need 4-byte aligned rows
     k_undistort_roi<<<g, 256, 0, st>>>(d_frames, h->und_roi, h->und_desc, d, n, aligned, lt_und_group_words(d));
     LT_LAUNCH_CHECK();
