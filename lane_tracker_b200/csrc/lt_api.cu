@@ -138,7 +138,7 @@ extern "C" int lt_destroy(lt_handle* h) {
                       f.merged, f.mask};
         for (void* p : fp) if (p) cudaFree(p);
     }
-    void* ptrs[] = {h->und_map, h->bv_map, h->ov_map, h->bv_desc, h->und_desc, h->lab_yz, h->fused_desc, h->lab_gamma, h->lab_cbrt, h->pixels, h->pix_counts, h->lane_rows,
+    void* ptrs[] = {h->und_map, h->bv_map, h->ov_map, h->bv_desc, h->und_desc, h->lab_yz, h->fused_desc, h->lab_gamma, h->lab_cbrt, h->pixels, h->pix_counts, h->lane_rows, h->lane_bbox, h->dl_bbox,
                     h->avg_x, h->state, h->att, h->retry_list, h->retry_count, h->draw_flags, h->scratch_bv, h->vis_scratch,
                     h->cap_pixels, h->cap_counts, h->cap_cents, h->cap_ncents, h->dl_rows, h->dl_flags, h->txt_state, h->txt_flags,
                     h->txt_tables, h->txt_char_start, h->txt_dy, h->txt_dx, h->txt_lut, h->txt_advance, h->txt_pair_overlap,
@@ -269,7 +269,7 @@ extern "C" int lt_create(const lt_config* cfg, lt_handle** out) {
     if (!rc) rc = alloc_front_set(h, 0);
     if (!rc) select_set(h, 0);
     A(pixels, S * 2 * (size_t)h->pix_cap); A(pix_counts, S * 2);
-    A(lane_rows, S * (size_t)d.bv_h); A(avg_x, S * 2 * (size_t)d.bv_h);
+    A(lane_rows, S * (size_t)d.bv_h); A(lane_bbox, S); A(avg_x, S * 2 * (size_t)d.bv_h);
     A(state, S); A(att, 2 * S); A(retry_list, S); A(retry_count, 1); A(draw_flags, 2 * S);
 #undef A
     if (rc) { lt_destroy(h); return rc; }
@@ -280,6 +280,7 @@ extern "C" int lt_create(const lt_config* cfg, lt_handle** out) {
     }
     cudaMemset(h->avg_x, 0, S * 2 * (size_t)d.bv_h * sizeof(int));
     cudaMemset(h->lane_rows, 0, S * (size_t)d.bv_h * sizeof(int2));
+    cudaMemset(h->lane_bbox, 0, S * sizeof(int4));                 // (rows of zeros = column 0 of every row: box (0, 0, 0, 0) never drawn, draw flag 0)
     cudaMemset(h->draw_flags, 0, 2 * S * sizeof(int));
     cudaMemset(h->retry_count, 0, sizeof(int));
     cudaMemset(h->att, 0, 2 * S * sizeof(LtAttemptOut));
@@ -786,9 +787,11 @@ extern "C" int lt_draw_lane(lt_handle* h, const uint8_t* d_frames, uint8_t* d_ou
     if (!h->dl_rows) {
         if ((rc = dev_alloc(&h->dl_rows, (size_t)h->S * h->d.bv_h))) return rc;
         if ((rc = dev_alloc(&h->dl_flags, (size_t)h->S))) return rc;
+        if ((rc = dev_alloc(&h->dl_bbox, (size_t)h->S))) return rc;
     }
     lt_handle view = *h;
     view.lane_rows = h->dl_rows;
+    view.lane_bbox = h->dl_bbox;
     view.draw_flags = h->dl_flags;
     if ((rc = lt_launch_lane_rows(&view, d_x, d_counts, n, st))) return rc;
     return lt_launch_overlay(&view, d_frames, d_out, n, view.draw_flags, st);
@@ -1011,6 +1014,7 @@ extern "C" int lt_set_state(lt_handle* h, int32_t id, const lt_state* hs, const 
         // lt_launch_lane_rows works on slot 0..n-1; shift the base pointers to this stream
         lt_handle tmp = *h;
         tmp.lane_rows = h->lane_rows + (size_t)id * H;
+        tmp.lane_bbox = h->lane_bbox + id;
         tmp.draw_flags = h->draw_flags + id;
         int rc = lt_launch_lane_rows(&tmp, h->avg_x + (size_t)id * 2 * H, d_counts, 1, 0);
         cudaDeviceSynchronize();

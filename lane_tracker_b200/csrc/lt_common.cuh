@@ -31,7 +31,7 @@ struct LtDims {
 // of the morphological pass that reads the plane, and every stream carries LT_HALO_Y pad rows above and below.
 // The plane pointers in lt_handle address (stream 0, row 0, column 0); negative offsets reach the halo.
 constexpr int LT_HALO_X = 32;     // multiple of 4 (16-byte staging) >= 28
-constexpr int LT_HALO_Y = 48;     // >= 27 + MORPH_RB - 1; the row-padded fast path of k_cross_v needs k + 8
+constexpr int LT_HALO_Y = 56;     // >= 27 + MORPH_RB - 1; the row-padded fast path of k_cross_v needs k + 16
 
 // Undistorted ROI buffer (lt_remap.cu): groups of LT_UND_GROUP streams, stream-minor, zero-bordered; words per group.
 constexpr int LT_UND_GROUP = 16;
@@ -100,6 +100,7 @@ struct lt_handle {
     int pix_cap;
     int* pix_counts;             // [S][2]
     int2* lane_rows;             // [S][bv_h]
+    int4* lane_bbox;             // [S] bounding box of the polygon rows: (min lo, max hi, first row, last row); empty: (W, -1, H, -1)
     int* avg_x;                  // [S][2][bv_h]   averaged polylines (state)
     LtDevState* state;           // [S]
     LtAttemptOut* att;           // [S]
@@ -114,7 +115,7 @@ struct lt_handle {
     uint8_t* txt_tables; int* txt_char_start; short* txt_dy; short* txt_dx; unsigned short* txt_lut; int* txt_advance;
     int txt_nchars, txt_first, txt_parallel_lines;
     int txt_row0, txt_row1;            // frame rows the text lines can touch: [txt_row0, txt_row1)
-    int2* dl_rows; int* dl_flags;      // lazily allocated polygon rows / flags of the lt_draw_lane stage call
+    int2* dl_rows; int* dl_flags; int4* dl_bbox;   // lazily allocated polygon rows / flags / bounding boxes of the lt_draw_lane stage call
     LtDevState* txt_state; int* txt_flags;   // lazily allocated state / flags the lt_draw_text stage call formats from
     unsigned long long* txt_bitmaps;   // [nchars][64] rows of 64 bits: glyph pixel (dy + 32, dx + 8)
     unsigned char* txt_pair_overlap;   // [nchars][nchars]: glyph b drawn right after glyph a shares pixels with it

@@ -511,7 +511,7 @@ k_cross_h_wide(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bi
 // the plane rows each step needs are fetched CV_CHUNK steps ahead so that the loads stay in flight (32-bit row offsets
 // from one base pointer: the address arithmetic is IMAD / IMAD.WIDE on the FMA pipe, the walk itself is ALU-pipe bound).
 // PACKED: k*255 + C*k + 1 < 2^15, the compare is done on both lanes at once with a guard bit.
-// ROWPAD: k + CV_CHUNK <= LT_HALO_Y, every row the walk touches exists in the padded plane (pad rows are zero, which
+// ROWPAD: k + 2 * CV_CHUNK <= LT_HALO_Y, every row the walk touches or prefetches exists in the padded plane (pad rows are zero, which
 //         is the filter's border), so loads carry no bounds logic.
 // Every lane shifts the pass bits of its own column into two registers (one per strip); after 32 rows the warp holds
 // two 32x32 bit matrices column-major, transposes them with five shuffle stages each, and lane r flushes the two
@@ -581,15 +581,21 @@ k_cross_v(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plan
     // together with them), so reading `pointer + j` never needs a wrap test.
     const int R = ring_rows;
     uint32_t* const rl = ring + lane;
-    auto fetch = [&](int slot_row, int r) {            // plane row r -> ring slot (row offsets fit 32 bits)
-        if (ROWPAD) r = min(r, d.bv_h + LT_HALO_Y - 1);                             // (prefetch past the pad rows: never used)
+    // row offsets are taken from the lowest row the band touches as UNSIGNED 32-bit numbers (IMAD.WIDE.U32 on the FMA
+    // pipe; a stream of a padded plane is far below 2^32 bytes)
+    const int rbase = yb0 - k;
+    const uint32_t* Pb = P + rbase * ppitch;
+    asm volatile("" : "+l"(Pb));                       // opaque base: keeps the per-row address a single IMAD.WIDE.U32
+    const int r_last = yb1 + k + CV_CHUNK;             // rows >= r_last are never read by the walk
+    auto fetch = [&](int slot_row, int r) {            // plane row r -> ring slot
         const bool ok = ROWPAD || (unsigned)r < (unsigned)d.bv_h;
-        cp_async4_zfill(rl + slot_row * 32, P + (ok ? r * ppitch : 0), ok);
+        cp_async4_zfill(rl + slot_row * 32, Pb + (unsigned)((ok ? r - rbase : 0) * ppitch), ok);
     };
     auto fetch_chunk = [&](int slot_row, int r0) {     // the CV_CHUNK rows a chunk adds, slot_row is chunk-aligned
+        if (r0 >= r_last) return;
 #pragma unroll
         for (int j = 0; j < CV_CHUNK; ++j) fetch(slot_row + j, r0 + j);
-        if (slot_row == 0) {
+        if (__all_sync(0xFFFFFFFFu, slot_row == 0)) {  // (uniform: a real branch instead of eight predicated copies)
 #pragma unroll
             for (int j = 0; j < CV_CHUNK; ++j) fetch(R + j, r0 + j);                 // mirror of slots 0 .. CV_CHUNK - 1
         }
@@ -957,8 +963,8 @@ static int launch_cross_v(lt_handle* h, const uint32_t* plane, uint32_t* bits, i
     const LtDims& d = h->d;
     const int ppitch = d.pp;
     const size_t pstride = h->stream_pad;
-    const bool packed = cross_packed(k, C), rowpad = pad_rows_zero && k + CV_CHUNK <= LT_HALO_Y;
-    if (plane1 && (cross_packed(k1, C1) != packed || (pad_rows_zero && k1 + CV_CHUNK <= LT_HALO_Y) != rowpad)) {
+    const bool packed = cross_packed(k, C), rowpad = pad_rows_zero && k + 2 * CV_CHUNK <= LT_HALO_Y;
+    if (plane1 && (cross_packed(k1, C1) != packed || (pad_rows_zero && k1 + 2 * CV_CHUNK <= LT_HALO_Y) != rowpad)) {
         int rc = launch_cross_v(h, plane, bits, k, C, n, list, count, st, pad_rows_zero);     // different kernel variants
         if (rc) return rc;
         return launch_cross_v(h, plane1, bits, k1, C1, n, list, count, st, pad_rows_zero);

@@ -194,9 +194,12 @@ constexpr int NSW = LT_UND_GROUP;      // streams per group
 #endif
 constexpr int UND_SPC = LT_UND_SPC;    // streams per CTA: 4, 8 or 16 (a CTA covers UND_SPC / 4 of the four 16-byte chunks of a pixel)
 constexpr int UND_CH = UND_SPC / 4;
+#ifndef LT_UND_MINB
+#define LT_UND_MINB 6
+#endif
 static_assert(UND_SPC == 4 || UND_SPC == 8 || UND_SPC == 16, "streams per CTA");
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, LT_UND_MINB)
 k_undistort_roi(const uint8_t* __restrict__ frames, uint32_t* __restrict__ und, const int2* __restrict__ desc, LtDims d, int n,
                 int aligned, size_t group_words) {
     __shared__ uint4 tile[256 * UND_CH];               // [pixel][chunk of four streams], chunk slot rotated by the pixel
@@ -217,18 +220,28 @@ k_undistort_roi(const uint8_t* __restrict__ frames, uint32_t* __restrict__ und, 
         for (int c = 0; c < UND_CH; ++c) {
             uint32_t o[4] = {0u, 0u, 0u, 0u};
             if (4 * c < ns) {
+                if (fast) {
+                    // all 24 words of the four streams are requested before the first blend needs one
+                    uint32_t a[4][3], b[4][3];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (4 * c + k >= ns) break;
-                    const uint8_t* img = frames + (size_t)(s0 + 4 * c + k) * frame_bytes;
-                    if (fast) {
-                        const uint32_t* w = reinterpret_cast<const uint32_t*>(img) + wi;
-                        const uint32_t a0 = __ldg(w), a1 = __ldg(w + 1), a2 = __ldg(w + 2);
-                        const uint32_t b0 = __ldg(w + wpitch), b1 = __ldg(w + wpitch + 1), b2 = __ldg(w + wpitch + 2);
-                        const uint32_t qa0 = __funnelshift_r(a0, a1, sh), qa1 = __funnelshift_r(a1, a2, sh);     // bytes o..o+3, o+4..o+7
-                        const uint32_t qb0 = __funnelshift_r(b0, b1, sh), qb1 = __funnelshift_r(b1, b2, sh);
+                    for (int k = 0; k < 4; ++k) {
+                        if (4 * c + k >= ns) break;
+                        const uint32_t* w = reinterpret_cast<const uint32_t*>(frames + (size_t)(s0 + 4 * c + k) * frame_bytes) + wi;
+                        a[k][0] = __ldg(w); a[k][1] = __ldg(w + 1); a[k][2] = __ldg(w + 2);
+                        b[k][0] = __ldg(w + wpitch); b[k][1] = __ldg(w + wpitch + 1); b[k][2] = __ldg(w + wpitch + 2);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (4 * c + k >= ns) break;
+                        const uint32_t qa0 = __funnelshift_r(a[k][0], a[k][1], sh), qa1 = __funnelshift_r(a[k][1], a[k][2], sh);     // bytes o..o+3, o+4..o+7
+                        const uint32_t qb0 = __funnelshift_r(b[k][0], b[k][1], sh), qb1 = __funnelshift_r(b[k][1], b[k][2], sh);
                         o[k] = blend_taps(qa0, __funnelshift_r(qa0, qa1, 24), qb0, __funnelshift_r(qb0, qb1, 24), wA, wB);
-                    } else if (m) {
+                    }
+                } else if (m) {
+#pragma unroll 1
+                    for (int k = 0; k < 4; ++k) {
+                        if (4 * c + k >= ns) break;
+                        const uint8_t* img = frames + (size_t)(s0 + 4 * c + k) * frame_bytes;
                         auto tap = [&](uint32_t bit, int off) -> uint32_t {     // BORDER_CONSTANT 0
                             if (!(m & bit)) return 0u;
                             const uint8_t* tp = img + q.x + off;
@@ -647,7 +660,7 @@ __device__ __forceinline__ int lane_tap(const int2* __restrict__ rows, const LtD
 
 __global__ void __launch_bounds__(256)
 k_overlay(const uint8_t* frames, uint8_t* out, const int2* __restrict__ map,
-          const int2* __restrict__ lane_rows, const int* __restrict__ draw, LtDims d, int row0) {
+          const int2* __restrict__ lane_rows, const int4* __restrict__ lane_bbox, const int* __restrict__ draw, LtDims d, int row0) {
     // one thread = 4 pixels = 12 bytes (three aligned 32-bit words); img_w % 4 == 0 is checked at create.
     // `out` may alias `frames` (in-place annotation): every thread reads and writes only its own 12 bytes.
     int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -658,29 +671,39 @@ k_overlay(const uint8_t* frames, uint8_t* out, const int2* __restrict__ map,
     const uint32_t* src = reinterpret_cast<const uint32_t*>(frames + base);
     uint32_t w0 = src[0], w1 = src[1], w2 = src[2];
     if (draw[s] && y >= d.ov0 && y < d.ov1) {
-        const int2* rows = lane_rows + (size_t)s * d.bv_h;
-        uint32_t gch[4] = {(w0 >> 8) & 255, w1 & 255, (w1 >> 24) & 255, (w2 >> 16) & 255};
+        // Q5 canvas coordinates of the four pixels; most of them cannot reach the polygon: one test against its
+        // bounding box (taps of a pixel: columns sx, sx + 1, rows sy, sy + 1) skips the span look-ups
+        const int4* mp = reinterpret_cast<const int4*>(map + (size_t)y * d.img_w + q * 4);
+        const int4 m01 = __ldg(mp), m23 = __ldg(mp + 1);
+        const int4 bb = __ldg(&lane_bbox[s]);
+        const int qx[4] = {m01.x, m01.z, m23.x, m23.z}, qy[4] = {m01.y, m01.w, m23.y, m23.w};
+        const int sx_lo = min(min(qx[0], qx[1]), min(qx[2], qx[3])) >> 5, sx_hi = max(max(qx[0], qx[1]), max(qx[2], qx[3])) >> 5;
+        const int sy_lo = min(min(qy[0], qy[1]), min(qy[2], qy[3])) >> 5, sy_hi = max(max(qy[0], qy[1]), max(qy[2], qy[3])) >> 5;
+        if (sx_hi + 1 >= bb.x && sx_lo <= bb.y && sy_hi + 1 >= bb.z && sy_lo <= bb.w) {
+            const int2* rows = lane_rows + (size_t)s * d.bv_h;
+            uint32_t gch[4] = {(w0 >> 8) & 255, w1 & 255, (w1 >> 24) & 255, (w2 >> 16) & 255};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            Tap4 t = make_taps(__ldg(&map[(size_t)y * d.img_w + q * 4 + k]));
-            // the two taps of a canvas row share its [lo, hi] span: two span loads instead of four
-            const int2 none = make_int2(1, 0);
-            const int2 s0 = ((unsigned)t.sy < (unsigned)d.bv_h) ? __ldg(&rows[t.sy]) : none;
-            const int2 s1 = ((unsigned)(t.sy + 1) < (unsigned)d.bv_h) ? __ldg(&rows[t.sy + 1]) : none;
-            const int xa = t.sx, xb = t.sx + 1;
-            const bool ina = (unsigned)xa < (unsigned)d.bv_w, inb = (unsigned)xb < (unsigned)d.bv_w;
-            int v = ((ina && xa >= s0.x && xa <= s0.y) ? t.w00 : 0) + ((inb && xb >= s0.x && xb <= s0.y) ? t.w01 : 0) +
-                    ((ina && xa >= s1.x && xa <= s1.y) ? t.w10 : 0) + ((inb && xb >= s1.x && xb <= s1.y) ? t.w11 : 0);
-            v = (v * 255 + 512) >> 10;
-            if (v) {
-                // cv2.addWeighted(img,1,lane,0.3,0): float32 a + b*0.3f, round half to even, saturate
-                float f = __fadd_rn((float)gch[k], __fmul_rn((float)v, 0.3f));
-                gch[k] = (uint32_t)min(255, __float2int_rn(f));
+            for (int k = 0; k < 4; ++k) {
+                Tap4 t = make_taps(make_int2(qx[k], qy[k]));
+                // the two taps of a canvas row share its [lo, hi] span: two span loads instead of four
+                const int2 none = make_int2(1, 0);
+                const int2 s0 = ((unsigned)t.sy < (unsigned)d.bv_h) ? __ldg(&rows[t.sy]) : none;
+                const int2 s1 = ((unsigned)(t.sy + 1) < (unsigned)d.bv_h) ? __ldg(&rows[t.sy + 1]) : none;
+                const int xa = t.sx, xb = t.sx + 1;
+                const bool ina = (unsigned)xa < (unsigned)d.bv_w, inb = (unsigned)xb < (unsigned)d.bv_w;
+                int v = ((ina && xa >= s0.x && xa <= s0.y) ? t.w00 : 0) + ((inb && xb >= s0.x && xb <= s0.y) ? t.w01 : 0) +
+                        ((ina && xa >= s1.x && xa <= s1.y) ? t.w10 : 0) + ((inb && xb >= s1.x && xb <= s1.y) ? t.w11 : 0);
+                v = (v * 255 + 512) >> 10;
+                if (v) {
+                    // cv2.addWeighted(img,1,lane,0.3,0): float32 a + b*0.3f, round half to even, saturate
+                    float f = __fadd_rn((float)gch[k], __fmul_rn((float)v, 0.3f));
+                    gch[k] = (uint32_t)min(255, __float2int_rn(f));
+                }
             }
+            w0 = (w0 & 0xFFFF00FFu) | (gch[0] << 8);
+            w1 = (w1 & 0x00FFFF00u) | gch[1] | (gch[2] << 24);
+            w2 = (w2 & 0xFF00FFFFu) | (gch[3] << 16);
         }
-        w0 = (w0 & 0xFFFF00FFu) | (gch[0] << 8);
-        w1 = (w1 & 0x00FFFF00u) | gch[1] | (gch[2] << 24);
-        w2 = (w2 & 0xFF00FFFFu) | (gch[3] << 16);
     }
     uint32_t* dst = reinterpret_cast<uint32_t*>(out + base);
     dst[0] = w0; dst[1] = w1; dst[2] = w2;
@@ -741,7 +764,7 @@ int lt_launch_overlay(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int
     if (!rows_already_copied) { int rc = lt_launch_copy_untouched_rows(h, d_frames, d_out, n, st); if (rc) return rc; }
     if (r1 > r0) {
         dim3 g(lt_div_up(d.img_w / 4, 256), r1 - r0, n);
-        k_overlay<<<g, 256, 0, st>>>(d_frames, d_out, h->ov_map, h->lane_rows, d_draw, d, r0);
+        k_overlay<<<g, 256, 0, st>>>(d_frames, d_out, h->ov_map, h->lane_rows, h->lane_bbox, d_draw, d, r0);
         LT_LAUNCH_CHECK();
     }
     return 0;

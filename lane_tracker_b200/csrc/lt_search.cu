@@ -623,8 +623,10 @@ int lt_launch_select_retry(lt_handle* h, int n, int n_tries, cudaStream_t st) {
 // lane polygon rows (cv2.fillPoly at lane_tracker.py:642-647) from the averaged polylines
 // ---------------------------------------------------------------------------
 
-__device__ void lane_rows_from_polylines(const int* xl, int nl, const int* xr, int nr, int W, int H, int2* rows) {
-    // all threads of the CTA call; xl[i] is the vertex on row H-nl+i
+__device__ void lane_rows_from_polylines(const int* xl, int nl, const int* xr, int nr, int W, int H, int2* rows,
+                                         int4* bbox = nullptr) {
+    // all threads of the CTA call; xl[i] is the vertex on row H-nl+i.  bbox (optional): bounding box of the non-empty
+    // rows, (min lo, max hi, first row, last row) -- lets the overlay skip the frame pixels whose taps cannot hit the polygon.
     for (int y = threadIdx.x; y < H; y += blockDim.x) {
         int lo = W, hi = -1;
         auto cover = [&](int a, int b) { lo = min(lo, max(min(a, b), 0)); hi = max(hi, min(max(a, b), W - 1)); };
@@ -700,6 +702,20 @@ __device__ void lane_rows_from_polylines(const int* xl, int nl, const int* xr, i
         }
     }
     __syncthreads();
+    if (bbox) {
+        __shared__ int sb[4];
+        if (threadIdx.x == 0) { sb[0] = W; sb[1] = -1; sb[2] = H; sb[3] = -1; }
+        __syncthreads();
+        int lo = W, hi = -1, y0 = H, y1 = -1;
+        for (int y = threadIdx.x; y < H; y += blockDim.x) {
+            const int2 r = rows[y];
+            if (r.x <= r.y) { lo = min(lo, r.x); hi = max(hi, r.y); y0 = min(y0, y); y1 = max(y1, y); }
+        }
+        if (hi >= 0) { atomicMin(&sb[0], lo); atomicMax(&sb[1], hi); atomicMin(&sb[2], y0); atomicMax(&sb[3], y1); }
+        __syncthreads();
+        if (threadIdx.x == 0) *bbox = make_int4(sb[0], sb[1], sb[2], sb[3]);
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -709,7 +725,7 @@ __device__ void lane_rows_from_polylines(const int* xl, int nl, const int* xr, i
 __global__ void __launch_bounds__(SEARCH_THREADS)
 k_update_state(LtDims d, lt_config cfg, LtDevState* __restrict__ state, const LtAttemptOut* __restrict__ att1,
                const LtAttemptOut* __restrict__ att2, const int* __restrict__ retry, int* __restrict__ avg_x,
-               int2* __restrict__ lane_rows, int* __restrict__ draw, lt_result* __restrict__ results) {
+               int2* __restrict__ lane_rows, int4* __restrict__ lane_bbox, int* __restrict__ draw, lt_result* __restrict__ results) {
     const int s = blockIdx.x, tid = threadIdx.x, W = d.bv_w, H = d.bv_h;
     extern __shared__ unsigned char smem_raw[];
     int* flags = reinterpret_cast<int*>(smem_raw);        // [H]
@@ -803,7 +819,7 @@ k_update_state(LtDims d, lt_config cfg, LtDevState* __restrict__ state, const Lt
             }
         }
         __syncthreads();
-        lane_rows_from_polylines(xl, st.n_left_avg, xr, st.n_right_avg, W, H, lane_rows + (size_t)s * H);
+        lane_rows_from_polylines(xl, st.n_left_avg, xr, st.n_right_avg, W, H, lane_rows + (size_t)s * H, lane_bbox + s);
     }
     if (tid == 0) {
         int drew = valid ? 1 : ((st.has_avg && st.n_left_avg != 0 && st.last_detection <= cfg.n_fail) ? 1 : 0);
@@ -830,7 +846,7 @@ int lt_launch_update_state(lt_handle* h, int n, lt_result* d_results, int attemp
     size_t smem = (size_t)3 * h->d.bv_h * sizeof(int);
     const int* retry = attempts_allowed >= 2 ? h->draw_flags + h->S : nullptr;
     k_update_state<<<n, SEARCH_THREADS, smem, st>>>(h->d, h->cfg, h->state, h->att, h->att + h->S, retry, h->avg_x,
-                                                    h->lane_rows, h->draw_flags, d_results);
+                                                    h->lane_rows, h->lane_bbox, h->draw_flags, d_results);
     LT_LAUNCH_CHECK();
     return 0;
 }
@@ -945,15 +961,15 @@ int lt_launch_poly_points(lt_handle* h, const double* d_fits, int n, double part
 
 __global__ void __launch_bounds__(SEARCH_THREADS)
 k_lane_rows(LtDims d, const int* __restrict__ xs, const int* __restrict__ counts, int2* __restrict__ lane_rows,
-            int* __restrict__ draw) {
+            int4* __restrict__ lane_bbox, int* __restrict__ draw) {
     const int s = blockIdx.x, H = d.bv_h;
     const int* xl = xs + (size_t)s * 2 * H;
-    lane_rows_from_polylines(xl, counts[s * 2], xl + H, counts[s * 2 + 1], d.bv_w, H, lane_rows + (size_t)s * H);
+    lane_rows_from_polylines(xl, counts[s * 2], xl + H, counts[s * 2 + 1], d.bv_w, H, lane_rows + (size_t)s * H, lane_bbox + s);
     if (threadIdx.x == 0) draw[s] = 1;
 }
 
 int lt_launch_lane_rows(lt_handle* h, const int* d_x, const int* d_counts, int n, cudaStream_t st) {
-    k_lane_rows<<<n, SEARCH_THREADS, 0, st>>>(h->d, d_x, d_counts, h->lane_rows, h->draw_flags);
+    k_lane_rows<<<n, SEARCH_THREADS, 0, st>>>(h->d, d_x, d_counts, h->lane_rows, h->lane_bbox, h->draw_flags);
     LT_LAUNCH_CHECK();
     return 0;
 }
