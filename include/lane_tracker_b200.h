@@ -283,6 +283,14 @@ int lt_bilateral_adaptive_threshold(const uint8_t* d_img, int32_t width, int32_t
 int lt_draw_text(lt_handle* h, uint8_t* d_frames, int32_t n_frames, const int32_t* h_kind, const int64_t* h_radius,
                  const double* h_eccentricity, const int32_t* h_counter, void* stream);
 
+/* ---- ingest (process_video.py:42-44: the reference receives RGB frames from moviepy / ffmpeg) ---- */
+
+/* Decoder output -> the RGB frames lt_process consumes: cv2.cvtColor(nv12, COLOR_YUV2RGB_NV12) (ITU-R BT.601 limited
+ * range, OpenCV's Q20 fixed point, chroma not interpolated), bit-exact.  d_nv12 [n][height * 3 / 2][width] uint8 (luma
+ * plane, then interleaved U, V rows), d_rgb [n][height][width][3].  width % 4 == 0, height even, 4-byte aligned
+ * buffers.  Runs on the current device. */
+int lt_nv12_to_rgb(const uint8_t* d_nv12, uint8_t* d_rgb, int32_t n_frames, int32_t width, int32_t height, void* stream);
+
 /* ---- debug views (lane_tracker.py:675-793, utils.py:57-103; not on the per-frame path) ---- */
 
 /* cv2.warpPerspective(img, M, warped_size) of the RAW frames (lane_tracker.py:1035, the middle panel of the

@@ -112,6 +112,7 @@ SIGNATURES = {
     "lt_bilateral_adaptive_threshold": (C.c_int, [P, i32, i32, C.c_int64, P, C.c_int64, i32, i32, i32, i32, i32, P]),
     "lt_draw_text": (C.c_int, [P, P, i32, P, P, P, P, P]),
     "lt_warp_frame": (C.c_int, [P, P, i32, P, P]),
+    "lt_nv12_to_rgb": (C.c_int, [P, P, i32, i32, i32, P]),
     "lt_visualize_search": (C.c_int, [P, C.POINTER(lt_vis), P, P, P, P, P, P]),
     "lt_resize_linear": (C.c_int, [P, i32, i32, i32, C.c_int64, P, i32, i32, C.c_int64, P]),
     "lt_get_state": (C.c_int, [P, i32, C.POINTER(lt_state), P, P]),

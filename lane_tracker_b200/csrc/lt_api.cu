@@ -669,6 +669,15 @@ extern "C" int lt_remap(lt_handle* h, const uint8_t* d_frames, uint8_t* d_bv_rgb
     return lt_launch_warp(h, d_bv_rgb, n, st);
 }
 
+extern "C" int lt_nv12_to_rgb(const uint8_t* d_nv12, uint8_t* d_rgb, int32_t n, int32_t width, int32_t height, void* stream) {
+    if (!d_nv12 || !d_rgb) { lt_set_error("null argument"); return -1; }
+    if (n < 1 || width < 4 || height < 2 || (width & 3) || (height & 1) || (((uintptr_t)d_nv12 | (uintptr_t)d_rgb) & 3)) {
+        lt_set_error("lt_nv12_to_rgb: width must be a multiple of 4, height even, buffers 4-byte aligned");
+        return -1;
+    }
+    return lt_launch_nv12_to_rgb(d_nv12, d_rgb, n, width, height, (cudaStream_t)stream);
+}
+
 extern "C" int lt_filter_lane_points(lt_handle* h, const uint8_t* d_bv_rgb, uint8_t* d_mask, int32_t n,
                                      int32_t filter_type, int32_t ksize_r, int32_t C_r, int32_t ksize_b, int32_t C_b,
                                      int32_t mask_noise, int32_t ksize_noise, int32_t C_noise, int32_t noise_thresh,

@@ -1,337 +1,14 @@
 // filter_lane_points (lane_tracker.py:183-240) on pair-packed planes:
 //   ellipse top-hat 29 (R) / 55 (Lab b)  -> cross ("bilateral") threshold  \
 //   or box-mean adaptive threshold on the raw planes                        > OR -> open 5x5 -> bit mask
-//
-// The ellipse erosion/dilation is the dominant cost of the whole path.  It is computed by
-// row-span decomposition:  out(y,x) = op_{dy} Hop_{hw[dy]}(y+dy, x)  where
-// Hop_w is the horizontal window min/max of half-width w.  Per source row the CTA builds
-// power-of-two window tables (4, 8, 16, 32) in shared memory; every thread owns one packed
-// column (two image strips in the two u16 lanes), derives the <=17 distinct Hop_w values of
-// the row from two table reads each, and folds them into a K-deep register pipeline
-// A[j] = op(A[j+1], Hop_{hw[j]}) whose head is a finished output row.  All min/max are
-// single VIMNMX(3).U16x2 instructions.
+// The ellipse erosion / dilation / top-hat kernels live in lt_morph.cu; this file holds the thresholds, the 5x5 opening
+// of the bit mask, the layout converters and the launcher of one filter attempt.
 #include <cstdlib>
 #include <cstdio>
-#include <algorithm>
-#include <functional>
-#include <vector>
 #include "lt_common.cuh"
-#include "lt_ellipse.cuh"
 
-// ---------------------------------------------------------------------------
-// the morphology kernel
-// ---------------------------------------------------------------------------
-
-constexpr int MORPH_TW = 192;       // packed columns per CTA (= threads); 3 CTAs/SM x 6 warps at 96 registers/thread
-constexpr int MORPH_CTAS_PER_SM = 3;
-constexpr int MORPH_RB = 8;         // source rows per table build (12 measured the same: fewer barriers, more overrun rows)
-
-template <bool IS_MAX> __device__ __forceinline__ uint32_t op2(uint32_t a, uint32_t b) {
-    return IS_MAX ? __vmaxu2(a, b) : __vminu2(a, b);
-}
-template <bool IS_MAX> __device__ __forceinline__ uint32_t op3(uint32_t a, uint32_t b, uint32_t c) {
-    return IS_MAX ? __vimax3_u16x2(a, b, c) : __vimin3_u16x2(a, b, c);
-}
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-
-// Morphology inputs live in PADDED planes (LtPlane with halo): 32 extra columns on either side of a row hold the
-// seam-stitched neighbours (the two image strips are adjacent in the image) or the operation's pad value, and 36
-// extra rows above and below hold the pad value.  Staging a row block is therefore a plain 16-byte cp.async copy:
-// no bounds checks, no lane fix-up, no registers held across the walk.
-template <int K> struct MorphHa { static constexpr int value = (Ellipse<K>::R + 3) & ~3; };    // staged halo columns per side
-
-template <int K, bool IS_MAX, bool TOPHAT>
-__device__ __forceinline__ void
-morph_body(const uint32_t* __restrict__ src, int src_pitch, uint32_t* __restrict__ dst, int dst_pitch, bool dst_padded,
-           const uint32_t* __restrict__ orig, int orig_pitch, const LtDims& d, int band_rows, int tile, int band) {
-    // The kernel is bound by shared-memory bandwidth, so the window tables are BYTE packed: element (pair m, column c)
-    // is one 32-bit word {a.lo, b.lo, a.hi, b.hi} (a, b = rows 2m, 2m+1; lo, hi = the two strips of the pair plane).
-    // One LDS.32 serves two source rows x two pixels.  The arithmetic stays on 16-bit lanes (VIMNMX.U16x2) by
-    // working at "scale 256": a lane holds value << 8 | junk, and min/max of such lanes orders by the value byte, so
-    // row b's lanes are the table word as loaded and row a's are the word shifted left by 8; the junk byte is dropped
-    // when a result is emitted.  The vertical pipeline advances two rows per step with one VIMNMX3 per accumulator:
-    //     A[j] <- op3(A[j+2], H_a[hw(j+1)], H_b[hw(j)])
-    using E = Ellipse<K>;
-    constexpr int R = E::R;
-    constexpr int TW = MORPH_TW, RB = MORPH_RB, RP = RB / 2, HA = MorphHa<K>::value;
-    constexpr int TE = TW + 2 * HA;         // staged columns per row; column i <-> packed column x0 - HA + i
-    constexpr int TEA = TE + 32;            // table row pitch: + slack for the window reads of the last columns
-    constexpr int TEP = TE + 4;             // raw row pitch: + slack read (never written, never used) by the last T4 columns
-    constexpr bool HAS32 = (2 * R + 1) >= 32;
-    constexpr int NTAB = HAS32 ? 4 : 3;     // T4, T8, T16 (, T32)
-    constexpr uint32_t PADL = IS_MAX ? 0u : 0xFFFFu;
-    constexpr uint32_t PAD2 = PADL | (PADL << 16);
-    static_assert(HA >= R && HA <= LT_HALO_X && R + RB - 1 <= LT_HALO_Y && HA % 4 == 0 && TE % 4 == 0, "staging must be 16-byte granular");
-
-    extern __shared__ uint32_t smem[];
-    uint32_t* T4 = smem;
-    uint32_t* T8 = T4 + RP * TEA;
-    uint32_t* T16 = T8 + RP * TEA;
-    uint32_t* T32 = T16 + RP * TEA;                     // only touched when HAS32
-    uint32_t* T0 = smem + NTAB * RP * TEA;              // [2 buffers][RB rows][TEP] raw source rows (row-major)
-    uint32_t* OG = T0 + 2 * RB * TEP;                    // [2 buffers][RB rows][TW] original rows (top-hat epilogue)
-
-    const int tid = threadIdx.x;
-    const int x0 = tile * TW;
-    const int yb0 = band * band_rows;
-    const int yb1 = min(yb0 + band_rows, d.bv_h);
-    const int r_begin = yb0 - R;
-    const int r_end = yb1 + R;      // exclusive
-    const int nblk = (r_end - r_begin + RB - 1) / RB;
-
-    // Table entries whose window runs past the staged columns are built from whatever follows in shared memory and
-    // are never read by the walk (its windows end at column tid + HA + w <= TE - 1), so nothing needs initialising.
-
-    // ---- staging: rows [rbase, rbase + RB) x columns [x0 - HA, x0 + TW + HA) as 16-byte cp.async, three groups of
-    // 64 threads each taking every third row; the halo columns / pad rows of the padded planes make every address valid
-    constexpr int CH = TE / 4;                                          // 16-byte chunks per staged row
-    static_assert(CH <= 64 && TW == 192 && RB % 4 == 0, "staging thread mapping");
-    const int sg = tid >> 6, sc = tid & 63;
-    const bool s_on = sc < CH;
-    const uint32_t* sp = src + (ptrdiff_t)(r_begin + sg) * src_pitch + (x0 - HA + 4 * sc);    // advances RB rows per block
-    uint32_t* const sdst = T0 + sg * TEP + 4 * sc;
-    // original rows for the top-hat epilogue: 48 chunks per row, thread -> (rows tid / 48, + 4, ..., chunk tid % 48)
-    const int orow = tid / 48, oc = tid - orow * 48;
-    const bool o_on = TOPHAT && x0 + 4 * oc < d.p2;
-    const uint32_t* op = TOPHAT ? orig + (ptrdiff_t)(r_begin - R + orow) * orig_pitch + (x0 + 4 * oc) : nullptr;
-    uint32_t* const odst = OG + orow * TW + 4 * oc;
-    int oy = r_begin - R + orow;                                        // image row of this thread's first original row
-    auto stage_async = [&](int buf) {
-        if (s_on) {
-            uint32_t* t = sdst + buf * RB * TEP;
-#pragma unroll
-            for (int rr = 0; rr < RB; rr += 3)                          // rows sg, sg + 3, sg + 6, ...
-                if (sg + rr < RB) cp_async16(t + rr * TEP, sp + rr * (ptrdiff_t)src_pitch);
-        }
-        sp += (ptrdiff_t)RB * src_pitch;
-        if (TOPHAT) {
-            uint32_t* t = odst + buf * RB * TW;
-#pragma unroll
-            for (int rr = 0; rr < RB; rr += 4)                          // rows orow, orow + 4, ...
-                if (o_on && (unsigned)(oy + rr) < (unsigned)d.bv_h) cp_async16(t + rr * TW, op + rr * (ptrdiff_t)orig_pitch);
-            op += (ptrdiff_t)RB * orig_pitch;
-            oy += RB;
-        }
-        cp_async_commit();
-    };
-    stage_async(0);
-
-    // ---- output addressing: one running pointer per thread; threads next to the seam also own one halo column
-    const int gx = x0 + tid;                       // this thread's packed column
-    const bool col_ok = gx < d.p2;
-    const uint32_t lane_mask = (gx + d.p2 < d.bv_w) ? 0xFFFFFFFFu : 0x0000FFFFu;
-    // halo copy for the pass that reads a padded dst (pad 0): column gx - p2 = {0, v.lo}, column gx + p2 = {v.hi, 0}
-    int hoff = 0;
-    uint32_t hsel = 0;
-    if (dst_padded && col_ok) {
-        if (gx >= d.p2 - LT_HALO_X) { hoff = -d.p2; hsel = 0x1044u; }
-        else if (gx < LT_HALO_X) { hoff = d.p2; hsel = 0x4432u; }
-    }
-    uint32_t* dp = dst + (ptrdiff_t)(yb0 - 2 * R) * dst_pitch + gx;     // row of the first (unemitted) walk output
-
-    uint32_t A[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) A[j] = PAD2;
-
-    // a table word seen as the scale-256 lanes of row a (.x) and row b (.y)
-    auto lanes = [](uint32_t t) { return make_uint2(t << 8, t); };
-    auto pack = [](uint2 v) { return __byte_perm(v.x, v.y, 0x7351); };          // value bytes back to {a.lo, b.lo, a.hi, b.hi}
-    auto o2 = [](uint2 a, uint2 b) { return make_uint2(op2<IS_MAX>(a.x, b.x), op2<IS_MAX>(a.y, b.y)); };
-    auto o3 = [](uint2 a, uint2 b, uint2 c) { return make_uint2(op3<IS_MAX>(a.x, b.x, c.x), op3<IS_MAX>(a.y, b.y, c.y)); };
-
-    // table columns beyond the thread's own: the 2*HA halo columns of the RP row pairs, spread over the threads
-    constexpr int NX = 2 * HA * RP;
-    constexpr int NXT = (NX + TW - 1) / TW;
-    auto halo_elem = [&](int q, int& pr, int& col) -> bool {
-        const int e = tid + q * TW;
-        pr = e / (2 * HA);
-        const int k = e - pr * 2 * HA;
-        col = k < HA ? k : TW + k;                                       // left halo 0..HA-1, right halo TW+HA..TE-1
-        return e < NX;
-    };
-
-    for (int blk = 0; blk < nblk; ++blk) {
-        const int rb0 = r_begin + blk * RB;
-        const uint32_t* Tc = T0 + (blk & 1) * RB * TEP;                  // this block's source rows
-        cp_async_wait_all();
-        __syncthreads();                                                 // rows landed; previous walk finished
-        if (blk + 1 < nblk) stage_async((blk + 1) & 1);
-        // window tables: T4 (from the raw rows) -> T8, T16, T32
-        auto build4 = [&](int pr, int col, int idx) {
-            const uint32_t* ra = Tc + (2 * pr) * TEP + col;
-            const uint32_t* rb = ra + TEP;
-            // raw lanes are plain values (or the 16-bit pad): their low bytes are the table bytes
-            T4[idx] = __byte_perm(op2<IS_MAX>(op3<IS_MAX>(ra[0], ra[1], ra[2]), ra[3]),
-                                  op2<IS_MAX>(op3<IS_MAX>(rb[0], rb[1], rb[2]), rb[3]), 0x6240);
-        };
-        auto build81632 = [&](int idx) {
-            const uint32_t* t = T4 + idx;
-            uint2 v8 = o2(lanes(t[0]), lanes(t[4]));
-            uint2 v16 = o3(v8, lanes(t[8]), lanes(t[12]));
-            T8[idx] = pack(v8);
-            T16[idx] = pack(v16);
-            if (HAS32) T32[idx] = pack(o3(v16, o2(lanes(t[16]), lanes(t[20])), o2(lanes(t[24]), lanes(t[28]))));
-        };
-#pragma unroll
-        for (int m = 0; m < RP; ++m) build4(m, tid + HA, m * TEA + tid + HA);
-#pragma unroll
-        for (int q = 0; q < NXT; ++q) { int pr, col; if (halo_elem(q, pr, col)) build4(pr, col, pr * TEA + col); }
-        __syncthreads();
-#pragma unroll
-        for (int m = 0; m < RP; ++m) build81632(m * TEA + tid + HA);
-#pragma unroll
-        for (int q = 0; q < NXT; ++q) { int pr, col; if (halo_elem(q, pr, col)) build81632(pr * TEA + col); }
-        __syncthreads();
-        // walk the RP row pairs of this block
-        const int npair = min(RP, (r_end - rb0 + 1) >> 1);
-        const uint32_t* Ob = OG + (blk & 1) * RB * TW + tid;
-        const uint32_t* Tw = Tc + tid + HA;
-        int base = tid + HA;                        // this thread's column in the tables of pair m
-#pragma unroll 1
-        for (int m = 0; m < npair; ++m, base += TEA, Tw += 2 * TEP, Ob += 2 * TW, dp += 2 * (ptrdiff_t)dst_pitch) {
-            uint32_t Ha[E::ND], Hb[E::ND];
-#pragma unroll
-            for (int u = 0; u < E::ND; ++u) {
-                const int w = E::uniq(u);
-                const int len = 2 * w + 1;
-                uint2 h;
-                if (w == 0) h = make_uint2(Tw[0] << 8, Tw[TEP] << 8);
-                else if (len >= 32) h = o2(lanes(T32[base - w]), lanes(T32[base + w - 31]));
-                else if (len >= 16) h = o2(lanes(T16[base - w]), lanes(T16[base + w - 15]));
-                else h = o2(lanes(T8[base - w]), lanes(T8[base + w - 7]));
-                Ha[u] = h.x;
-                Hb[u] = h.y;
-            }
-            const uint32_t out_a = op2<IS_MAX>(A[1], Ha[ell_uidx<K>(E::hw(0))]);
-#pragma unroll
-            for (int j = 0; j < K - 2; ++j)
-                A[j] = op3<IS_MAX>(A[j + 2], Ha[ell_uidx<K>(E::hw(j + 1))], Hb[ell_uidx<K>(E::hw(j))]);
-            A[K - 2] = op2<IS_MAX>(Ha[ell_uidx<K>(E::hw(K - 1))], Hb[ell_uidx<K>(E::hw(K - 2))]);
-            A[K - 1] = Hb[ell_uidx<K>(E::hw(K - 1))];
-            // the pair completes output rows ya = rb0 + 2m - R (dp points at it) and ya + 1
-            const int ya = rb0 + 2 * m - R;
-            if (ya + 1 < yb0 || ya >= yb1 || !col_ok) continue;
-            uint32_t va = __byte_perm(out_a, 0, 0x4341), vb = __byte_perm(A[0], 0, 0x4341);   // scale 256 -> plain values
-            if (TOPHAT) { va = Ob[0] - va; vb = Ob[TW] - vb; }          // open <= src per lane: no borrow between lanes
-            va &= lane_mask;                                             // hi lane beyond the image: 0 (the pad of the
-            vb &= lane_mask;                                             // dilation that consumes an eroded plane)
-            uint32_t* const pb = dp + dst_pitch;
-            const bool ea = ya >= yb0, eb = ya + 1 < yb1;
-            if (ea) dp[0] = va;
-            if (eb) pb[0] = vb;
-            if (dst_padded && hsel) {                                    // seam-stitched halo copies for the next pass
-                if (ea) dp[hoff] = __byte_perm(va, 0, hsel);
-                if (eb) pb[hoff] = __byte_perm(vb, 0, hsel);
-            }
-        }
-        dp += 2 * (ptrdiff_t)(RP - npair) * dst_pitch;                   // (only the last block is short)
-    }
-}
-
-// One launch erodes (or dilates) BOTH planes: the 55x55 work items of the Lab-b plane come first, the lighter
-// 29x29 items of the R plane fill the slots they leave free, so the grid packs the SMs without a second wave.
-struct MorphJob {
-    const uint32_t* src; uint32_t* dst; const uint32_t* orig;     // src, orig: padded planes (pitch d.pp)
-    int bands, band_rows;
-};
-
-template <int K>
-constexpr size_t morph_smem_bytes(bool tophat) {
-    constexpr int R = Ellipse<K>::R;
-    constexpr int TE = MORPH_TW + 2 * MorphHa<K>::value;
-    constexpr int NTAB = (2 * R + 1 >= 32) ? 4 : 3;
-    return ((size_t)NTAB * (MORPH_RB / 2) * (TE + 32) + (size_t)2 * MORPH_RB * (TE + 4) +
-            (tophat ? 2 * MORPH_RB * MORPH_TW : 0)) * sizeof(uint32_t);
-}
-
-template <bool IS_MAX, bool TOPHAT>
-__global__ void __launch_bounds__(MORPH_TW, MORPH_CTAS_PER_SM)
-k_morph_pair(MorphJob j55, MorphJob j29, LtDims d, int tiles, int n, size_t src_stride, size_t dst_stride,
-             const int* __restrict__ list, const int* __restrict__ count) {
-    int item = blockIdx.x;
-    const int n55 = n * tiles * j55.bands;
-    const bool big = item < n55;
-    const MorphJob& j = big ? j55 : j29;
-    if (!big) item -= n55;
-    const int slot = item % n;                 // stream slot fastest: neighbouring CTAs share the shared tables' L2 lines
-    const int tb = item / n;
-    const int tile = tb % tiles, band = tb / tiles;
-    if (count != nullptr && slot >= *count) return;
-    const int s = list ? list[slot] : slot;
-    // all planes are padded; only the eroded planes (read by the dilation) need their column halos written
-    const uint32_t* src = j.src + (size_t)s * src_stride;
-    uint32_t* dst = j.dst + (size_t)s * dst_stride;
-    const uint32_t* orig = TOPHAT ? j.orig + (size_t)s * src_stride : nullptr;
-    const int dst_pitch = d.pp;
-    if (big) morph_body<55, IS_MAX, TOPHAT>(src, d.pp, dst, dst_pitch, !TOPHAT, orig, d.pp, d, j.band_rows, tile, band);
-    else morph_body<29, IS_MAX, TOPHAT>(src, d.pp, dst, dst_pitch, !TOPHAT, orig, d.pp, d, j.band_rows, tile, band);
-}
-
-// Pick the band counts of the two jobs by simulating list scheduling of the combined grid on `slots` CTA slots.
-// Per-row costs are the measured relative walk costs of the two structuring elements (profiles/, round 1).
-static void choose_bands(lt_handle* h, int n, int tiles, int H, int slots, int* b55, int* b29) {
-    if (h->bands_key[0] == n && h->bands_key[1] == H && h->bands_key[2] == slots) { *b55 = h->bands_val[0]; *b29 = h->bands_val[1]; return; }
-    int c55 = 1, c29 = 1;
-    double best = 1e300;
-    if (const char* ov = getenv("LT_MORPH_BANDS")) {      // tuning knob: "b55,b29"
-        if (sscanf(ov, "%d,%d", &c55, &c29) == 2 && c55 >= 1 && c29 >= 1) {
-            h->bands_key[0] = n; h->bands_key[1] = H; h->bands_key[2] = slots;
-            h->bands_val[0] = c55; h->bands_val[1] = c29;
-            *b55 = c55; *b29 = c29;
-            return;
-        }
-        c55 = c29 = 1;
-    }
-    std::vector<double> freeat;
-    for (int a = 1; a <= 24; ++a)
-        for (int b = 1; b <= 24; ++b) {
-            int ra = lt_div_up(H, a), rb = lt_div_up(H, b);
-            int na = n * tiles * lt_div_up(H, ra), nb = n * tiles * lt_div_up(H, rb);
-            double ta = (ra + 54) * 0.735, tb = (rb + 28) * 0.513;
-            freeat.assign(slots, 0.0);
-            // CTAs start in grid order on the earliest free slot
-            std::make_heap(freeat.begin(), freeat.end(), std::greater<double>());
-            double makespan = 0.0;
-            for (int i = 0; i < na + nb; ++i) {
-                std::pop_heap(freeat.begin(), freeat.end(), std::greater<double>());
-                double t = freeat.back() + (i < na ? ta : tb);
-                freeat.back() = t;
-                std::push_heap(freeat.begin(), freeat.end(), std::greater<double>());
-                if (t > makespan) makespan = t;
-            }
-            if (makespan < best - 1e-9) { best = makespan; c55 = a; c29 = b; }
-        }
-    h->bands_key[0] = n; h->bands_key[1] = H; h->bands_key[2] = slots;
-    h->bands_val[0] = c55; h->bands_val[1] = c29;
-    *b55 = c55; *b29 = c29;
-}
-
-template <bool IS_MAX, bool TOPHAT>
-static int launch_morph_pair(lt_handle* h, MorphJob j55, MorphJob j29, int n, const int* list, const int* count,
-                             cudaStream_t st) {
-    size_t smem = morph_smem_bytes<55>(TOPHAT) > morph_smem_bytes<29>(TOPHAT) ? morph_smem_bytes<55>(TOPHAT)
-                                                                               : morph_smem_bytes<29>(TOPHAT);
-    int rc = lt_ensure_smem((const void*)k_morph_pair<IS_MAX, TOPHAT>, smem);
-    if (rc) return rc;
-    const LtDims& d = h->d;
-    const int tiles = lt_div_up(d.p2, MORPH_TW);
-    const int slots = MORPH_CTAS_PER_SM * (h->sm_count > 0 ? h->sm_count : 148);
-    int b55, b29;
-    choose_bands(h, n, tiles, d.bv_h, slots, &b55, &b29);
-    j55.band_rows = lt_div_up(d.bv_h, b55); j55.bands = lt_div_up(d.bv_h, j55.band_rows);
-    j29.band_rows = lt_div_up(d.bv_h, b29); j29.bands = lt_div_up(d.bv_h, j29.band_rows);
-    const int grid = n * tiles * (j55.bands + j29.bands);
-    k_morph_pair<IS_MAX, TOPHAT><<<grid, MORPH_TW, smem, st>>>(j55, j29, d, tiles, n, h->stream_pad,
-                                                               h->stream_pad, list, count);
-    LT_LAUNCH_CHECK();
-    return 0;
-}
 
 // ---------------------------------------------------------------------------
 // cross ("bilateral") threshold, bilateral_adaptive_threshold (lane_tracker.py:14-83)
@@ -790,69 +467,64 @@ k_noise_combine(const uint32_t* __restrict__ planeB_all, const uint32_t* __restr
 // open 5x5 ellipse on the bit mask (lane_tracker.py:238): rows [0,2,2,2,0]
 // ---------------------------------------------------------------------------
 
-constexpr int OPEN_ROWS = 32;   // output rows per CTA
+// One lane = one mask word (32 columns), walking down a band of rows with the last rows in registers; the neighbour
+// words come from the adjacent lanes by shuffle.  A warp carries 28 output words and two halo words either side (the
+// erosion of a halo word feeds the dilation of an output word), so nothing goes through shared memory:
+//   A5(y) = AND of the five horizontal shifts of row y            E(y) = M(y-2) & M(y+2) & A5(y-1) & A5(y) & A5(y+1)
+//   O5(y) = OR  of the five horizontal shifts of E(y)           out(y) = E(y-2) | E(y+2) | O5(y-1) | O5(y) | O5(y+1)
+// Outside the image: ones for the erosion (never blocks), zeros for the dilation (cv2.morphologyEx's default border).
+constexpr int OPEN_BAND = 32;   // output rows per CTA (+ 8 warm-up rows: short bands keep enough warps in flight)
+constexpr int OPEN_CORE = 28;   // output words per warp
 
 __device__ __forceinline__ uint32_t shl_bits(uint32_t prev, uint32_t cur, int n) {   // bit x <- bit x-n
-    return (cur << n) | (prev >> (32 - n));
+    return __funnelshift_l(prev, cur, n);
 }
 __device__ __forceinline__ uint32_t shr_bits(uint32_t cur, uint32_t next, int n) {   // bit x <- bit x+n
-    return (cur >> n) | (next << (32 - n));
+    return __funnelshift_r(cur, next, n);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(64)
 k_open5(const uint32_t* __restrict__ in_all, uint32_t* __restrict__ out_all, LtDims d, size_t bits_stride,
         const int* __restrict__ list, const int* __restrict__ count, int nslots) {
     const int nsl = count ? *count : nslots;
-    for (int slot = blockIdx.y; slot < nsl; slot += gridDim.y) {
-    const int s = list ? list[slot] : slot;
-    extern __shared__ uint32_t smem[];
+    const int lane = threadIdx.x & 31, warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int mw = d.mwords;
-    const int y0 = blockIdx.x * OPEN_ROWS;
-    const int nin = OPEN_ROWS + 8, ner = OPEN_ROWS + 4;
-    uint32_t* M = smem;                 // rows y0-4 .. y0+OPEN_ROWS+3, erode padding (ones) applied
-    uint32_t* Er = smem + nin * mw;     // eroded rows y0-2 .. y0+OPEN_ROWS+1, dilate padding (zeros)
-    const uint32_t* in = in_all + (size_t)s * bits_stride;
-    uint32_t* out = out_all + (size_t)s * bits_stride;
-    for (int e = threadIdx.x; e < nin * mw; e += blockDim.x) {
-        int r = e / mw, w = e - r * mw, y = y0 - 4 + r;
-        uint32_t valid = (w * 32 + 32 <= d.bv_w) ? 0xFFFFFFFFu : (w * 32 >= d.bv_w ? 0u : ((1u << (d.bv_w - w * 32)) - 1u));
-        uint32_t v = ((unsigned)y < (unsigned)d.bv_h) ? (__ldg(&in[(size_t)y * mw + w]) & valid) : 0xFFFFFFFFu;
-        M[e] = v | ~valid;              // outside the image never blocks an erosion
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < ner * mw; e += blockDim.x) {
-        int r = e / mw, w = e - r * mw, y = y0 - 2 + r;
-        uint32_t res = 0;
-        if ((unsigned)y < (unsigned)d.bv_h) {
-            const uint32_t* c = M + (r + 2) * mw;     // row y in M
-            res = c[w - 2 * mw] & c[w + 2 * mw];
-#pragma unroll
-            for (int dy = -1; dy <= 1; ++dy) {
-                const uint32_t* q = c + dy * mw;
-                uint32_t cur = q[w], prev = w > 0 ? q[w - 1] : 0xFFFFFFFFu, next = w + 1 < mw ? q[w + 1] : 0xFFFFFFFFu;
-                res &= cur & shl_bits(prev, cur, 1) & shl_bits(prev, cur, 2) & shr_bits(cur, next, 1) & shr_bits(cur, next, 2);
-            }
-            uint32_t valid = (w * 32 + 32 <= d.bv_w) ? 0xFFFFFFFFu : (w * 32 >= d.bv_w ? 0u : ((1u << (d.bv_w - w * 32)) - 1u));
-            res &= valid;
+    const int wd = warp * OPEN_CORE + lane - 2;                         // this lane's mask word
+    if (warp * OPEN_CORE >= mw) return;
+    const bool w_in = wd >= 0 && wd < mw;
+    const uint32_t valid = !w_in ? 0u : (wd * 32 + 32 <= d.bv_w) ? 0xFFFFFFFFu : (wd * 32 >= d.bv_w ? 0u : ((1u << (d.bv_w - wd * 32)) - 1u));
+    const bool emit = lane >= 2 && lane < 2 + OPEN_CORE && w_in;
+    const int y0 = blockIdx.y * OPEN_BAND, y1 = min(y0 + OPEN_BAND, d.bv_h);
+    for (int slot = blockIdx.z; slot < nsl; slot += gridDim.z) {
+        const int s = list ? list[slot] : slot;
+        const uint32_t* in = in_all + (size_t)s * bits_stride + (w_in ? wd : 0);
+        uint32_t* out = out_all + (size_t)s * bits_stride + (w_in ? wd : 0);
+        // rows r = y0 - 4 .. y1 + 3 enter one by one; row r completes E(r - 2) and out(r - 4)
+        uint32_t m1 = ~0u, m2 = ~0u, m3 = ~0u, m4 = ~0u;                // M(r-1) .. M(r-4)
+        uint32_t a1 = ~0u, a2 = ~0u, a3 = ~0u;                          // A5(r-1) .. A5(r-3)
+        uint32_t e1 = 0u, e2 = 0u, e3 = 0u, e4 = 0u;                    // E(r-3) .. E(r-6)
+        uint32_t o1 = 0u, o2 = 0u, o3 = 0u;                             // O5(r-3) .. O5(r-5)
+        uint32_t nxt = ((unsigned)(y0 - 4) < (unsigned)d.bv_h && w_in) ? __ldg(in + (size_t)(y0 - 4) * mw) : 0u;
+#pragma unroll 4
+        for (int r = y0 - 4; r < y1 + 4; ++r) {
+            const bool row_in = (unsigned)r < (unsigned)d.bv_h;
+            const uint32_t m0 = row_in ? ((nxt & valid) | ~valid) : ~0u;
+            nxt = ((unsigned)(r + 1) < (unsigned)d.bv_h && w_in) ? __ldg(in + (size_t)(r + 1) * mw) : 0u;      // one row ahead
+            uint32_t pv = __shfl_up_sync(0xFFFFFFFFu, m0, 1), nx = __shfl_down_sync(0xFFFFFFFFu, m0, 1);
+            const uint32_t a0 = m0 & shl_bits(pv, m0, 1) & shl_bits(pv, m0, 2) & shr_bits(m0, nx, 1) & shr_bits(m0, nx, 2);
+            // E(r - 2): zero on rows outside the image and on columns beyond it
+            const bool e_in = (unsigned)(r - 2) < (unsigned)d.bv_h;
+            const uint32_t e0 = e_in ? (m4 & m0 & a3 & a2 & a1 & valid) : 0u;
+            pv = __shfl_up_sync(0xFFFFFFFFu, e0, 1); nx = __shfl_down_sync(0xFFFFFFFFu, e0, 1);
+            const uint32_t o0 = e0 | shl_bits(pv, e0, 1) | shl_bits(pv, e0, 2) | shr_bits(e0, nx, 1) | shr_bits(e0, nx, 2);
+            // out(r - 4) = E(r-6) | E(r-2) | O5(r-5) | O5(r-4) | O5(r-3)
+            const int yo = r - 4;
+            if (emit && yo >= y0 && yo < y1) out[(size_t)yo * mw] = (e4 | e0 | o3 | o2 | o1) & valid;
+            m4 = m3; m3 = m2; m2 = m1; m1 = m0;
+            a3 = a2; a2 = a1; a1 = a0;
+            e4 = e3; e3 = e2; e2 = e1; e1 = e0;
+            o3 = o2; o2 = o1; o1 = o0;
         }
-        Er[e] = res;                    // rows outside the image: zeros (ignored by the dilation)
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < OPEN_ROWS * mw; e += blockDim.x) {
-        int r = e / mw, w = e - r * mw, y = y0 + r;
-        if (y >= d.bv_h) continue;
-        const uint32_t* c = Er + (r + 2) * mw;
-        uint32_t res = c[w - 2 * mw] | c[w + 2 * mw];
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-            const uint32_t* q = c + dy * mw;
-            uint32_t cur = q[w], prev = w > 0 ? q[w - 1] : 0u, next = w + 1 < mw ? q[w + 1] : 0u;
-            res |= cur | shl_bits(prev, cur, 1) | shl_bits(prev, cur, 2) | shr_bits(cur, next, 1) | shr_bits(cur, next, 2);
-        }
-        uint32_t valid = (w * 32 + 32 <= d.bv_w) ? 0xFFFFFFFFu : (w * 32 >= d.bv_w ? 0u : ((1u << (d.bv_w - w * 32)) - 1u));
-        out[(size_t)y * mw + w] = res & valid;
-    }
-    __syncthreads();
     }
 }
 
@@ -1017,20 +689,10 @@ int lt_launch_filter(lt_handle* h, int n, const LtAttemptParams& p, const int* l
     const LtDims& d = h->d;
     int rc;
     if (p.filter_type == 0) {
-        static const bool legacy = [] { const char* e = getenv("LT_MORPH_IMPL"); return e && e[0] == 'l'; }();
-        if (legacy) {
-            MorphJob e55 = {h->planeB, h->tmpB, nullptr, 0, 0}, e29 = {h->planeR, h->tmpR, nullptr, 0, 0};
-            if ((rc = launch_morph_pair<false, false>(h, e55, e29, n, list, count, st))) return rc;
-            lt_prof_mark(h, ST_ERODE55, st);            // both erosions (55x55 on Lab-b, 29x29 on R) in one launch
-            MorphJob t55 = {h->tmpB, h->topB, h->planeB, 0, 0}, t29 = {h->tmpR, h->topR, h->planeR, 0, 0};
-            if ((rc = launch_morph_pair<true, true>(h, t55, t29, n, list, count, st))) return rc;
-            lt_prof_mark(h, ST_TOPHAT55, st);           // both dilations + top-hat epilogues in one launch
-        } else {
-            if ((rc = lt_launch_morph_pair(h, false, n, list, count, st))) return rc;
-            lt_prof_mark(h, ST_ERODE55, st);            // both erosions (55x55 on Lab-b, 29x29 on R), two concurrent kernels
-            if ((rc = lt_launch_morph_pair(h, true, n, list, count, st))) return rc;
-            lt_prof_mark(h, ST_TOPHAT55, st);           // both dilations + top-hat epilogues
-        }
+        if ((rc = lt_launch_morph_pair(h, false, n, list, count, st))) return rc;
+        lt_prof_mark(h, ST_ERODE55, st);            // both erosions (55x55 on Lab-b, 29x29 on R), two concurrent kernels
+        if ((rc = lt_launch_morph_pair(h, true, n, list, count, st))) return rc;
+        lt_prof_mark(h, ST_TOPHAT55, st);           // both dilations + top-hat epilogues
         if (list == nullptr && h->side) {
             // The four threshold halves (R/Lab-b x horizontal/vertical) only OR bits into the merged mask and each
             // of them fills about half of the issue slots: the horizontal pair runs on a side stream, the vertical
@@ -1061,9 +723,8 @@ int lt_launch_filter(lt_handle* h, int n, const LtAttemptParams& p, const int* l
         LT_LAUNCH_CHECK();
         lt_prof_mark(h, ST_NOISE, st);
     }
-    size_t smem = (size_t)(2 * OPEN_ROWS + 12) * d.mwords * sizeof(uint32_t);
-    dim3 go(lt_div_up(d.bv_h, OPEN_ROWS), list ? (n < 8 ? n : 8) : n);
-    k_open5<<<go, 256, smem, st>>>(h->merged, h->mask, d, h->stream_mask, list, count, n);
+    dim3 go(lt_div_up(lt_div_up(d.mwords, OPEN_CORE), 2), lt_div_up(d.bv_h, OPEN_BAND), list ? (n < 8 ? n : 8) : n);
+    k_open5<<<go, 64, 0, st>>>(h->merged, h->mask, d, h->stream_mask, list, count, n);
     LT_LAUNCH_CHECK();
     lt_prof_mark(h, ST_OPEN5, st);
     return 0;

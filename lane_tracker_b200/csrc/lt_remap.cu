@@ -439,8 +439,11 @@ constexpr int WARP_ITEMS = 64;        // packed columns per pass of a CTA (x 4 s
 #endif
 constexpr int WARP_NB = LT_WARP_NB;   // passes per CTA (the Lab tables are loaded once per CTA)
 
+#ifndef LT_WARP_MINB
+#define LT_WARP_MINB 4
+#endif
 template <bool RGB_OUT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, LT_WARP_MINB)
 k_warp_planes(const uint32_t* __restrict__ und_all, const int2* __restrict__ desc, uint32_t* __restrict__ planeR,
               uint32_t* __restrict__ planeB, uint8_t* __restrict__ bv_rgb, const uint2* __restrict__ yz,
               const unsigned short* __restrict__ cb, LtDims d, unsigned stream_pad, int n, size_t group_words) {
@@ -767,5 +770,56 @@ int lt_launch_overlay(lt_handle* h, const uint8_t* d_frames, uint8_t* d_out, int
         k_overlay<<<g, 256, 0, st>>>(d_frames, d_out, h->ov_map, h->lane_rows, h->lane_bbox, d_draw, d, r0);
         LT_LAUNCH_CHECK();
     }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Decoder output -> RGB frames (the reference gets RGB frames from moviepy / ffmpeg,
+// process_video.py:42-44; a hardware decoder delivers NV12).  cv::cvtColor(COLOR_YUV2RGB_NV12) restated: ITU-R BT.601
+// limited range in Q20 fixed point, one chroma sample per 2x2 block, no interpolation (oracle.cvops.yuv2rgb_nv12,
+// pinned against cv2 in tests/test_oracle_cvops.py).  HBM-bound: 1.5 bytes in, 3 bytes out per pixel.
+// One thread = 4 x 2 pixels: two aligned luma words, one chroma word (two U,V pairs), six RGB words out.
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t sat_q20(int v) { return (uint32_t)min(255, max(0, v >> 20)); }
+
+__global__ void __launch_bounds__(256)
+k_nv12_to_rgb(const uint8_t* __restrict__ nv12, uint8_t* __restrict__ rgb, int w, int h) {
+    const int qx = blockIdx.x * blockDim.x + threadIdx.x;            // group of four columns
+    const int yp = blockIdx.y, s = blockIdx.z;                         // row pair
+    if (qx * 4 >= w) return;
+    const uint8_t* f = nv12 + (size_t)s * w * (h + h / 2);
+    const uint32_t y0 = __ldg(reinterpret_cast<const uint32_t*>(f + (size_t)(2 * yp) * w) + qx);
+    const uint32_t y1 = __ldg(reinterpret_cast<const uint32_t*>(f + (size_t)(2 * yp + 1) * w) + qx);
+    const uint32_t uv = __ldg(reinterpret_cast<const uint32_t*>(f + (size_t)(h + yp) * w) + qx);   // U0 V0 U1 V1
+    int ruv[2], guv[2], buv[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const int u = (int)((uv >> (16 * c)) & 255u) - 128, v = (int)((uv >> (16 * c + 8)) & 255u) - 128;
+        ruv[c] = (1 << 19) + 1673527 * v;
+        guv[c] = (1 << 19) - 852492 * v - 409993 * u;
+        buv[c] = (1 << 19) + 2116026 * u;
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const uint32_t yy = r ? y1 : y0;
+        uint32_t px[4];                                                // R | G << 8 | B << 16
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int y = max(0, (int)((yy >> (8 * i)) & 255u) - 16) * 1220542;
+            const int c = i >> 1;
+            px[i] = sat_q20(y + ruv[c]) | (sat_q20(y + guv[c]) << 8) | (sat_q20(y + buv[c]) << 16);
+        }
+        uint32_t* o = reinterpret_cast<uint32_t*>(rgb + (((size_t)s * h + 2 * yp + r) * w + (size_t)qx * 4) * 3);
+        o[0] = px[0] | (px[1] << 24);
+        o[1] = (px[1] >> 8) | (px[2] << 16);
+        o[2] = (px[2] >> 16) | (px[3] << 8);
+    }
+}
+
+int lt_launch_nv12_to_rgb(const uint8_t* d_nv12, uint8_t* d_rgb, int n, int w, int h, cudaStream_t st) {
+    dim3 g(lt_div_up(w / 4, 256), h / 2, n);
+    k_nv12_to_rgb<<<g, 256, 0, st>>>(d_nv12, d_rgb, w, h);
+    LT_LAUNCH_CHECK();
     return 0;
 }

@@ -476,6 +476,20 @@ class BatchedLaneTracker:
                                            r.ctypes.data_as(C.c_void_p), _ptr(out), _stream_ptr(self.device)))
         return out
 
+    def nv12_to_rgb(self, nv12, out=None):
+        """Decoder output -> the RGB frames ``process`` consumes: ``cv2.cvtColor(f, cv2.COLOR_YUV2RGB_NV12)`` of every
+        frame of a uint8 device tensor [n, H * 3 / 2, W] (luma plane, then interleaved U, V rows), bit-exact.  The
+        reference receives RGB frames from moviepy / ffmpeg (process_video.py:42-44); a hardware decoder delivers NV12."""
+        if nv12.dim() != 3 or nv12.dtype != torch.uint8 or not nv12.is_contiguous() or nv12.shape[1] % 3:
+            raise ValueError("nv12_to_rgb: expected a contiguous uint8 tensor [n, H * 3 / 2, W]")
+        n, h, w = int(nv12.shape[0]), int(nv12.shape[1]) * 2 // 3, int(nv12.shape[2])
+        if out is None:
+            out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=nv12.device)
+        if tuple(out.shape) != (n, h, w, 3) or not out.is_contiguous():
+            raise ValueError("nv12_to_rgb: bad destination layout")
+        check(self.lib.lt_nv12_to_rgb(_ptr(nv12), _ptr(out), n, w, h, _stream_ptr(self.device)))
+        return out
+
     def resize_linear(self, src, dsize, out=None):
         """``cv2.resize(src, dsize)`` (utils.py:88) of a uint8 [h, w] or [h, w, 3] device tensor; ``out`` may be a
         view into a larger canvas (rows strided, pixels contiguous)."""

@@ -578,3 +578,27 @@ def fused_bird_view(frame, K, D, M, bv_width, bv_height):
     out = bilinear_q5(frame, U.astype(np.int32), V.astype(np.int32))
     out[~inside] = 0
     return out
+
+
+# ---------------------------------------------------------------------------
+# decoder output -> RGB frame (the video front end of process_video.py:42-44)
+# ---------------------------------------------------------------------------
+
+# cv::cvtColor(COLOR_YUV2RGB_NV12): ITU-R BT.601, limited range, Q20 fixed point (imgproc/src/color_yuv.simd.hpp,
+# uvToRGBuv / yRGBuvToRGBA); the chroma sample of a 2x2 block is used for all four pixels (no interpolation).
+NV12_CY, NV12_CUB, NV12_CUG, NV12_CVG, NV12_CVR, NV12_SHIFT = 1220542, 2116026, -409993, -852492, 1673527, 20
+
+
+def yuv2rgb_nv12(nv12, width, height):
+    """uint8 [height * 3 / 2, width] NV12 frame (luma plane, then interleaved U, V rows) -> uint8 [height, width, 3] RGB."""
+    nv12 = np.asarray(nv12, dtype=np.uint8).reshape(height * 3 // 2, width)
+    Y = nv12[:height].astype(np.int64)
+    UV = nv12[height:].reshape(height // 2, width // 2, 2).astype(np.int64)
+    u = np.repeat(np.repeat(UV[..., 0], 2, axis=0), 2, axis=1) - 128
+    v = np.repeat(np.repeat(UV[..., 1], 2, axis=0), 2, axis=1) - 128
+    half = 1 << (NV12_SHIFT - 1)
+    y = np.maximum(0, Y - 16) * NV12_CY
+    rgb = np.stack([(y + half + NV12_CVR * v) >> NV12_SHIFT,
+                    (y + half + NV12_CVG * v + NV12_CUG * u) >> NV12_SHIFT,
+                    (y + half + NV12_CUB * u) >> NV12_SHIFT], axis=-1)
+    return np.clip(rgb, 0, 255).astype(np.uint8)

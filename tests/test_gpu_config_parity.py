@@ -312,3 +312,43 @@ def _reference_bilateral(img, ksize=30, C=0, mode='floor', true_value=255, false
     else:
         mask[((0 < lt_) & (0 < rt_)) | ((0 < ut_) & (0 < dt_))] = true_value
     return mask
+
+
+def test_nv12_ingest_matches_oracle_and_feeds_process(torch_mod):
+    """lt_nv12_to_rgb: decoder output -> RGB frames, bit-exact with the oracle restatement of
+    cv2.cvtColor(COLOR_YUV2RGB_NV12); the converted frames then go through process() like any other frame."""
+    from lane_tracker_b200 import BatchedLaneTracker
+    from oracle import cvops
+    torch = torch_mod
+    rng = np.random.default_rng(5)
+    H, W = 720, 1280
+    nv = rng.integers(0, 256, (3, H * 3 // 2, W), dtype=np.uint8)
+    nv[0, :2, :8] = [[0, 255, 16, 235, 15, 17, 1, 254]] * 2          # luma extremes
+    nv[0, H, :8] = [0, 0, 255, 255, 0, 255, 255, 0]                  # chroma extremes: every channel saturates
+    # frame 2: a rendered road frame taken through an RGB -> NV12 round trip (what a camera / decoder delivers)
+    vid = synth.RoadVideo(3)
+    rgb = vid.frame(0).astype(np.float64)
+    y = 16 + (65.481 * rgb[..., 0] + 128.553 * rgb[..., 1] + 24.966 * rgb[..., 2]) / 255
+    cb = 128 + (-37.797 * rgb[..., 0] - 74.203 * rgb[..., 1] + 112.0 * rgb[..., 2]) / 255
+    cr = 128 + (112.0 * rgb[..., 0] - 93.786 * rgb[..., 1] - 18.214 * rgb[..., 2]) / 255
+    nv[2, :H] = np.clip(np.rint(y), 0, 255)
+    sub = lambda c: c.reshape(H // 2, 2, W // 2, 2).mean(axis=(1, 3))
+    nv[2, H:] = np.clip(np.rint(np.stack([sub(cb), sub(cr)], axis=-1)), 0, 255).reshape(H // 2, W)
+    trk = BatchedLaneTracker(3, **CAL, device=0)
+    try:
+        got = trk.nv12_to_rgb(torch.as_tensor(nv).cuda())
+        want = np.stack([cvops.yuv2rgb_nv12(f, W, H) for f in nv])
+        assert _mism(got.cpu().numpy(), want) == 0
+        with pytest.raises(ValueError):
+            trk.nv12_to_rgb(torch.zeros((1, 1081, 1280), dtype=torch.uint8, device="cuda"))
+        # the converted frames are ordinary input frames: same result records as the oracle on the same RGB
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            res = trk.process(got, n_tries=1)
+            ref = OracleLaneTracker(**CAL)
+            ref.process(want[2].copy(), n_tries=1)
+        assert bool(res["detected_pixels"][2]) == bool(ref.detected_pixels)
+        assert bool(res["valid_lane_lines"][2]) == bool(ref.valid_lane_lines)
+        assert _mism(trk.debug_read("mask", 2), ref.trace["attempts"][0]["mask"]) == 0
+    finally:
+        trk.close()

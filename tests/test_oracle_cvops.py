@@ -188,3 +188,15 @@ def test_fill_poly_search_bands_leaving_the_canvas():
         checked += 1
         clipped += int((x - bw).min() < 0 or (x + bw).max() > W - 1)
     assert checked > 150 and clipped > 30
+
+
+@pytest.mark.parametrize("shape", [(720, 1280), (1080, 1920), (16, 64)])
+def test_yuv2rgb_nv12(shape):
+    """cv2.cvtColor(COLOR_YUV2RGB_NV12): the colour definition the NV12 ingest kernel (lt_nv12_to_rgb) is pinned to.
+    Random planes plus every (Y, U, V) extreme, so that the saturation of all three channels is exercised."""
+    h, w = shape
+    rng = np.random.default_rng(21)
+    nv = rng.integers(0, 256, (h * 3 // 2, w), dtype=np.uint8)
+    nv[:2, :8] = [[0, 255, 16, 235, 15, 17, 1, 254]] * 2
+    nv[h, :8] = [0, 0, 255, 255, 0, 255, 255, 0]
+    assert np.array_equal(cvops.yuv2rgb_nv12(nv, w, h), cv2.cvtColor(nv, cv2.COLOR_YUV2RGB_NV12))

@@ -34,7 +34,7 @@ def one():
     e1.record()
     torch.cuda.synchronize()
     st, calls = trk.profile_read()
-    print(json.dumps({"impl": os.environ.get("LT_MORPH_IMPL", "new"), "bands": os.environ.get("LT_MORPH_BANDS", "auto"), "occ": os.environ.get("LT_MORPH_OCC", "default") + " " + os.environ.get("LT_LIBRARY_VARIANT", "-"),
+    print(json.dumps({"bands": os.environ.get("LT_MORPH_BANDS", "auto"), "occ": os.environ.get("LT_MORPH_OCC", "default") + " " + os.environ.get("LT_LIBRARY_VARIANT", "-"),
                       "chosen": trk.morph_bands(), "ms_per_step": e0.elapsed_time(e1) / n,
                       "stages": {k: round(v / calls, 4) for k, v in st.items() if v > 0}}), flush=True)
 
@@ -42,11 +42,10 @@ def one():
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "--one":
         return one()
-    settings = sys.argv[1:] or ["legacy:auto", "new:auto", "new:2,5", "new:2,4", "new:3,5", "new:3,6", "new:2,6", "new:4,8"]
+    settings = sys.argv[1:] or ["new:auto", "new:2,5", "new:2,4", "new:3,5", "new:3,6", "new:2,6", "new:4,8"]
     for s in settings:
         impl, bands = s.split(":")[:2]
         env = dict(os.environ)
-        env.pop("LT_MORPH_IMPL", None)
         env.pop("LT_MORPH_BANDS", None)
         env.pop("LT_MORPH_OCC", None)
         if len(s.split(":")) > 2:
@@ -55,8 +54,6 @@ def main():
         env.pop("LT_LIBRARY_VARIANT", None)
         if len(s.split(":")) > 3 and s.split(":")[3]:
             env["LT_LIBRARY_VARIANT"] = s.split(":")[3]
-        if impl == "legacy":
-            env["LT_MORPH_IMPL"] = "legacy"
         if bands != "auto":
             env["LT_MORPH_BANDS"] = bands
         subprocess.run([sys.executable, os.path.abspath(__file__), "--one"], env=env, check=False)
