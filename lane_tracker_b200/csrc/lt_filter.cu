@@ -420,9 +420,9 @@ k_box_v(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plane1
             const uint32_t n = (uint32_t)(2 * half + 1) * (uint32_t)(2 * half + 1);
             for (int y = yb0; y < yb1; ++y) {
                 uint32_t p = __ldg(&P[(size_t)y * ppitch]);
-                int ml = (int)((2u * Sl + n) / (2u * n)), mh = (int)((2u * Sh + n) / (2u * n));
-                bool pl_ = ((int)(p & 0xFFFFu) - ml) > c;
-                bool ph = hi_ok && (((int)(p >> 16) - mh) > c);
+                // mean = floor((2S + n) / 2n) (rounded box mean); p - mean > c  <=>  2S + n < 2n (p - c): no division
+                bool pl_ = (int)(2u * Sl + n) < (int)(2u * n) * ((int)(p & 0xFFFFu) - c);
+                bool ph = hi_ok && ((int)(2u * Sh + n) < (int)(2u * n) * ((int)(p >> 16) - c));
                 uint32_t bl = __ballot_sync(0xFFFFFFFFu, pl_), bh = __ballot_sync(0xFFFFFFFFu, ph);
                 const int g = (y - yb0) >> 5;
                 if (lane == ((y - yb0) & 31)) { kl[g] |= bl; kh[g] |= bh; }
