@@ -473,7 +473,8 @@ k_noise_combine(const uint32_t* __restrict__ planeB_all, const uint32_t* __restr
 //   A5(y) = AND of the five horizontal shifts of row y            E(y) = M(y-2) & M(y+2) & A5(y-1) & A5(y) & A5(y+1)
 //   O5(y) = OR  of the five horizontal shifts of E(y)           out(y) = E(y-2) | E(y+2) | O5(y-1) | O5(y) | O5(y+1)
 // Outside the image: ones for the erosion (never blocks), zeros for the dilation (cv2.morphologyEx's default border).
-constexpr int OPEN_BAND = 32;   // output rows per CTA (+ 8 warm-up rows: short bands keep enough warps in flight)
+constexpr int OPEN_BAND = 32;   // output rows per CTA (+ 8 warm-up rows: short bands keep enough warps in flight);
+constexpr int OPEN_BAND_FEW = 8;   // with only a few streams the walk is pure latency: shorter bands, more warps
 constexpr int OPEN_CORE = 28;   // output words per warp
 
 __device__ __forceinline__ uint32_t shl_bits(uint32_t prev, uint32_t cur, int n) {   // bit x <- bit x-n
@@ -485,7 +486,7 @@ __device__ __forceinline__ uint32_t shr_bits(uint32_t cur, uint32_t next, int n)
 
 __global__ void __launch_bounds__(64)
 k_open5(const uint32_t* __restrict__ in_all, uint32_t* __restrict__ out_all, LtDims d, size_t bits_stride,
-        const int* __restrict__ list, const int* __restrict__ count, int nslots) {
+        const int* __restrict__ list, const int* __restrict__ count, int nslots, int band) {
     const int nsl = count ? *count : nslots;
     const int lane = threadIdx.x & 31, warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int mw = d.mwords;
@@ -494,7 +495,7 @@ k_open5(const uint32_t* __restrict__ in_all, uint32_t* __restrict__ out_all, LtD
     const bool w_in = wd >= 0 && wd < mw;
     const uint32_t valid = !w_in ? 0u : (wd * 32 + 32 <= d.bv_w) ? 0xFFFFFFFFu : (wd * 32 >= d.bv_w ? 0u : ((1u << (d.bv_w - wd * 32)) - 1u));
     const bool emit = lane >= 2 && lane < 2 + OPEN_CORE && w_in;
-    const int y0 = blockIdx.y * OPEN_BAND, y1 = min(y0 + OPEN_BAND, d.bv_h);
+    const int y0 = blockIdx.y * band, y1 = min(y0 + band, d.bv_h);
     for (int slot = blockIdx.z; slot < nsl; slot += gridDim.z) {
         const int s = list ? list[slot] : slot;
         const uint32_t* in = in_all + (size_t)s * bits_stride + (w_in ? wd : 0);
@@ -723,8 +724,10 @@ int lt_launch_filter(lt_handle* h, int n, const LtAttemptParams& p, const int* l
         LT_LAUNCH_CHECK();
         lt_prof_mark(h, ST_NOISE, st);
     }
-    dim3 go(lt_div_up(lt_div_up(d.mwords, OPEN_CORE), 2), lt_div_up(d.bv_h, OPEN_BAND), list ? (n < 8 ? n : 8) : n);
-    k_open5<<<go, 64, 0, st>>>(h->merged, h->mask, d, h->stream_mask, list, count, n);
+    const int zs = list ? (n < 8 ? n : 8) : n;
+    const int band = zs >= 16 ? OPEN_BAND : OPEN_BAND_FEW;
+    dim3 go(lt_div_up(lt_div_up(d.mwords, OPEN_CORE), 2), lt_div_up(d.bv_h, band), zs);
+    k_open5<<<go, 64, 0, st>>>(h->merged, h->mask, d, h->stream_mask, list, count, n, band);
     LT_LAUNCH_CHECK();
     lt_prof_mark(h, ST_OPEN5, st);
     return 0;
