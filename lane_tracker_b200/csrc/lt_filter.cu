@@ -357,41 +357,79 @@ k_cross_v(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plan
 // box sum with replicated border = row sums (k_box_h) then running column sums (k_box_v)
 // ---------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(ROWK_WARPS * 32)
+// Row sums: the tile scheme of k_cross_h.  A CTA stages 32 rows of a raw plane as (lo, hi) byte pairs, builds the
+// `half` halo entries either side of a row in shared memory -- BORDER_REPLICATE at the image edges (the first / last
+// pixel of the row), the neighbouring strip at the seam -- and thread (row = lane, segment = warp) walks its segment
+// with ONE running window sum per lane (packed u16x2: <= 255 * 255 fits), storing four sums per 16-byte store.
+__global__ void __launch_bounds__(CROSSH_WARPS * 32)
 k_box_h(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plane1, uint32_t* __restrict__ hs0,
-        uint32_t* __restrict__ hs1, LtDims d, int half0, int half1,
+        uint32_t* __restrict__ hs1, LtDims d, int half0, int half1, int pitch0, int pitch1,
         int ppitch, size_t plane_stride, size_t hs_stride, const int* __restrict__ list, const int* __restrict__ count, int nslots) {
     extern __shared__ uint32_t smem[];
+    unsigned short* tile = reinterpret_cast<unsigned short*>(smem);     // [32][pitch], entry i <-> packed column i - K
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int y = blockIdx.x * ROWK_WARPS + warp;
-    if (y >= d.bv_h) return;
-    const int wpad = (d.bv_w + 32) & ~31;
-    uint32_t* lin = smem + (size_t)warp * 2 * wpad;
-    uint32_t* E = lin + wpad;
     const int nsl = count ? *count : nslots;          // attempt-2 launches loop over the (usually empty) retry list
     const uint32_t* plane_all = blockIdx.z ? plane1 : plane0;      // both planes (R, Lab-b) in one launch
     uint32_t* hs_all = blockIdx.z ? hs1 : hs0;
-    const int half = blockIdx.z ? half1 : half0;
+    const int half = blockIdx.z ? half1 : half0, pitch = blockIdx.z ? pitch1 : pitch0;
+    const int K = (half + 2) & ~1;                    // even and > half: packed column 0 starts a 32-bit word
+    const int y0 = blockIdx.x * CROSSH_ROWS;
+    const int xint = d.bv_w - d.p2;                   // high lanes of columns >= xint lie beyond the image
+    const int nw = d.p2 >> 5;
+    const int w0 = (warp * nw) / CROSSH_WARPS, w1 = ((warp + 1) * nw) / CROSSH_WARPS;
     for (int slot = blockIdx.y; slot < nsl; slot += gridDim.y) {
         const int s = list ? list[slot] : slot;
-        warp_row_prefix(plane_all + (size_t)s * plane_stride + (size_t)y * ppitch, d, lin, E, lane);
-        uint32_t* hrow = hs_all + (size_t)s * hs_stride + (size_t)y * ppitch;
-        const int W = d.bv_w;
-        const uint32_t first = lin[0], last = lin[W - 1];
-        auto rowsum = [&](int c) -> uint32_t {
-            uint32_t v = E[min(c + half + 1, W)] - E[max(c - half, 0)];
-            v += (uint32_t)max(half - c, 0) * first + (uint32_t)max(c + half - (W - 1), 0) * last;
-            return v;
-        };
-        for (int x = lane; x < d.p2; x += 32) {
-            uint32_t lo = rowsum(x), hi = (x + d.p2 < W) ? rowsum(x + d.p2) : 0u;
-            hrow[x] = lo | (hi << 16);
+        const uint32_t* src = plane_all + (size_t)s * plane_stride + y0 * ppitch;
+        {
+            // rows below the plane are pad rows of the padded layout: valid addresses, results dropped
+            constexpr int RPW = CROSSH_ROWS / CROSSH_WARPS;
+            for (int g0 = lane * 4; g0 < d.p2; g0 += 128) {
+                uint4 v[RPW];
+#pragma unroll
+                for (int j = 0; j < RPW; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(src + (warp + j * CROSSH_WARPS) * ppitch + g0));
+#pragma unroll
+                for (int j = 0; j < RPW; ++j) {
+                    uint32_t* o = reinterpret_cast<uint32_t*>(tile + (warp + j * CROSSH_WARPS) * pitch + K + g0);
+                    o[0] = __byte_perm(v[j].x, v[j].y, 0x6420);             // {lo0, hi0, lo1, hi1}
+                    o[1] = __byte_perm(v[j].z, v[j].w, 0x6420);
+                }
+            }
         }
-        __syncwarp();
+        __syncthreads();
+        {
+            const int nfix = d.p2 - xint, per_row = 2 * half + 1 + nfix;
+            for (int e = threadIdx.x; e < CROSSH_ROWS * per_row; e += blockDim.x) {
+                const int r = e / per_row, j = e - r * per_row;
+                unsigned short* t = tile + r * pitch + K;
+                const uint32_t first = t[0] & 0xFFu, last = t[xint - 1] >> 8;         // image columns 0 and bv_w - 1
+                if (j < nfix) t[xint + j] = (unsigned short)((t[xint + j] & 0xFFu) | (last << 8));
+                else if (j < nfix + half) { const int q = j - nfix + 1; t[-q] = (unsigned short)(first | ((t[d.p2 - q] & 0xFFu) << 8)); }
+                else { const int q = j - nfix - half; t[d.p2 + q] = (unsigned short)((q < xint ? t[q] >> 8 : last) | (last << 8)); }
+            }
+        }
+        __syncthreads();
+        if (w0 < w1 && y0 + lane < d.bv_h) {
+            const unsigned short* trow = tile + lane * pitch + K;
+            uint32_t* hrow = hs_all + (size_t)s * hs_stride + (size_t)(y0 + lane) * ppitch;
+            int x = w0 * 32;
+            uint32_t S = 0;
+            for (int i = -half; i <= half; ++i) S += unpack_pair(trow[x + i]);
+            for (; x < w1 * 32; x += 4) {
+                uint32_t o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    o[k] = S;
+                    S = S + unpack_pair(trow[x + k + half + 1]) - unpack_pair(trow[x + k - half]);
+                }
+                *reinterpret_cast<uint4*>(hrow + x) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+        __syncthreads();                              // the tile is reused by the next slot
     }
 }
 
 constexpr int BOXV_BAND = 64;        // rows per CTA (two 32-row groups)
+constexpr int BOXV_CHUNK = 8;        // rows whose loads are in flight together
 
 __global__ void __launch_bounds__(32)
 k_box_v(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plane1, const uint32_t* __restrict__ hs0,
@@ -414,21 +452,37 @@ k_box_v(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plane1
             const uint32_t* P = (pl ? plane1 : plane0) + (size_t)s * plane_stride + x;
             const uint32_t* Hs = (pl ? hs1 : hs0) + (size_t)s * hs_stride + x;
             const int half = pl ? half1 : half0, c = pl ? c1 : c0;
-            auto ldh = [&](int r) -> uint32_t { r = max(0, min(d.bv_h - 1, r)); return __ldg(&Hs[(size_t)r * ppitch]); };
+            auto ldh = [&](int r) -> uint32_t { r = max(0, min(d.bv_h - 1, r)); return __ldg(&Hs[r * ppitch]); };   // BORDER_REPLICATE
             uint32_t Sl = 0, Sh = 0;
-            for (int dy = -half; dy <= half; ++dy) { uint32_t v = ldh(yb0 + dy); Sl += v & 0xFFFFu; Sh += v >> 16; }
+            for (int dy0 = -half; dy0 <= half; dy0 += BOXV_CHUNK) {
+                uint32_t v[BOXV_CHUNK];
+#pragma unroll
+                for (int j = 0; j < BOXV_CHUNK; ++j) v[j] = (dy0 + j <= half) ? ldh(yb0 + dy0 + j) : 0u;
+#pragma unroll
+                for (int j = 0; j < BOXV_CHUNK; ++j) { Sl += v[j] & 0xFFFFu; Sh += v[j] >> 16; }
+            }
             const uint32_t n = (uint32_t)(2 * half + 1) * (uint32_t)(2 * half + 1);
-            for (int y = yb0; y < yb1; ++y) {
-                uint32_t p = __ldg(&P[(size_t)y * ppitch]);
-                // mean = floor((2S + n) / 2n) (rounded box mean); p - mean > c  <=>  2S + n < 2n (p - c): no division
-                bool pl_ = (int)(2u * Sl + n) < (int)(2u * n) * ((int)(p & 0xFFFFu) - c);
-                bool ph = hi_ok && ((int)(2u * Sh + n) < (int)(2u * n) * ((int)(p >> 16) - c));
-                uint32_t bl = __ballot_sync(0xFFFFFFFFu, pl_), bh = __ballot_sync(0xFFFFFFFFu, ph);
-                const int g = (y - yb0) >> 5;
-                if (lane == ((y - yb0) & 31)) { kl[g] |= bl; kh[g] |= bh; }
-                uint32_t a = ldh(y + half + 1), b = ldh(y - half);
-                Sl += (a & 0xFFFFu) - (b & 0xFFFFu);
-                Sh += (a >> 16) - (b >> 16);
+            for (int yc = yb0; yc < yb1; yc += BOXV_CHUNK) {
+                uint32_t p[BOXV_CHUNK], a[BOXV_CHUNK], b[BOXV_CHUNK];
+#pragma unroll
+                for (int j = 0; j < BOXV_CHUNK; ++j) {
+                    p[j] = __ldg(&P[min(yc + j, d.bv_h - 1) * ppitch]);
+                    a[j] = ldh(yc + j + half + 1);
+                    b[j] = ldh(yc + j - half);
+                }
+#pragma unroll
+                for (int j = 0; j < BOXV_CHUNK; ++j) {
+                    const int y = yc + j;
+                    // mean = floor((2S + n) / 2n) (rounded box mean); p - mean > c  <=>  2S + n < 2n (p - c): no division
+                    const bool ok = y < yb1;
+                    bool pl_ = ok && (int)(2u * Sl + n) < (int)(2u * n) * ((int)(p[j] & 0xFFFFu) - c);
+                    bool ph = ok && hi_ok && ((int)(2u * Sh + n) < (int)(2u * n) * ((int)(p[j] >> 16) - c));
+                    uint32_t bl = __ballot_sync(0xFFFFFFFFu, pl_), bh = __ballot_sync(0xFFFFFFFFu, ph);
+                    const int g = (y - yb0) >> 5;             // (BOXV_BAND = 64: g is 0 or 1 for rows of the band)
+                    if (lane == ((y - yb0) & 31)) { kl[g & 1] |= bl; kh[g & 1] |= bh; }
+                    Sl += (a[j] & 0xFFFFu) - (b[j] & 0xFFFFu);
+                    Sh += (a[j] >> 16) - (b[j] >> 16);
+                }
             }
         }
 #pragma unroll
@@ -670,13 +724,19 @@ static int launch_box_pair(lt_handle* h, int block_r, int c_r, int block_b, int 
     // adaptiveThreshold of the R and the Lab-b plane in two launches (row sums of both, then columns + OR);
     // the top-hat planes, unused by this filter type, hold the row sums
     const LtDims& d = h->d;
-    int wpad = (d.bv_w + 32) & ~31;
-    size_t smem = (size_t)ROWK_WARPS * 2 * wpad * sizeof(uint32_t);
+    const int half_r = block_r / 2, half_b = block_b / 2;
+    auto box_pitch = [&](int half) {                  // in half-words: 2 * odd, like crossh_pitch
+        int pitch = d.p2 + 2 * ((half + 2) & ~1) + 4;
+        while (((pitch >> 1) & 1) == 0 || (pitch & 1)) ++pitch;
+        return pitch;
+    };
+    const int pitch_r = box_pitch(half_r), pitch_b = box_pitch(half_b);
+    size_t smem = (size_t)CROSSH_ROWS * (pitch_r > pitch_b ? pitch_r : pitch_b) * sizeof(unsigned short);
     { int rc = lt_ensure_smem((const void*)k_box_h, smem); if (rc) return rc; }
     const int zs = list ? (n < 8 ? n : 8) : n;      // retry-list launches: few slots, each CTA loops over the list
-    dim3 gh(lt_div_up(d.bv_h, ROWK_WARPS), zs, 2);
-    k_box_h<<<gh, ROWK_WARPS * 32, smem, st>>>(h->planeR, h->planeB, h->topR, h->topB, d, block_r / 2, block_b / 2, d.pp,
-                                               h->stream_pad, h->stream_pad, list, count, n);
+    dim3 gh(lt_div_up(d.bv_h, CROSSH_ROWS), zs, 2);
+    k_box_h<<<gh, CROSSH_WARPS * 32, smem, st>>>(h->planeR, h->planeB, h->topR, h->topB, d, half_r, half_b, pitch_r, pitch_b, d.pp,
+                                                 h->stream_pad, h->stream_pad, list, count, n);
     LT_LAUNCH_CHECK();
     dim3 gv(d.p2 / 32, lt_div_up(d.bv_h, BOXV_BAND), zs);
     k_box_v<<<gv, 32, 0, st>>>(h->planeR, h->planeB, h->topR, h->topB, h->merged, d, block_r / 2, block_b / 2, c_r, c_b,
