@@ -95,16 +95,17 @@ k_cross_h(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plan
             }
         }
     }
-    __syncthreads();
+    __syncwarp();
     {
+        // every warp finishes the rows it staged itself: high lanes beyond the image, then the two halos
         const int xint = d.bv_w - d.p2;                                  // high lanes of columns >= xint lie beyond the image
-        const int nfix = d.p2 - xint, per_row = 2 * k + 1 + nfix;
-        for (int e = threadIdx.x; e < CROSSH_ROWS * per_row; e += blockDim.x) {
-            const int r = e / per_row, j = e - r * per_row;
+        const int nfix = d.p2 - xint;
+        for (int r = warp; r < CROSSH_ROWS; r += CROSSH_WARPS) {
             unsigned short* t = tile + r * pitch + K;
-            if (j < nfix) t[xint + j] &= 0x00FFu;
-            else if (j < nfix + k) { const int q = j - nfix + 1; t[-q] = (unsigned short)((t[d.p2 - q] & 0xFFu) << 8); }   // column -q
-            else { const int q = j - nfix - k; t[d.p2 + q] = (unsigned short)(q < xint ? t[q] >> 8 : 0u); }               // column p2 + q, q = 0..k
+            for (int j = lane; j < nfix; j += 32) t[xint + j] &= 0x00FFu;
+            __syncwarp();
+            for (int q = lane + 1; q <= k; q += 32) t[-q] = (unsigned short)((t[d.p2 - q] & 0xFFu) << 8);          // column -q
+            for (int q = lane; q <= k; q += 32) t[d.p2 + q] = (unsigned short)(q < xint ? t[q] >> 8 : 0u);          // column p2 + q
         }
     }
     __syncthreads();

@@ -200,3 +200,17 @@ def test_yuv2rgb_nv12(shape):
     nv[:2, :8] = [[0, 255, 16, 235, 15, 17, 1, 254]] * 2
     nv[h, :8] = [0, 0, 255, 255, 0, 255, 255, 0]
     assert np.array_equal(cvops.yuv2rgb_nv12(nv, w, h), cv2.cvtColor(nv, cv2.COLOR_YUV2RGB_NV12))
+
+
+def test_lab_b_never_saturates():
+    """The 8-bit saturation at the end of OpenCV's RGB -> Lab b (lane_tracker.py:208) never triggers: over all 2^24 RGB
+    inputs the value lies well inside [0, 255].  k_warp_planes relies on it (no clamp in its Lab path)."""
+    g, cb = (np.asarray(t, dtype=np.int64) for t in cvops.lab_tables())
+    B = g[np.arange(256)]
+    lo, hi = 1 << 30, -(1 << 30)
+    for R in range(256):
+        Y = (871 * g[R] + 2929 * g[:, None] + 296 * B[None, :] + 2048) >> 12        # [G, B]
+        Z = (73 * g[R] + 448 * g[:, None] + 3575 * B[None, :] + 2048) >> 12
+        v = (200 * (cb[Y] - cb[Z]) + 128 * 32768 + 16384) >> 15
+        lo, hi = min(lo, int(v.min())), max(hi, int(v.max()))
+    assert (lo, hi) == (20, 223)
