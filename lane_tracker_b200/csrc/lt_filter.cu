@@ -396,16 +396,17 @@ k_box_h(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plane1
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();
         {
-            const int nfix = d.p2 - xint, per_row = 2 * half + 1 + nfix;
-            for (int e = threadIdx.x; e < CROSSH_ROWS * per_row; e += blockDim.x) {
-                const int r = e / per_row, j = e - r * per_row;
+            // every warp finishes the rows it staged itself: the high lanes beyond the image, then the two halos
+            const int nfix = d.p2 - xint;
+            for (int r = warp; r < CROSSH_ROWS; r += CROSSH_WARPS) {
                 unsigned short* t = tile + r * pitch + K;
                 const uint32_t first = t[0] & 0xFFu, last = t[xint - 1] >> 8;         // image columns 0 and bv_w - 1
-                if (j < nfix) t[xint + j] = (unsigned short)((t[xint + j] & 0xFFu) | (last << 8));
-                else if (j < nfix + half) { const int q = j - nfix + 1; t[-q] = (unsigned short)(first | ((t[d.p2 - q] & 0xFFu) << 8)); }
-                else { const int q = j - nfix - half; t[d.p2 + q] = (unsigned short)((q < xint ? t[q] >> 8 : last) | (last << 8)); }
+                for (int j = lane; j < nfix; j += 32) t[xint + j] = (unsigned short)((t[xint + j] & 0xFFu) | (last << 8));
+                __syncwarp();
+                for (int q = lane + 1; q <= half; q += 32) t[-q] = (unsigned short)(first | ((t[d.p2 - q] & 0xFFu) << 8));
+                for (int q = lane; q <= half; q += 32) t[d.p2 + q] = (unsigned short)((q < xint ? t[q] >> 8 : last) | (last << 8));
             }
         }
         __syncthreads();

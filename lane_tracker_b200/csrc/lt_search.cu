@@ -101,7 +101,9 @@ struct SearchShared {
 
 // Column histogram of mask rows [r0, r1) for the 32 columns of mask word `w`, written to out[0..31] (int):
 // the rows are added bit-sliced (six carry-save bit planes hold up to 63 rows, then the planes are flushed).
-__device__ void hist_word(const uint32_t* __restrict__ mask, int mwords, int r0, int r1, int w, int* __restrict__ out) {
+// Only the first `nvalid` columns of the word are stored (the last mask word runs past the image: storing all 32
+// counts would spill into the prefix-sum row of the next level, which another thread is filling).
+__device__ void hist_word(const uint32_t* __restrict__ mask, int mwords, int r0, int r1, int w, int nvalid, int* __restrict__ out) {
     int cnt[32];
 #pragma unroll
     for (int b = 0; b < 32; ++b) cnt[b] = 0;
@@ -123,7 +125,8 @@ __device__ void hist_word(const uint32_t* __restrict__ mask, int mwords, int r0,
                             (((p4 >> b) & 1u) << 4) | (((p5 >> b) & 1u) << 5));
     }
 #pragma unroll
-    for (int b = 0; b < 32; ++b) out[b] = cnt[b];
+    for (int b = 0; b < 32; ++b)
+        if (b < nvalid) out[b] = cnt[b];
 }
 
 // In-place: P[0] = 0, P[x + 1] = cnt[0] + ... + cnt[x] for the counts stored at P[1..W]; one warp.
@@ -350,7 +353,7 @@ k_search(LtDims d, LtAttemptParams p, LtSearchArgs a, const LtDevState* __restri
         {   // ---- level 0: one histogram of rows [y0, Hh) serves both sides
             int r0, r1;
             pyslice(y0, Hh, H, r0, r1);
-            for (int w = tid; w < d.mwords; w += blockDim.x) hist_word(mask, d.mwords, r0, r1, w, Pbuf + 1 + w * 32);
+            for (int w = tid; w < d.mwords; w += blockDim.x) hist_word(mask, d.mwords, r0, r1, w, min(32, W - w * 32), Pbuf + 1 + w * 32);
             __syncthreads();
             if (warp == 0) {
                 warp_prefix_inplace(Pbuf, W, lane);
@@ -386,7 +389,7 @@ k_search(LtDims d, LtAttemptParams p, LtSearchArgs a, const LtDevState* __restri
                 const int lv = t / d.mwords, w = t - lv * d.mwords, level = l0 + lv;
                 int r0, r1;
                 pyslice(Hh - (1 + level) * wh, Hh - level * wh, H, r0, r1);
-                hist_word(mask, d.mwords, r0, r1, w, Pbuf + (size_t)lv * PW + 1 + w * 32);
+                hist_word(mask, d.mwords, r0, r1, w, min(32, W - w * 32), Pbuf + (size_t)lv * PW + 1 + w * 32);
             }
             __syncthreads();
             for (int lv = warp; lv < nl; lv += nwarp) warp_prefix_inplace(Pbuf + (size_t)lv * PW, W, lane);

@@ -38,3 +38,9 @@ lt = LaneTracker(**cal)
 for i in range(2):
     canvas = lt.process(vid.frame(i), split_view=True)
 print("debug views ok", canvas.shape)
+
+# decoder output ingest
+nv = torch.from_numpy(np.random.default_rng(1).integers(0, 256, (2, 1080, 1280), dtype=np.uint8)).cuda()
+t = BatchedLaneTracker(2, **cal)
+print("nv12 ok", tuple(t.nv12_to_rgb(nv).shape))
+t.close()
