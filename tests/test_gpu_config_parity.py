@@ -384,3 +384,33 @@ def test_sliding_window_search_sees_the_leftmost_columns(torch_mod):
         assert detected >= 3
     finally:
         trk.close()
+
+
+def test_stream_counts_that_straddle_the_16_stream_groups(torch_mod):
+    """The undistorted buffer is organised in groups of 16 streams and chunks of 4 (lt_remap.cu): stream counts that end
+    inside a chunk of the second group must give every stream the same result as the same frame in slot 0 / 1."""
+    from lane_tracker_b200 import BatchedLaneTracker
+    torch = torch_mod
+    vid = synth.RoadVideo(7)
+    a, b = vid.frame(0), vid.frame(1)
+    for S in (18, 21):
+        frames = np.stack([a if s % 2 == 0 else b for s in range(S)])
+        trk = BatchedLaneTracker(S, **CAL, device=0)
+        try:
+            bv = trk.remap(torch.as_tensor(frames).cuda()).cpu().numpy()
+            for s in range(2, S):
+                assert _mism(bv[s], bv[s % 2]) == 0, (S, s)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                res = trk.process(torch.as_tensor(frames).cuda(), n_tries=1)
+            for s in range(2, S):
+                assert _mism(trk.debug_read("mask", s), trk.debug_read("mask", s % 2)) == 0, (S, s)
+                assert res["n_left"][s] == res["n_left"][s % 2] and res["n_right"][s] == res["n_right"][s % 2], (S, s)
+            # and slot 0 itself against the oracle
+            ref = OracleLaneTracker(**CAL)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                ref.process(a.copy(), n_tries=1)
+            assert _mism(trk.debug_read("mask", 0), ref.trace["attempts"][0]["mask"]) == 0
+        finally:
+            trk.close()
