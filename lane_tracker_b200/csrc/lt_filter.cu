@@ -199,6 +199,7 @@ constexpr int CV_CHUNK = 8;
 #define LT_CV_BAND 288
 #endif
 constexpr int CV_BAND = LT_CV_BAND;  // rows per CTA (multiple of 32)
+constexpr int CV_BAND_FEW = 96;      // ... when fewer than 16 streams are processed (latency, not throughput)
 static_assert(CV_BAND % 32 == 0 && CV_BAND % CV_CHUNK == 0 && 32 % CV_CHUNK == 0, "band geometry");
 
 // w[lane r] bit c  ->  w[lane c] bit r
@@ -238,7 +239,7 @@ template <bool PACKED, bool ROWPAD>
 __global__ void __launch_bounds__(32)
 k_cross_v(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plane1, uint32_t* __restrict__ bits_all, LtDims d,
           int k0, int C0, int k1, int C1, int nslots, int ppitch, size_t plane_stride, size_t bits_stride,
-          const int* __restrict__ list, const int* __restrict__ count, int ring_rows) {
+          const int* __restrict__ list, const int* __restrict__ count, int ring_rows, int band) {
     // blockIdx.z = plane * nslots + stream slot (two planes in one launch when plane1 != nullptr)
     const int which = blockIdx.z >= nslots ? 1 : 0;
     int slot = blockIdx.z - which * nslots;
@@ -248,7 +249,7 @@ k_cross_v(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plan
     const int k = which ? k1 : k0, C = which ? C1 : C0;
     const int lane = threadIdx.x;
     const int x = blockIdx.x * 32 + lane;              // packed column; p2 is a multiple of 32
-    const int yb0 = blockIdx.y * CV_BAND, yb1 = min(yb0 + CV_BAND, d.bv_h);
+    const int yb0 = blockIdx.y * band, yb1 = min(yb0 + band, d.bv_h);      // band: a multiple of 32
     const uint32_t* __restrict__ P = plane_all + (size_t)s * plane_stride + x;
     uint32_t* bits = bits_all + (size_t)s * bits_stride;
     const bool hi_ok = x + d.p2 < d.bv_w;
@@ -698,12 +699,13 @@ static int launch_cross_v(lt_handle* h, const uint32_t* plane, uint32_t* bits, i
         if (rc) return rc;
         return launch_cross_v(h, plane1, bits, k1, C1, n, list, count, st, pad_rows_zero);
     }
-    dim3 gv(d.p2 / 32, lt_div_up(d.bv_h, CV_BAND), plane1 ? 2 * n : n);
+    const int band = n >= 16 ? CV_BAND : CV_BAND_FEW;               // few streams: shorter sequential walks, more warps
+    dim3 gv(d.p2 / 32, lt_div_up(d.bv_h, band), plane1 ? 2 * n : n);
     const int kmax = (plane1 && k1 > k) ? k1 : k;
     const int ring_rows = crossv_ring_rows(kmax);
     const size_t ring_bytes = (size_t)(ring_rows + CV_CHUNK) * 32 * sizeof(uint32_t);      // + the mirror slots
 #define LT_CROSS_V(PK, RP) do { int rc_ = lt_ensure_smem((const void*)k_cross_v<PK, RP>, ring_bytes); if (rc_) return rc_; \
-        k_cross_v<PK, RP><<<gv, 32, ring_bytes, st>>>(plane, plane1, bits, d, k, C, k1, C1, n, ppitch, pstride, h->stream_mask, list, count, ring_rows); } while (0)
+        k_cross_v<PK, RP><<<gv, 32, ring_bytes, st>>>(plane, plane1, bits, d, k, C, k1, C1, n, ppitch, pstride, h->stream_mask, list, count, ring_rows, band); } while (0)
     if (packed && rowpad) LT_CROSS_V(true, true);
     else if (packed) LT_CROSS_V(true, false);
     else if (rowpad) LT_CROSS_V(false, true);
