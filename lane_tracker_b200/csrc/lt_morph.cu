@@ -30,6 +30,11 @@
 #include <algorithm>
 #include <functional>
 #include <vector>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <cstring>
+#include <cuda.h>                    // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
 #include "lt_common.cuh"
 #include "lt_ellipse.cuh"
 
@@ -67,6 +72,26 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+// ---- TMA (cp.async.bulk.tensor) + mbarrier: the alternative row-block staging of the producers (LT_MORPH_TMA=1)
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"(x), "r"(y),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 template <bool IS_MAX> __device__ __forceinline__ uint32_t op2(uint32_t a, uint32_t b) { return IS_MAX ? __vmaxu2(a, b) : __vminu2(a, b); }
 template <bool IS_MAX> __device__ __forceinline__ uint32_t op3(uint32_t a, uint32_t b, uint32_t c) {
     return IS_MAX ? __vimax3_u16x2(a, b, c) : __vimin3_u16x2(a, b, c);
@@ -85,7 +110,9 @@ template <int K> struct Geo {
     static constexpr int TEP = TE + 4;                 // raw row pitch: slack read by the last T4 chunk
     static constexpr int PRIV = RP * TEA + 2 * RB * TEP;   // producer-private words: T4[RP][TEA], RAW[2][RB][TEP]
     static constexpr int OGW = 2 * RB * TW;            // words of the two original-row buffers of the top-hat epilogue
-    static constexpr size_t smem(bool tophat) { return (size_t)(2 * TBUF + PRIV + (tophat ? OGW : 0)) * sizeof(uint32_t); }
+    static constexpr size_t smem(bool tophat) { return (size_t)(2 * TBUF + PRIV + (tophat ? OGW : 0)) * sizeof(uint32_t) + 32; }   // + four mbarriers (TMA staging)
+    static_assert((2 * TBUF + RP * TEA) % 32 == 0 && (RB * TEP) % 32 == 0 && TE <= 256, "the raw row buffers must be 128-byte aligned for the TMA variant");
+    static_assert((2 * TBUF + PRIV) % 32 == 0 && (RB * TW) % 32 == 0, "so must the original-row buffers");
     static_assert(HA >= R && HA <= LT_HALO_X && R + RB <= LT_HALO_Y && TE % 4 == 0, "staging must be 16-byte granular and inside the plane padding");
 };
 
@@ -133,9 +160,9 @@ struct MorphArgs {
     const int* list; const int* count;
 };
 
-template <int K, bool IS_MAX, bool TOPHAT, int MINB>
+template <int K, bool IS_MAX, bool TOPHAT, int MINB, bool TMA>
 __global__ void __launch_bounds__(NTHREADS, MINB)
-k_morph(MorphArgs a, LtDims d) {
+k_morph(MorphArgs a, LtDims d, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap omap) {
     using G = Geo<K>;
     using E = Ellipse<K>;
     constexpr int R = G::R, HA = G::HA, TEA = G::TEA;
@@ -151,11 +178,12 @@ k_morph(MorphArgs a, LtDims d) {
     uint32_t* dst = a.dst + (size_t)s * a.stride;
     const int pitch = d.pp;
 
-    extern __shared__ uint32_t smem[];
+    extern __shared__ __align__(128) uint32_t smem[];
     uint32_t* const TB = smem;                          // [2 buffers][NCT tables][RP pairs][TEA]
     uint32_t* const T4 = smem + 2 * G::TBUF;            // [RP][TEA]            producer private
     uint32_t* const RAW = T4 + RP * TEA;                // [2 buffers][RB][TEP] producer private
     uint32_t* const OG = RAW + 2 * RB * G::TEP;         // [2 buffers][RB][TW]  original rows of the top-hat epilogue
+    uint64_t* const mbar = reinterpret_cast<uint64_t*>(smem + 2 * G::TBUF + G::PRIV + (TOPHAT ? G::OGW : 0));   // [4], TMA variant: raw rows, original rows
 
     const int x0 = tile * TW;
     const int yb0 = band * a.band_rows;
@@ -206,16 +234,51 @@ k_morph(MorphArgs a, LtDims d) {
             oy += RB;
             cp_async_commit();
         };
-        stage(0);
+        // TMA variant: ONE producer thread requests the whole 8-row block (box TE x RB of the plane's tensor map, rows
+        // dense in shared memory) and every producer waits on the buffer's mbarrier instead of its own cp.async groups
+        constexpr int RPITCH = TMA ? G::TE : TEP;        // row pitch of a raw buffer
+        constexpr unsigned BLOCK_BYTES = RB * G::TE * sizeof(uint32_t);
+        const int tx = LT_HALO_X + x0 - HA;              // box origin in the padded plane: column ...
+        int ty = s * (d.bv_h + 2 * LT_HALO_Y) + LT_HALO_Y + r_begin;     // ... and row (advances RB per block)
+        auto stage_tma = [&](int buf) {
+            if (pt == 0) {
+                fence_proxy_async();                     // the generic-proxy reads of this buffer are ordered before the bulk copy
+                mbar_expect_tx(&mbar[buf], BLOCK_BYTES);
+                tma_load_2d(RAW + buf * RB * TEP, &tmap, tx, ty, &mbar[buf]);
+            }
+            ty += RB;
+        };
+        // ... and the original rows of the top-hat epilogue (box TW x RB of the original plane's map; rows outside the
+        // plane are pad rows of the layout and are never emitted)
+        const int ox = LT_HALO_X + x0;
+        int oyt = s * (d.bv_h + 2 * LT_HALO_Y) + LT_HALO_Y + r_begin - R;
+        auto stage_orig_tma = [&](int buf) {
+            if (pt == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(&mbar[2 + buf], (unsigned)(RB * TW * sizeof(uint32_t)));
+                tma_load_2d(OG + buf * RB * TW, &omap, ox, oyt, &mbar[2 + buf]);
+            }
+            oyt += RB;
+        };
+        if (TMA) {
+            if (pt == 0) {
+                mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_init(&mbar[2], 1); mbar_init(&mbar[3], 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            bar_sync(BAR_PROD, NPROD);
+            stage_tma(0);
+        } else {
+            stage(0);
+        }
         for (int blk = 0; blk < nblk; ++blk) {
             const int b = blk & 1;
-            cp_async_wait_all();
+            if (TMA) mbar_wait(&mbar[b], (unsigned)(blk >> 1) & 1u); else cp_async_wait_all();
             bar_sync(BAR_PROD, NPROD);                   // rows of this block landed; everybody is done with T4 and RAW[b ^ 1]
-            if (blk + 1 < nblk) stage(b ^ 1);            // next block's rows: in flight during the whole build
+            if (blk + 1 < nblk) { if (TMA) stage_tma(b ^ 1); else stage(b ^ 1); }     // next block's rows: in flight during the whole build
             if (blk >= 2) bar_sync(BAR_EMPTY + b, NTHREADS);     // the consumers have left table buffer b (and OG[b])
-            if (TOPHAT) stage_orig(b);                   // lands during the build (waited for before "full" is signalled)
+            if (TOPHAT) { if (TMA) stage_orig_tma(b); else stage_orig(b); }      // lands during the build (waited for before "full" is signalled)
             uint32_t* const Tb = TB + b * G::TBUF;
-            const uint32_t* const Rw = RAW + b * RB * TEP;
+            const uint32_t* const Rw = RAW + b * RB * TEP;     // (rows RPITCH apart)
             // ---- T1 (the rows themselves) and T4, four consecutive columns per task
             constexpr int NTASK = RP * G::CH, NIT = (NTASK + NPROD - 1) / NPROD;
 #pragma unroll UNROLL4
@@ -223,8 +286,8 @@ k_morph(MorphArgs a, LtDims d) {
                 const int q = pt + it * NPROD;
                 if (q >= NTASK) break;
                 const int pr = q / G::CH, c = (q - pr * G::CH) * 4;
-                const uint4* ra = reinterpret_cast<const uint4*>(Rw + (2 * pr) * TEP + c);
-                const uint4* rb = reinterpret_cast<const uint4*>(Rw + (2 * pr + 1) * TEP + c);
+                const uint4* ra = reinterpret_cast<const uint4*>(Rw + (2 * pr) * RPITCH + c);
+                const uint4* rb = reinterpret_cast<const uint4*>(Rw + (2 * pr + 1) * RPITCH + c);
                 const uint4 a0 = ra[0], a1 = ra[1], b0 = rb[0], b1 = rb[1];
                 // raw lanes are plain values (or the 16-bit pad): their low bytes are the table bytes
                 uint4 t1;
@@ -295,7 +358,7 @@ k_morph(MorphArgs a, LtDims d) {
                     *reinterpret_cast<uint4*>(Tb + 3 * RP * TEA + pr * TEA + c) = make_uint4(m(u.x, v.x), m(u.y, v.y), m(u.z, v.z), m(u.w, v.w));
                 }
             }
-            if (TOPHAT) cp_async_wait_all();             // OG[b] (and the long-issued next rows) have landed
+            if (TOPHAT) { if (TMA) mbar_wait(&mbar[2 + b], (unsigned)(blk >> 1) & 1u); else cp_async_wait_all(); }   // OG[b] has landed
             bar_arrive(BAR_FULL + b, NTHREADS);
         }
         return;
@@ -356,12 +419,48 @@ k_morph(MorphArgs a, LtDims d) {
     }
 }
 
+// Tensor map of one padded plane allocation for the TMA variant: 2-D uint32 [rows][pp], box = TE x RB.  Cached per
+// (device, allocation, geometry); the encoder comes from the driver through cudaGetDriverEntryPoint (no -lcuda).
+static int plane_tensor_map(lt_handle* h, const uint32_t* plane, int box_w, CUtensorMap* out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    static std::mutex mu;
+    static std::map<std::tuple<int, const void*, int, long long, int>, CUtensorMap> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            lt_set_error("cuTensorMapEncodeTiled is not available");
+            return -2;
+        }
+        encode = (EncodeFn)fn;
+    }
+    const LtDims& d = h->d;
+    const uint32_t* base = plane - ((size_t)LT_HALO_Y * d.pp + LT_HALO_X);          // start of the allocation
+    const long long rows = (long long)h->S * (d.bv_h + 2 * LT_HALO_Y) + 1;
+    const auto key = std::make_tuple(h->cfg.device, (const void*)base, d.pp, rows, box_w);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        CUtensorMap m;
+        const cuuint64_t dims[2] = {(cuuint64_t)d.pp, (cuuint64_t)rows};
+        const cuuint64_t strides[1] = {(cuuint64_t)d.pp * sizeof(uint32_t)};
+        const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)RB}, estr[2] = {1, 1};
+        CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { lt_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return -2; }
+        it = cache.emplace(key, m).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
 template <int K, bool IS_MAX, bool TOPHAT, int MINB>
 int launch_occ(lt_handle* h, const uint32_t* src, uint32_t* dst, const uint32_t* orig, int bands, int n, const int* list,
                const int* count, cudaStream_t st) {
     const LtDims& d = h->d;
-    int rc = lt_ensure_smem((const void*)k_morph<K, IS_MAX, TOPHAT, MINB>, Geo<K>::smem(TOPHAT));
-    if (rc) return rc;
     MorphArgs a;
     a.src = src; a.dst = dst; a.orig = orig;
     a.band_rows = (lt_div_up(d.bv_h, bands) + 1) & ~1;          // even: output rows come out in aligned pairs
@@ -371,7 +470,23 @@ int launch_occ(lt_handle* h, const uint32_t* src, uint32_t* dst, const uint32_t*
     a.sms = h->sm_count > 0 ? h->sm_count : 148;
     static const bool parity = [] { const char* e = getenv("LT_MORPH_PARITY"); return e && e[0] == '1'; }();
     if (!parity) a.sms = 1 << 30;
-    k_morph<K, IS_MAX, TOPHAT, MINB><<<n * a.tiles * a.bands, NTHREADS, Geo<K>::smem(TOPHAT), st>>>(a, d);
+    // The producers stage their row blocks with cp.async.bulk.tensor + mbarrier (one request per block by one thread);
+    // LT_MORPH_TMA=0 selects the 16-byte cp.async staging it replaced (measured 3 % slower: the producers are the
+    // critical path and every instruction they do not issue counts)
+    static const bool tma = [] { const char* e = getenv("LT_MORPH_TMA"); return !(e && e[0] == '0'); }();      // default on
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    int rc;
+    CUtensorMap om = tm;
+    if (tma) {
+        if ((rc = plane_tensor_map(h, src, Geo<K>::TE, &tm))) return rc;
+        if (TOPHAT && (rc = plane_tensor_map(h, orig, TW, &om))) return rc;
+        if ((rc = lt_ensure_smem((const void*)k_morph<K, IS_MAX, TOPHAT, MINB, true>, Geo<K>::smem(TOPHAT)))) return rc;
+        k_morph<K, IS_MAX, TOPHAT, MINB, true><<<n * a.tiles * a.bands, NTHREADS, Geo<K>::smem(TOPHAT), st>>>(a, d, tm, om);
+    } else {
+        if ((rc = lt_ensure_smem((const void*)k_morph<K, IS_MAX, TOPHAT, MINB, false>, Geo<K>::smem(TOPHAT)))) return rc;
+        k_morph<K, IS_MAX, TOPHAT, MINB, false><<<n * a.tiles * a.bands, NTHREADS, Geo<K>::smem(TOPHAT), st>>>(a, d, tm, om);
+    }
     LT_LAUNCH_CHECK();
     return 0;
 }
