@@ -5,7 +5,10 @@
 // of the bit mask, the layout converters and the launcher of one filter attempt.
 #include <cstdlib>
 #include <cstdio>
+#include <cuda.h>                    // CUtensorMap (types only)
 #include "lt_common.cuh"
+
+int lt_plane_tensor_map(lt_handle* h, const uint32_t* plane, int box_w, CUtensorMap* out);      // lt_morph.cu
 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
@@ -352,6 +355,133 @@ k_cross_v(const uint32_t* __restrict__ plane0, const uint32_t* __restrict__ plan
         }
     }
     cp_async_wait_all();
+}
+
+// ---- the same walk with the ring filled by TMA (row-padded planes only: the pad rows are the filter's border) ------
+// One lane requests a whole chunk -- a box of 32 columns x 8 rows of the plane's tensor map lands as eight consecutive
+// ring slots -- and the warp waits on the chunk's mbarrier: the eight cp.async per chunk, their address arithmetic and
+// the group bookkeeping leave the instruction stream (the walk is issue-bound).
+__device__ __forceinline__ void v_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void v_mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void v_mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void v_tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"(x), "r"(y),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+constexpr int CV_NST = CV_PF + 1;    // chunk mbarriers (chunks in flight)
+static_assert(CV_CHUNK == 8, "lt_plane_tensor_map builds boxes of 8 rows");
+
+static int crossv_tma_ring_rows(int k) {              // fill boxes + the chunks in flight, whole chunks
+    return CV_CHUNK * ((2 * k + 1 + CV_CHUNK - 1) / CV_CHUNK + CV_PF + 1);
+}
+
+__global__ void __launch_bounds__(32)
+k_cross_v_tma(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1, uint32_t* __restrict__ bits_all,
+              LtDims d, int k0, int C0, int k1, int C1, int nslots, size_t bits_stride, const int* __restrict__ list,
+              const int* __restrict__ count, int ring_rows, int band) {
+    const int which = blockIdx.z >= nslots ? 1 : 0;
+    int slot = blockIdx.z - which * nslots;
+    if (count != nullptr && slot >= *count) return;
+    const int s = list ? list[slot] : slot;
+    const CUtensorMap* const tm = which ? &tmap1 : &tmap0;
+    const int k = which ? k1 : k0, C = which ? C1 : C0;
+    const int lane = threadIdx.x;
+    const int x = blockIdx.x * 32 + lane;
+    const int yb0 = blockIdx.y * band, yb1 = min(yb0 + band, d.bv_h);
+    uint32_t* bits = bits_all + (size_t)s * bits_stride;
+    const bool hi_ok = x + d.p2 < d.bv_w;
+    extern __shared__ __align__(128) uint32_t ring[];  // [ring_rows + CV_CHUNK][32], then the mbarriers
+    const int R = ring_rows;
+    uint32_t* const rl = ring + lane;
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(ring + (R + CV_CHUNK) * 32);     // [CV_NST] chunks, [CV_NST] = fill
+    const int tx = LT_HALO_X + blockIdx.x * 32;                                        // box origin: column ...
+    const int ty0 = s * (d.bv_h + 2 * LT_HALO_Y) + LT_HALO_Y;                          // ... and row of image row 0
+    constexpr unsigned BOX = CV_CHUNK * 32 * sizeof(uint32_t);
+    const int nbox = (2 * k + 1 + CV_CHUNK - 1) / CV_CHUNK;                            // fill boxes: they end at row yb0 + k
+    const int r_last = yb1 + k + CV_CHUNK;                                             // rows >= r_last are never read
+    if (lane == 0) {
+        for (int i = 0; i <= CV_NST; ++i) v_mbar_init(&bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        v_mbar_expect_tx(&bar[CV_NST], BOX * nbox);
+        for (int j = 0; j < nbox; ++j)
+            v_tma_load_2d(ring + (R - CV_CHUNK * (nbox - j)) * 32, tm, tx, ty0 + yb0 + k + 1 - CV_CHUNK * (nbox - j), &bar[CV_NST]);
+    }
+    __syncwarp();
+    // chunk c adds rows yb0 + k + 1 + 8c .. + 7 to slots (8c) mod R (and their mirror when that is slot 0)
+    auto fetch_chunk = [&](int c) {
+        const int r0 = yb0 + k + 1 + CV_CHUNK * c;
+        if (r0 >= r_last) return;
+        const int slot_row = (CV_CHUNK * c) % R;
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            uint64_t* b = &bar[c % CV_NST];
+            v_mbar_expect_tx(b, slot_row == 0 ? 2 * BOX : BOX);
+            v_tma_load_2d(ring + slot_row * 32, tm, tx, ty0 + r0, b);
+            if (slot_row == 0) v_tma_load_2d(ring + R * 32, tm, tx, ty0 + r0, b);
+        }
+    };
+#pragma unroll
+    for (int c = 0; c < CV_PF; ++c) fetch_chunk(c);
+    const int Ck = C * k;
+    const uint32_t kk = (uint32_t)k, bias = (uint32_t)(Ck + 1) * 0x00010001u;
+    uint32_t U = bias, D = bias, p = 0;
+    int r_new = 0, r_cur = R - k, r_old = R - 2 * k - 1;
+    uint32_t wl = 0, wh = 0;
+    int c = 0;
+    for (int yc = yb0; yc < yb1; yc += CV_CHUNK, ++c) {
+        __syncwarp();                                  // every lane has finished reading the slots the next copy overwrites
+        fetch_chunk(c + CV_PF);
+        if (yc == yb0) {
+            v_mbar_wait(&bar[CV_NST], 0u);
+            const uint32_t* f = rl + (R - 2 * k - 1) * 32;
+            for (int i = 0; i < k; ++i) { U += f[i * 32]; D += f[(k + 1 + i) * 32]; }
+            p = f[k * 32];
+        }
+        v_mbar_wait(&bar[c % CV_NST], (unsigned)(c / CV_NST) & 1u);
+        const uint32_t* const pn = rl + r_new * 32;
+        const uint32_t* const pcur = rl + r_cur * 32;
+        const uint32_t* const pold = rl + r_old * 32;
+#pragma unroll
+        for (int j = 0; j < CV_CHUNK; ++j) {
+            const uint32_t pc = pcur[j * 32], pu = pold[j * 32], pd = pn[j * 32];
+            const uint32_t T = p * kk + 0x80008000u;
+            const uint32_t ok = (T - U) & (T - D);
+            wl = __funnelshift_l(ok * 0x10000u, wl, 1);
+            wh = __funnelshift_l(ok, wh, 1);
+            U = U + p - pu;
+            D = D + pd - pc;
+            p = pc;
+        }
+        r_new += CV_CHUNK; if (r_new >= R) r_new -= R;
+        r_cur += CV_CHUNK; if (r_cur >= R) r_cur -= R;
+        r_old += CV_CHUNK; if (r_old >= R) r_old -= R;
+        const int ynext = yc + CV_CHUNK;
+        if ((ynext & 31) == 0 || ynext >= yb1) {
+            const int ybase = (ynext - 1) & ~31;
+            const int sh = 32 - (ynext - ybase);
+            uint32_t ml = __brev(wl << sh), mh = hi_ok ? __brev(wh << sh) : 0u;
+            ml = warp_transpose32(ml, lane);
+            mh = warp_transpose32(mh, lane);
+            const int y = ybase + lane;
+            if (y < yb1) {
+                uint32_t* brow = bits + (size_t)y * d.mwords;
+                if (ml) atomicOr(&brow[blockIdx.x], ml);
+                if (mh) atomicOr(&brow[blockIdx.x + (d.p2 >> 5)], mh);
+            }
+            wl = wh = 0;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -706,7 +836,17 @@ static int launch_cross_v(lt_handle* h, const uint32_t* plane, uint32_t* bits, i
     const size_t ring_bytes = (size_t)(ring_rows + CV_CHUNK) * 32 * sizeof(uint32_t);      // + the mirror slots
 #define LT_CROSS_V(PK, RP) do { int rc_ = lt_ensure_smem((const void*)k_cross_v<PK, RP>, ring_bytes); if (rc_) return rc_; \
         k_cross_v<PK, RP><<<gv, 32, ring_bytes, st>>>(plane, plane1, bits, d, k, C, k1, C1, n, ppitch, pstride, h->stream_mask, list, count, ring_rows, band); } while (0)
-    if (packed && rowpad) LT_CROSS_V(true, true);
+    static const bool v_tma = [] { const char* e = getenv("LT_CROSSV_TMA"); return !(e && e[0] == '0'); }();      // default on
+    if (packed && rowpad && v_tma) {
+        CUtensorMap tm0, tm1;
+        int rc_ = lt_plane_tensor_map(h, plane, 32, &tm0);
+        if (!rc_) { if (plane1) rc_ = lt_plane_tensor_map(h, plane1, 32, &tm1); else tm1 = tm0; }
+        if (rc_) return rc_;
+        const int rr = crossv_tma_ring_rows(kmax);
+        const size_t bytes = (size_t)(rr + CV_CHUNK) * 32 * sizeof(uint32_t) + (CV_NST + 1) * sizeof(uint64_t);
+        if ((rc_ = lt_ensure_smem((const void*)k_cross_v_tma, bytes))) return rc_;
+        k_cross_v_tma<<<gv, 32, bytes, st>>>(tm0, tm1, bits, d, k, C, k1, C1, n, h->stream_mask, list, count, rr, band);
+    } else if (packed && rowpad) LT_CROSS_V(true, true);
     else if (packed) LT_CROSS_V(true, false);
     else if (rowpad) LT_CROSS_V(false, true);
     else LT_CROSS_V(false, false);

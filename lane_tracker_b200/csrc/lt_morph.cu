@@ -511,6 +511,9 @@ int launch_one(lt_handle* h, const uint32_t* src, uint32_t* dst, const uint32_t*
 
 }  // namespace
 
+// (also used by the vertical threshold, lt_filter.cu: box = box_w columns x 8 rows of a padded plane)
+int lt_plane_tensor_map(lt_handle* h, const uint32_t* plane, int box_w, CUtensorMap* out) { return plane_tensor_map(h, plane, box_w, out); }
+
 // Band counts of the two jobs: simulate list scheduling of both grids (55x55 CTAs first, they are the long ones) on
 // the CTA slots of the device.  Per-row costs: measured relative walk costs of the two structuring elements.
 static void choose_bands(lt_handle* h, int n, int tiles, int H, int* b55, int* b29) {
