@@ -564,7 +564,7 @@ class BatchedLaneTracker:
 
 class GraphedProcess:
     """``process_async`` of a fixed batch shape captured once into a CUDA graph and replayed per frame: the chain
-    of ~20 small launches costs one launch.  Pays off for few streams (one stream: 0.26 -> 0.22 ms per frame);
+    of ~20 small launches costs one launch.  Pays off for few streams (one stream: 0.25 -> 0.21 ms per frame);
     ``lt_process`` only enqueues kernels (and forks/joins its side stream with events), so it is capturable.
 
         g = GraphedProcess(tracker, n_streams)          # static device buffers g.frames / g.out
