@@ -188,9 +188,10 @@ k_cross_h_wide(const uint32_t* __restrict__ plane_all, uint32_t* __restrict__ bi
     }
 }
 
-// Vertical half: one thread per packed column walks a band of rows with running sums U, D (packed u16x2);
-// the plane rows each step needs are fetched CV_CHUNK steps ahead so that the loads stay in flight (32-bit row offsets
-// from one base pointer: the address arithmetic is IMAD / IMAD.WIDE on the FMA pipe, the walk itself is ALU-pipe bound).
+// Vertical half: one thread per packed column walks a band of rows with running sums U, D (packed u16x2).  The rows a
+// step needs (y + k + 1 to add, y + 1 as the next centre, y - k to drop) come from a per-warp ring of plane rows in
+// shared memory that is filled CV_PF chunks of CV_CHUNK rows ahead of the walk -- by TMA for row-padded planes
+// (k_cross_v_tma, the hot path), by 4-byte cp.async otherwise (k_cross_v).
 // PACKED: k*255 + C*k + 1 < 2^15, the compare is done on both lanes at once with a guard bit.
 // ROWPAD: k + 2 * CV_CHUNK <= LT_HALO_Y, every row the walk touches or prefetches exists in the padded plane (pad rows are zero, which
 //         is the filter's border), so loads carry no bounds logic.
