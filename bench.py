@@ -32,7 +32,7 @@ if ROOT not in sys.path:
 METRIC = "frames/sec at 1280x720 (batched streams)"
 STREAMS_PER_GPU = 64
 FRAME_POOL = 4                       # pre-rendered frames per stream, cycled
-BATCHES_PER_STEP = 10                # a driver step = 10 batches of STREAMS_PER_GPU frames
+BATCHES_PER_STEP = 16                # a driver step = 16 batches of STREAMS_PER_GPU frames (>= 0.3 s timed at the default 20 steps)
 FRAME_BYTES = 1280 * 720 * 3
 ALGO_BYTES_PER_FRAME = 2 * FRAME_BYTES + 128          # frame in + annotated frame out + results
 PLANE_PIXELS = 1080 * 1100
