@@ -491,22 +491,12 @@ int launch_occ(lt_handle* h, const uint32_t* src, uint32_t* dst, const uint32_t*
     return 0;
 }
 
-// resident CTAs per SM the kernel is compiled for (register budget): tuning knob LT_MORPH_OCC="o55,o29"
+// resident CTAs per SM each kernel is compiled for (register budget): two for 55x55 (106 registers), three for 29x29
+// (76 registers); three / four were measured slower (spills)
 template <int K, bool IS_MAX, bool TOPHAT>
 int launch_one(lt_handle* h, const uint32_t* src, uint32_t* dst, const uint32_t* orig, int bands, int n, const int* list,
                const int* count, cudaStream_t st) {
-    static const int occ = [] {
-        int o55 = 2, o29 = 3;
-        if (const char* e = getenv("LT_MORPH_OCC")) sscanf(e, "%d,%d", &o55, &o29);
-        return K == 55 ? o55 : o29;
-    }();
-    if (K == 55) {
-        if (occ == 2) return launch_occ<K, IS_MAX, TOPHAT, 2>(h, src, dst, orig, bands, n, list, count, st);
-        return launch_occ<K, IS_MAX, TOPHAT, 3>(h, src, dst, orig, bands, n, list, count, st);
-    }
-    if (occ == 2) return launch_occ<K, IS_MAX, TOPHAT, 2>(h, src, dst, orig, bands, n, list, count, st);
-    if (occ == 4) return launch_occ<K, IS_MAX, TOPHAT, 4>(h, src, dst, orig, bands, n, list, count, st);
-    return launch_occ<K, IS_MAX, TOPHAT, 3>(h, src, dst, orig, bands, n, list, count, st);
+    return launch_occ<K, IS_MAX, TOPHAT, K == 55 ? 2 : 3>(h, src, dst, orig, bands, n, list, count, st);
 }
 
 }  // namespace

@@ -34,7 +34,7 @@ def one():
     e1.record()
     torch.cuda.synchronize()
     st, calls = trk.profile_read()
-    print(json.dumps({"bands": os.environ.get("LT_MORPH_BANDS", "auto"), "occ": os.environ.get("LT_MORPH_OCC", "default") + " " + os.environ.get("LT_LIBRARY_VARIANT", "-"),
+    print(json.dumps({"bands": os.environ.get("LT_MORPH_BANDS", "auto"), "variant": os.environ.get("LT_LIBRARY_VARIANT", "-"),
                       "chosen": trk.morph_bands(), "ms_per_step": e0.elapsed_time(e1) / n,
                       "stages": {k: round(v / calls, 4) for k, v in st.items() if v > 0}}), flush=True)
 
@@ -47,9 +47,6 @@ def main():
         impl, bands = s.split(":")[:2]
         env = dict(os.environ)
         env.pop("LT_MORPH_BANDS", None)
-        env.pop("LT_MORPH_OCC", None)
-        if len(s.split(":")) > 2:
-            env["LT_MORPH_OCC"] = s.split(":")[2]
         env.pop("LT_MORPH_PARITY", None)
         env.pop("LT_LIBRARY_VARIANT", None)
         if len(s.split(":")) > 3 and s.split(":")[3]:
